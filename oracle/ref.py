@@ -50,12 +50,14 @@ def _ip(a):
 class Checker:
     """One of the two CPU implementations behind a common Python interface."""
 
-    def __init__(self, kind):
-        assert kind in ("reference", "port")
+    def __init__(self, kind, path=None, prefix=None):
         self.kind = kind
-        name = "libtess_ref.so" if kind == "reference" else "libtess_oracle.so"
-        self.prefix = "ref_" if kind == "reference" else "orc_"
-        path = os.path.join(HERE, "_ref", name)
+        if path is None:
+            assert kind in ("reference", "port")
+            name = "libtess_ref.so" if kind == "reference" else "libtess_oracle.so"
+            prefix = "ref_" if kind == "reference" else "orc_"
+            path = os.path.join(HERE, "_ref", name)
+        self.prefix = prefix
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} missing: run `make -C oracle` (or __graft_entry__.build())")
         self.lib = C.CDLL(path)
@@ -115,7 +117,7 @@ class Checker:
             for d in range(3):
                 arr[i].bounds_min[d] = float(b["bounds_min"][d])
                 arr[i].bounds_max[d] = float(b["bounds_max"][d])
-            dens = np.zeros(cap if nb == 1 else min(cap, self._block_cap(b, blocks, gs)), dtype=np.float32)
+            dens = np.zeros(cap if nb * cap <= (1 << 27) else min(cap, self._block_cap(b, blocks, gs)), dtype=np.float32)
             keep.append(dens)
             arr[i].density = _fp(dens)
             arr[i].density_capacity = len(dens)

@@ -1,0 +1,1021 @@
+// api.cu -- host side of the C ABI declared in include/tess_b200.h.
+//
+// The grid bookkeeping the reference does on the host (DataBounds, GridStepParams,
+// BlockGridParams; src/dense.cpp:1221-1275, 1712-1767, 575-648) stays on the host here too --
+// it is a few dozen flops per block -- in the reference's fp32 operation order (this file is
+// compiled with -fmad=false / -ffp-contract=off).  Everything per tet, per cell and per grid
+// point runs in the kernels of kernels.cuh.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/tess_b200.h"
+#include "kernels.cuh"
+#include "host_geom.hpp"
+#ifdef TESSB200_WITH_NCCL
+#include <nccl.h>
+#include <dlfcn.h>
+// NCCL is bound at run time (dlopen) instead of at link time: a process that also imports torch
+// must end up with ONE libnccl.so.2 (torch bundles its own, newer than the system's), and the
+// loader keys on the SONAME, so whichever copy is already mapped is the one used here.
+namespace ncclw
+{
+struct Api
+{
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static Api g;
+static const char *load()
+{
+  if (g.h) return nullptr;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return dlerror();
+#define TB_SYM(field, name)                                \
+  *(void **)(&g.field) = dlsym(h, name);                   \
+  if (!g.field) return "libnccl.so.2 lacks " name;
+  TB_SYM(GetUniqueId, "ncclGetUniqueId")
+  TB_SYM(CommInitRank, "ncclCommInitRank")
+  TB_SYM(CommDestroy, "ncclCommDestroy")
+  TB_SYM(AllGather, "ncclAllGather")
+  TB_SYM(Send, "ncclSend")
+  TB_SYM(Recv, "ncclRecv")
+  TB_SYM(GroupStart, "ncclGroupStart")
+  TB_SYM(GroupEnd, "ncclGroupEnd")
+  TB_SYM(GetErrorString, "ncclGetErrorString")
+#undef TB_SYM
+  g.h = h;
+  return nullptr;
+}
+} // namespace ncclw
+#endif
+
+using namespace tb;
+
+// ---- error plumbing ----------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(expr)                                                                                             \
+  do {                                                                                                       \
+    cudaError_t e_ = (expr);                                                                                 \
+    if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? TESSB200_ENOMEM : TESSB200_ECUDA, \
+                                       "%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+
+// grow-only device buffer
+struct Buf
+{
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) {
+      p = nullptr;
+      cudaGetLastError();
+      return fail(TESSB200_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = want;
+    return 0;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct BlockRes
+{
+  int gid = 0;
+  int num_orig = 0, num_particles = 0, num_tets = 0;
+  float bmin[3], bmax[3];
+  bool have_v2t = false;
+  Buf particles, tets, v2t, cc;
+  // geometry of the last run
+  int mn[3], num[3];
+  long long npts = 0, nrows = 0, row_base = 0, out_off = 0;
+  uint32_t cell_base = 0;
+};
+
+struct LayoutBlock
+{
+  int gid;
+  float bmin[3], bmax[3];
+  int owner;
+};
+
+struct tessb200_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<BlockRes *> blocks;   // uploaded blocks of this rank, ascending gid
+  std::vector<LayoutBlock> layout;  // every block of the decomposition (multi-GPU), ascending gid
+  int nranks = 1, rank = 0;
+#ifdef TESSB200_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
+  Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data;
+  Counters *h_cnt = nullptr;        // pinned
+  double *h_sum = nullptr;
+  float *h_max = nullptr;
+  cudaEvent_t ev[12];
+  bool ran = false;
+  tessb200_dense_params last_params;
+  long long out_floats = 0;
+  ~tessb200_ctx() {}
+};
+
+extern "C" const char *tessb200_last_error(void) { return g_err.c_str(); }
+extern "C" int tessb200_version(void) { return TESSB200_VERSION; }
+
+extern "C" int tessb200_create(tessb200_ctx **out, int device)
+{
+  if (!out) return fail(TESSB200_EINVAL, "tessb200_create: ctx is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(TESSB200_ECUDA, "no CUDA device available (%s); tess_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= n) return fail(TESSB200_EINVAL, "device %d out of range [0,%d)", device, n);
+  CU(cudaSetDevice(device));
+  tessb200_ctx *c = new tessb200_ctx;
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaMallocHost(&c->h_cnt, sizeof(Counters)));
+  CU(cudaMallocHost(&c->h_sum, sizeof(double) * 1024));
+  CU(cudaMallocHost(&c->h_max, sizeof(float) * 1024));
+  for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
+  CU(cudaFuncSetAttribute(k_cell_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_topo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_volumes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
+  *out = c;
+  return 0;
+}
+
+static void free_blocks(tessb200_ctx *c)
+{
+  for (BlockRes *b : c->blocks) {
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
+    delete b;
+  }
+  c->blocks.clear();
+}
+
+extern "C" void tessb200_destroy(tessb200_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_blocks(c);
+  Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
+                 &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
+                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data};
+  for (Buf *b : bufs) b->release();
+#ifdef TESSB200_WITH_NCCL
+  if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
+#endif
+  cudaFreeHost(c->h_cnt); cudaFreeHost(c->h_sum); cudaFreeHost(c->h_max);
+  for (auto &ev : c->ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+struct Geometry
+{
+  GridGeom g;
+  KeyLayout kl;
+  int key_bits;
+  std::vector<BlockBox> boxes;      // every block of the decomposition
+  std::vector<int> local_of;        // global block index -> index into ctx->blocks, or -1
+  std::vector<RowBlock> rblocks;    // this rank's blocks
+  unsigned long long row0 = 0, nrows = 0, total_rows = 0;
+  long long out_floats = 0;
+  int nx_max = 1;
+  unsigned long long total_cells = 0;
+};
+
+static int check_params(const tessb200_dense_params *p)
+{
+  if (!p) return fail(TESSB200_EINVAL, "params is NULL");
+  if (p->alg != TESSB200_DENSE_TESS && p->alg != TESSB200_DENSE_CIC) return fail(TESSB200_EINVAL, "unknown alg %d", p->alg);
+  for (int d = 0; d < 3; d++)
+    if (p->glo_num_idx[d] < 2 || p->glo_num_idx[d] > 32767)
+      return fail(TESSB200_ELIMIT, "glo_num_idx[%d] = %d outside [2, 32767]", d, p->glo_num_idx[d]);
+  if (p->num_given_bounds < 0 || p->num_given_bounds > 3) return fail(TESSB200_EINVAL, "num_given_bounds = %d", p->num_given_bounds);
+  if (p->project && !(p->proj_plane[0] == 0.0f && p->proj_plane[1] == 0.0f && p->proj_plane[2] != 0.0f))
+    return fail(TESSB200_EINVAL, "projection is supported along z only (the reference asserts the same, src/dense.cpp:1077)");
+  if (!(p->eps >= 0.0f)) return fail(TESSB200_EINVAL, "eps must be >= 0");
+  return 0;
+}
+
+// fills params outputs and every block's grid geometry; `all` = every block of the decomposition
+static int make_geometry(tessb200_ctx *c, tessb200_dense_params *p, Geometry *G)
+{
+  TRY(check_params(p));
+  std::vector<LayoutBlock> all;
+  if (!c->layout.empty()) all = c->layout;
+  else
+    for (BlockRes *b : c->blocks) {
+      LayoutBlock l;
+      l.gid = b->gid;
+      memcpy(l.bmin, b->bmin, 12); memcpy(l.bmax, b->bmax, 12);
+      l.owner = c->rank;
+      all.push_back(l);
+    }
+  if (all.empty()) return fail(TESSB200_ESTATE, "no blocks uploaded");
+  // DataBounds, src/dense.cpp:1221-1275 (min/max over every block's bounds)
+  for (size_t i = 0; i < all.size(); i++)
+    for (int d = 0; d < 3; d++) {
+      if (i == 0 || all[i].bmin[d] < p->data_mins[d]) p->data_mins[d] = all[i].bmin[d];
+      if (i == 0 || all[i].bmax[d] > p->data_maxs[d]) p->data_maxs[d] = all[i].bmax[d];
+    }
+  grid_step_params(p);
+  GridGeom &g = G->g;
+  for (int d = 0; d < 3; d++) {
+    g.gmin[d] = p->grid_phys_mins[d]; g.step[d] = p->grid_step_size[d];
+    g.dmin[d] = p->data_mins[d]; g.dmax[d] = p->data_maxs[d];
+    g.dext_eps[d] = (p->data_maxs[d] - p->data_mins[d]) * 2.0f * FLT_EPSILON;
+    g.gnum[d] = p->glo_num_idx[d];
+    if (!(g.step[d] > 0.0f)) return fail(TESSB200_EINVAL, "grid step %d is not positive (degenerate bounds)", d);
+  }
+  g.eps = p->eps; g.mass = p->mass; g.project = p->project ? 1 : 0; g.alg = p->alg;
+  g.div = p->project ? g.step[0] * g.step[1] : g.step[0] * g.step[1] * g.step[2]; // src/dense.cpp:90-91
+
+  G->boxes.resize(all.size());
+  G->local_of.assign(all.size(), -1);
+  long long row_base = 0;
+  unsigned long long cell_base = 0;
+  long long out_off = 0;
+  G->rblocks.clear();
+  bool seen_local = false, past_local = false;
+  for (size_t i = 0; i < all.size(); i++) {
+    BlockBox &bx = G->boxes[i];
+    block_grid_params(all[i].bmin, all[i].bmax, p, bx.b_lo, bx.b_num);
+    phys_box(all[i].bmin, all[i].bmax, p, bx.p_lo, bx.p_hi);
+    for (int d = 0; d < 3; d++)
+      if (bx.b_num[d] < 1) return fail(TESSB200_EINVAL, "block gid %d owns no grid points along axis %d", all[i].gid, d);
+    long long nrows = p->project ? bx.b_num[1] : (long long)bx.b_num[1] * bx.b_num[2];
+    bx.row_base = row_base;
+    if (all[i].owner == c->rank) {
+      if (past_local) return fail(TESSB200_EINVAL, "blocks owned by one rank must be contiguous in gid order");
+      int li = -1;
+      for (size_t k = 0; k < c->blocks.size(); k++)
+        if (c->blocks[k]->gid == all[i].gid) li = (int)k;
+      if (li < 0) return fail(TESSB200_ESTATE, "block gid %d is owned by this rank but was not uploaded", all[i].gid);
+      if (!seen_local) G->row0 = (unsigned long long)row_base;
+      seen_local = true;
+      G->local_of[i] = li;
+      BlockRes *b = c->blocks[li];
+      memcpy(b->mn, bx.b_lo, 12); memcpy(b->num, bx.b_num, 12);
+      b->nrows = nrows;
+      b->npts = nrows * bx.b_num[0];
+      b->row_base = row_base;
+      b->out_off = out_off;
+      b->cell_base = (uint32_t)cell_base;
+      RowBlock rb;
+      rb.row_base = row_base; rb.nrows = nrows; rb.out_off = out_off; rb.nx = bx.b_num[0]; rb.pad = 0;
+      G->rblocks.push_back(rb);
+      out_off += (b->npts + 3) & ~3LL;
+      G->nrows += (unsigned long long)nrows;
+      if (bx.b_num[0] > G->nx_max) G->nx_max = bx.b_num[0];
+      cell_base += (unsigned long long)b->num_orig;
+    } else if (seen_local) {
+      past_local = true;
+    }
+    row_base += nrows;
+  }
+  if (c->layout.empty()) {
+    // single rank: cell numbering over the uploaded blocks
+  } else {
+    // multi rank: cell numbers must be globally ordered by gid; use a fixed 2^26 window per rank
+    // (checked against the per-rank cell count) so that no exchange of counts is needed
+    if (cell_base > (1ull << 26)) return fail(TESSB200_ELIMIT, "more than 2^26 cells on one rank in a multi-GPU run");
+    for (BlockRes *b : c->blocks) b->cell_base += (uint32_t)c->rank << 26;
+    cell_base = (unsigned long long)c->nranks << 26;
+  }
+  G->total_rows = (unsigned long long)row_base;
+  G->out_floats = out_off;
+  G->total_cells = cell_base;
+  G->kl.cell_bits = ceil_log2(cell_base + 1);
+  G->kl.z_bits = p->project ? ceil_log2((unsigned long long)p->glo_num_idx[2] + 2) : 0;
+  G->key_bits = ceil_log2(G->total_rows + 1) + 1 + G->kl.cell_bits + G->kl.z_bits;
+  if (G->key_bits > 64) return fail(TESSB200_ELIMIT, "sort key needs %d bits (> 64): grid rows x cells too large", G->key_bits);
+  return 0;
+}
+
+// ---- upload ----------------------------------------------------------------------------------------
+extern "C" int tessb200_dense_upload(tessb200_ctx *c, int nblocks, const tessb200_block *blocks)
+{
+  if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
+  if (nblocks < 1 || !blocks) return fail(TESSB200_EINVAL, "need at least one block");
+  if (nblocks > 65535) return fail(TESSB200_ELIMIT, "more than 65535 blocks");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  // reuse device buffers of a previous upload where possible
+  std::vector<int> order(nblocks);
+  for (int i = 0; i < nblocks; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return blocks[a].gid < blocks[b].gid; });
+  for (int i = 1; i < nblocks; i++)
+    if (blocks[order[i]].gid == blocks[order[i - 1]].gid) return fail(TESSB200_EINVAL, "duplicate gid %d", blocks[order[i]].gid);
+  while ((int)c->blocks.size() > nblocks) {
+    BlockRes *b = c->blocks.back();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
+    delete b;
+    c->blocks.pop_back();
+  }
+  while ((int)c->blocks.size() < nblocks) c->blocks.push_back(new BlockRes);
+  for (int k = 0; k < nblocks; k++) {
+    const tessb200_block &hb = blocks[order[k]];
+    BlockRes *b = c->blocks[k];
+    if (hb.num_particles < 0 || hb.num_orig_particles < 0 || hb.num_orig_particles > hb.num_particles || hb.num_tets < 0)
+      return fail(TESSB200_EINVAL, "block gid %d: inconsistent counts", hb.gid);
+    if ((hb.num_particles && !hb.particles) || (hb.num_tets && !hb.tets)) return fail(TESSB200_EINVAL, "block gid %d: NULL input array", hb.gid);
+    b->gid = hb.gid;
+    b->num_orig = hb.num_orig_particles; b->num_particles = hb.num_particles; b->num_tets = hb.num_tets;
+    memcpy(b->bmin, hb.bounds_min, 12); memcpy(b->bmax, hb.bounds_max, 12);
+    for (int d = 0; d < 3; d++)
+      if (!(b->bmin[d] <= b->bmax[d])) return fail(TESSB200_EINVAL, "block gid %d: bounds_min > bounds_max on axis %d", hb.gid, d);
+    TRY(b->particles.ensure(sizeof(float) * 3 * (size_t)std::max(1, hb.num_particles)));
+    TRY(b->tets.ensure(32 * (size_t)std::max(1, hb.num_tets)));
+    TRY(b->v2t.ensure(sizeof(int) * (size_t)std::max(1, hb.num_particles)));
+    TRY(b->cc.ensure(16 * (size_t)std::max(1, hb.num_tets)));
+    if (hb.num_particles) CU(cudaMemcpyAsync(b->particles.p, hb.particles, sizeof(float) * 3 * (size_t)hb.num_particles, cudaMemcpyHostToDevice, c->stream));
+    if (hb.num_tets) CU(cudaMemcpyAsync(b->tets.p, hb.tets, 32 * (size_t)hb.num_tets, cudaMemcpyHostToDevice, c->stream));
+    b->have_v2t = hb.vert_to_tet != nullptr;
+    if (b->have_v2t && hb.num_particles)
+      CU(cudaMemcpyAsync(b->v2t.p, hb.vert_to_tet, sizeof(int) * (size_t)hb.num_particles, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->ran = false;
+  return 0;
+}
+
+static DevBlock dev_block(const BlockRes *b)
+{
+  DevBlock d;
+  d.particles = (const float *)b->particles.p;
+  d.tets = (const int4 *)b->tets.p;
+  d.v2t = (const int *)b->v2t.p;
+  d.cc = (const float4 *)b->cc.p;
+  d.num_orig = b->num_orig; d.num_particles = b->num_particles; d.num_tets = b->num_tets;
+  d.cell_base = b->cell_base;
+  return d;
+}
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+static int prep_block_geometry(tessb200_ctx *c, BlockRes *b)
+{
+  // vert_to_tet (if not given) and circumcenters for one resident block
+  if (!b->have_v2t && b->num_particles) {
+    k_fill_i32<<<cdiv(b->num_particles, 256), 256, 0, c->stream>>>((int *)b->v2t.p, b->num_particles, -1);
+    if (b->num_tets) k_vert_to_tet<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (int *)b->v2t.p);
+  }
+  if (b->num_tets)
+    k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, (float4 *)b->cc.p);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int read_counters(tessb200_ctx *c)
+{
+  CU(cudaMemcpyAsync(c->h_cnt, c->d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+#ifdef TESSB200_WITH_NCCL
+static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned long long *n_spans);
+#endif
+
+// ---- run ---------------------------------------------------------------------------------------------
+extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_stats *st)
+{
+  if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
+  if (c->blocks.empty()) return fail(TESSB200_ESTATE, "tessb200_dense_run before tessb200_dense_upload");
+  CU(cudaSetDevice(c->device));
+  Geometry G;
+  TRY(make_geometry(c, p, &G));
+  cudaStream_t s = c->stream;
+  const int nloc = (int)c->blocks.size();
+  const int nall = (int)G.boxes.size();
+  long long cells = 0, tets = 0;
+  for (BlockRes *b : c->blocks) { cells += b->num_orig; tets += b->num_tets; }
+
+  CU(cudaEventRecord(c->ev[2], s));
+  // device descriptors
+  std::vector<DevBlock> hblocks(nall);
+  memset(hblocks.data(), 0, sizeof(DevBlock) * nall);
+  for (int i = 0; i < nall; i++)
+    if (G.local_of[i] >= 0) hblocks[i] = dev_block(c->blocks[G.local_of[i]]);
+  TRY(c->d_blocks.ensure(sizeof(DevBlock) * nall));
+  TRY(c->d_boxes.ensure(sizeof(BlockBox) * nall));
+  TRY(c->d_rblocks.ensure(sizeof(RowBlock) * std::max<size_t>(1, G.rblocks.size())));
+  TRY(c->d_cnt.ensure(sizeof(Counters)));
+  CU(cudaMemcpyAsync(c->d_blocks.p, hblocks.data(), sizeof(DevBlock) * nall, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(c->d_boxes.p, G.boxes.data(), sizeof(BlockBox) * nall, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(c->d_rblocks.p, G.rblocks.data(), sizeof(RowBlock) * G.rblocks.size(), cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(c->d_cnt.p, 0, sizeof(Counters), s));
+  Counters *cnt = c->d_cnt.as<Counters>();
+  ScanCtx sc;
+  sc.boxes = c->d_boxes.as<BlockBox>(); sc.nblocks = nall; sc.kl = G.kl; sc.project = G.g.project;
+
+  unsigned long long n_spans = 0;
+  unsigned long long span_cap = 0;
+  auto ensure_spans = [&](unsigned long long cap) -> int {
+    for (int i = 0; i < 2; i++) {
+      TRY(c->keys[i].ensure(8 * (size_t)cap));
+      TRY(c->data[i].ensure(8 * (size_t)cap));
+    }
+    span_cap = std::min(c->keys[0].cap, std::min(c->keys[1].cap, std::min(c->data[0].cap, c->data[1].cap))) / 8;
+    return 0;
+  };
+
+  CU(cudaEventRecord(c->ev[3], s));
+  if (p->alg == TESSB200_DENSE_TESS) {
+    // K0/K1
+    for (BlockRes *b : c->blocks) TRY(prep_block_geometry(c, b));
+    CU(cudaEventRecord(c->ev[4], s));
+    // K3a part 1
+    TRY(c->plane_pool.ensure(48 * ((size_t)2 * tets + (size_t)cells + 64)));   // sum of faces <= 4 T
+    TRY(c->hdr_small.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
+    TRY(c->hdr_big.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
+    TRY(c->big_bitoff.ensure(8 * (size_t)std::max<long long>(1, cells)));
+    const uint32_t cap_ovf = (uint32_t)std::max<long long>(1024, cells / 64);
+    TRY(c->overflow.ensure(sizeof(uint2) * (size_t)cap_ovf));
+    TopoOut to;
+    to.small = c->hdr_small.as<CellHdr>(); to.big = c->hdr_big.as<CellHdr>();
+    to.big_bit_off = c->big_bitoff.as<unsigned long long>();
+    to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.cnt = cnt;
+    to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
+    for (int i = 0; i < nall; i++) {
+      if (G.local_of[i] < 0) continue;
+      const DevBlock &db = hblocks[i];
+      if (db.num_orig == 0) continue;
+      k_cell_topo<<<cdiv(db.num_orig, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, s>>>(db, i, G.g, to);
+    }
+    CU(cudaGetLastError());
+    TRY(read_counters(c));
+    if (c->h_cnt->n_overflow > cap_ovf) return fail(TESSB200_ELIMIT, "%u cells exceed the fast star workspace (capacity %u)", c->h_cnt->n_overflow, cap_ovf);
+    long long n_slow = c->h_cnt->n_overflow;
+    if (c->h_cnt->n_overflow) {
+      int n = (int)c->h_cnt->n_overflow;
+      TRY(c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)((n + 127) & ~127)));
+      k_cell_topo_big<<<cdiv(n, 128), 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>(), n, c->ws_big.as<int>());
+      CU(cudaGetLastError());
+      TRY(read_counters(c));
+    }
+    CU(cudaEventRecord(c->ev[5], s));
+    const unsigned n_small = c->h_cnt->n_small, n_big = c->h_cnt->n_big;
+    n_slow += n_big;
+    if (n_big) TRY(c->bits_big.ensure((size_t)(c->h_cnt->big_bits / 8) + 64));
+    TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells)));
+    for (int attempt = 0; attempt < 2; attempt++) {
+      SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
+      if (n_small)
+        k_cell_scan<<<cdiv(n_small, SCAN_CELLS), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), cnt, to.cap_small, c->plane_pool.as<float>(),
+                                                                              c->d_blocks.as<DevBlock>(), sc, G.g, so);
+      if (n_big)
+        k_cell_scan_big<<<n_big, 128, 0, s>>>(c->hdr_big.as<CellHdr>(), c->big_bitoff.as<unsigned long long>(), (int)n_big, c->plane_pool.as<float>(),
+                                              c->bits_big.as<uint32_t>(), c->d_blocks.as<DevBlock>(), sc, G.g, so);
+      CU(cudaGetLastError());
+      TRY(read_counters(c));
+      n_spans = c->h_cnt->n_spans;
+      if (n_spans <= span_cap) break;
+      if (attempt == 1) return fail(TESSB200_ECAPACITY, "span buffer overflow after regrow");
+      // regrow and redo the scan (counters of the scan stage reset)
+      TRY(ensure_spans(n_spans + n_spans / 16 + 1024));
+      Counters z = *c->h_cnt;
+      z.n_spans = 0; z.n_deposit = 0; z.n_cic_fallback = 0;
+      CU(cudaMemcpyAsync(c->d_cnt.p, &z, sizeof(Counters), cudaMemcpyHostToDevice, s));
+      CU(cudaStreamSynchronize(s));
+    }
+    if (st) st->num_slow_cells = n_slow;
+  } else {
+    CU(cudaEventRecord(c->ev[4], s));
+    CU(cudaEventRecord(c->ev[5], s));
+    TRY(ensure_spans(std::max<unsigned long long>(1ull << 16, 8ull * (unsigned long long)cells + 1024)));
+    SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
+    for (int i = 0; i < nall; i++) {
+      if (G.local_of[i] < 0) continue;
+      const DevBlock &db = hblocks[i];
+      if (db.num_orig == 0) continue;
+      k_cic<<<cdiv(db.num_orig, 256), 256, 0, s>>>(db, i, sc, G.g, so);
+    }
+    CU(cudaGetLastError());
+    TRY(read_counters(c));
+    n_spans = c->h_cnt->n_spans;
+    if (n_spans > span_cap) return fail(TESSB200_ECAPACITY, "span buffer overflow in CIC");
+    if (st) st->num_slow_cells = 0;
+  }
+  CU(cudaEventRecord(c->ev[6], s));
+
+  int cur = 0;
+#ifdef TESSB200_WITH_NCCL
+  if (c->nranks > 1) TRY(exchange_spans(c, G, cur, &n_spans));
+#endif
+  CU(cudaEventRecord(c->ev[7], s));
+
+  // sort by (row, remote, cell, z)
+  if (n_spans) {
+    if (n_spans > 0x7fffffffull) return fail(TESSB200_ELIMIT, "%llu span records exceed the sorter's 2^31 limit", n_spans);
+    size_t tmp_bytes = 0;
+    cub::DoubleBuffer<uint64_t> dk(c->keys[cur].as<uint64_t>(), c->keys[cur ^ 1].as<uint64_t>());
+    cub::DoubleBuffer<uint64_t> dv(c->data[cur].as<uint64_t>(), c->data[cur ^ 1].as<uint64_t>());
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n_spans, 0, G.key_bits, s));
+    TRY(c->cub_tmp.ensure(tmp_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_spans, 0, G.key_bits, s));
+    if (dk.Current() != c->keys[cur].as<uint64_t>()) cur ^= 1;
+    if (dv.Current() != c->data[cur].as<uint64_t>()) return fail(TESSB200_ECUDA, "sorter returned mismatched buffers");
+  }
+  CU(cudaEventRecord(c->ev[8], s));
+
+  // deposit
+  TRY(c->row_start.ensure(8 * (size_t)(G.nrows + 2)));
+  TRY(c->out.ensure(sizeof(float) * (size_t)std::max<long long>(4, G.out_floats)));
+  k_row_starts<<<cdiv((long long)n_spans + 1, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows,
+                                                                 c->row_start.as<unsigned long long>());
+  {
+    size_t smem = sizeof(float) * (size_t)ROWS_WARPS * (size_t)G.nx_max;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rows<<<cdiv((long long)G.nrows, ROWS_WARPS), ROWS_WARPS * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0,
+                                                                               G.nrows, c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div,
+                                                                               G.nx_max, c->out.as<float>());
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev[9], s));
+
+  if (st) {
+    // dense_stats (src/dense.cpp:1284-1333): max density and total mass, from the final grid
+    const int nb = 512;
+    TRY(c->stat_sum.ensure(sizeof(double) * nb));
+    TRY(c->stat_max.ensure(sizeof(float) * nb));
+    double tot = 0.0;
+    float mx = 0.0f;
+    for (BlockRes *b : c->blocks) {
+      if (!b->npts) continue;
+      k_grid_stats<<<nb, 256, 0, s>>>(c->out.as<float>() + b->out_off, (unsigned long long)b->npts, c->stat_sum.as<double>(), c->stat_max.as<float>());
+      CU(cudaMemcpyAsync(c->h_sum, c->stat_sum.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync(c->h_max, c->stat_max.p, sizeof(float) * nb, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      for (int i = 0; i < nb; i++) { tot += c->h_sum[i]; mx = std::max(mx, c->h_max[i]); }
+    }
+    st->tot_mass = tot * (double)G.g.div;
+    st->max_dense = mx;
+  }
+  CU(cudaEventRecord(c->ev[10], s));
+  CU(cudaStreamSynchronize(s));
+
+  c->ran = true;
+  c->last_params = *p;
+  c->out_floats = G.out_floats;
+  if (st) {
+    st->num_cells = cells;
+    st->num_no_tet = (int64_t)c->h_cnt->n_no_tet;
+    st->num_incomplete = (int64_t)c->h_cnt->n_incomplete;
+    st->num_outside = (int64_t)(c->h_cnt->n_outside + c->h_cnt->n_bad);
+    st->num_deposit_cells = (int64_t)c->h_cnt->n_deposit;
+    st->num_cic_fallback = (int64_t)c->h_cnt->n_cic_fallback;
+    st->num_spans = (int64_t)n_spans;
+    st->num_tets = tets;
+    st->num_grid_pts = 0;
+    for (BlockRes *b : c->blocks) st->num_grid_pts += b->npts;
+    auto ms = [&](int a, int b) { float m = 0; cudaEventElapsedTime(&m, c->ev[a], c->ev[b]); return m; };
+    st->ms_upload = ms(0, 1);
+    st->ms_circumcenters = ms(3, 4);
+    st->ms_cells = ms(4, 5);
+    st->ms_scan = ms(5, 6);
+    st->ms_exchange = ms(6, 7);
+    st->ms_sort = ms(7, 8);
+    st->ms_deposit = ms(8, 9);
+    st->ms_total_device = ms(2, 9);
+    st->ms_download = 0;
+  }
+  return 0;
+}
+
+extern "C" int tessb200_dense_geometry(tessb200_ctx *c, tessb200_dense_params *p, int nblocks, tessb200_block *blocks)
+{
+  if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
+  Geometry G;
+  TRY(make_geometry(c, p, &G));
+  for (int i = 0; i < nblocks; i++) {
+    BlockRes *b = nullptr;
+    for (BlockRes *x : c->blocks) if (x->gid == blocks[i].gid) b = x;
+    if (!b) return fail(TESSB200_EINVAL, "block gid %d was not uploaded", blocks[i].gid);
+    memcpy(blocks[i].block_min_idx, b->mn, 12); memcpy(blocks[i].block_num_idx, b->num, 12);
+    blocks[i].num_grid_pts = b->npts;
+  }
+  return 0;
+}
+
+extern "C" int tessb200_dense_device_density(tessb200_ctx *c, int gid, void **dptr, int64_t *num_floats)
+{
+  if (!c || !c->ran) return fail(TESSB200_ESTATE, "no completed run");
+  for (BlockRes *b : c->blocks)
+    if (b->gid == gid) {
+      if (dptr) *dptr = c->out.as<float>() + b->out_off;
+      if (num_floats) *num_floats = b->npts;
+      return 0;
+    }
+  return fail(TESSB200_EINVAL, "block gid %d was not uploaded", gid);
+}
+
+// ---- download ---------------------------------------------------------------------------------------
+extern "C" int tessb200_dense_download(tessb200_ctx *c, int nblocks, tessb200_block *blocks, float *global_grid)
+{
+  if (!c || !c->ran) return fail(TESSB200_ESTATE, "tessb200_dense_download before a completed tessb200_dense_run");
+  CU(cudaSetDevice(c->device));
+  const tessb200_dense_params &p = c->last_params;
+  for (int i = 0; i < nblocks; i++) {
+    BlockRes *b = nullptr;
+    for (BlockRes *x : c->blocks) if (x->gid == blocks[i].gid) b = x;
+    if (!b) return fail(TESSB200_EINVAL, "block gid %d was not uploaded", blocks[i].gid);
+    memcpy(blocks[i].block_min_idx, b->mn, 12); memcpy(blocks[i].block_num_idx, b->num, 12);
+    blocks[i].num_grid_pts = b->npts;
+    if (blocks[i].density) {
+      if (blocks[i].density_capacity < b->npts)
+        return fail(TESSB200_ECAPACITY, "block gid %d: density_capacity %lld < %lld grid points", b->gid, (long long)blocks[i].density_capacity, b->npts);
+      CU(cudaMemcpyAsync(blocks[i].density, c->out.as<float>() + b->out_off, sizeof(float) * (size_t)b->npts, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  if (global_grid) {
+    if (p.project) return fail(TESSB200_EINVAL, "global_grid is only assembled for 3-D runs; use tessb200_write_grid for projections");
+    const size_t gx = p.glo_num_idx[0], gy = p.glo_num_idx[1];
+    for (BlockRes *b : c->blocks) {
+      if (!b->npts) continue;
+      cudaMemcpy3DParms cp;
+      memset(&cp, 0, sizeof(cp));
+      cp.srcPtr = make_cudaPitchedPtr(c->out.as<float>() + b->out_off, sizeof(float) * (size_t)b->num[0], (size_t)b->num[0], (size_t)b->num[1]);
+      cp.dstPtr = make_cudaPitchedPtr(global_grid, sizeof(float) * gx, gx, gy);
+      cp.dstPos = make_cudaPos(sizeof(float) * (size_t)b->mn[0], (size_t)b->mn[1], (size_t)b->mn[2]);
+      cp.extent = make_cudaExtent(sizeof(float) * (size_t)b->num[0], (size_t)b->num[1], (size_t)b->num[2]);
+      cp.kind = cudaMemcpyDeviceToHost;
+      CU(cudaMemcpy3DAsync(&cp, c->stream));
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nblocks, tessb200_block *blocks, float *global_grid,
+                              tessb200_dense_stats *st)
+{
+  TRY(tessb200_dense_upload(c, nblocks, blocks));
+  TRY(tessb200_dense_run(c, p, st));
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  TRY(tessb200_dense_download(c, nblocks, blocks, global_grid));
+  if (st) {
+    CU(cudaEventRecord(c->ev[1], c->stream));
+    CU(cudaEventSynchronize(c->ev[1]));
+    cudaEventElapsedTime(&st->ms_download, c->ev[0], c->ev[1]);
+  }
+  return 0;
+}
+
+// ---- per-tet / per-site entry points ----------------------------------------------------------------
+struct TmpBlock
+{
+  BlockRes b;
+  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); }
+};
+
+static int upload_tmp(tessb200_ctx *c, TmpBlock &t, int num_particles, const float *particles, int num_tets, const int *tets, const int *v2t)
+{
+  if (num_particles < 0 || num_tets < 0) return fail(TESSB200_EINVAL, "negative count");
+  if ((num_tets && !tets) || (num_particles && particles == nullptr && false)) return fail(TESSB200_EINVAL, "NULL input");
+  BlockRes &b = t.b;
+  b.num_particles = num_particles; b.num_tets = num_tets; b.num_orig = num_particles;
+  TRY(b.particles.ensure(sizeof(float) * 3 * (size_t)std::max(1, num_particles)));
+  TRY(b.tets.ensure(32 * (size_t)std::max(1, num_tets)));
+  TRY(b.v2t.ensure(sizeof(int) * (size_t)std::max(1, num_particles)));
+  TRY(b.cc.ensure(16 * (size_t)std::max(1, num_tets)));
+  if (particles && num_particles) CU(cudaMemcpyAsync(b.particles.p, particles, sizeof(float) * 3 * (size_t)num_particles, cudaMemcpyHostToDevice, c->stream));
+  if (num_tets) CU(cudaMemcpyAsync(b.tets.p, tets, 32 * (size_t)num_tets, cudaMemcpyHostToDevice, c->stream));
+  b.have_v2t = v2t != nullptr;
+  if (v2t && num_particles) CU(cudaMemcpyAsync(b.v2t.p, v2t, sizeof(int) * (size_t)num_particles, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+extern "C" int tessb200_fill_vert_to_tet(tessb200_ctx *c, int num_particles, int num_tets, const int *tets, int *vert_to_tet)
+{
+  if (!c || !vert_to_tet) return fail(TESSB200_EINVAL, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  TmpBlock t;
+  TRY(upload_tmp(c, t, num_particles, nullptr, num_tets, tets, nullptr));
+  if (num_particles) {
+    k_fill_i32<<<cdiv(num_particles, 256), 256, 0, c->stream>>>((int *)t.b.v2t.p, num_particles, -1);
+    if (num_tets) k_vert_to_tet<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (int *)t.b.v2t.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(vert_to_tet, t.b.v2t.p, sizeof(int) * (size_t)num_particles, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int tessb200_circumcenters(tessb200_ctx *c, int num_particles, const float *particles, int num_tets, const int *tets, float *out)
+{
+  if (!c || !out || !particles) return fail(TESSB200_EINVAL, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  TmpBlock t;
+  TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, nullptr));
+  if (num_tets) {
+    k_circumcenters<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (const float *)t.b.particles.p, (float4 *)t.b.cc.p);
+    CU(cudaGetLastError());
+    // float4 -> packed xyz on the way out (the reference's std::vector<float> layout, volume.cpp:8)
+    CU(cudaMemcpy2DAsync(out, 12, t.b.cc.p, 16, 12, (size_t)num_tets, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int tessb200_cell_volumes(tessb200_ctx *c, int num_sites, int num_particles, const float *particles, int num_tets, const int *tets,
+                                     const int *vert_to_tet, float mass, int *complete, float *volume, float *density)
+{
+  if (!c || !particles) return fail(TESSB200_EINVAL, "NULL argument");
+  if (num_sites < 0 || num_sites > num_particles) return fail(TESSB200_EINVAL, "num_sites out of range");
+  CU(cudaSetDevice(c->device));
+  TmpBlock t;
+  TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, vert_to_tet));
+  TRY(prep_block_geometry(c, &t.b));
+  if (num_sites) {
+    Buf d_comp, d_vol, d_den, d_ovf, d_n, d_ws;
+    auto cleanup = [&]() { d_comp.release(); d_vol.release(); d_den.release(); d_ovf.release(); d_n.release(); d_ws.release(); };
+    const uint32_t cap = (uint32_t)std::max(1024, num_sites / 64);
+    int rc = 0;
+    if ((rc = d_comp.ensure(4 * (size_t)num_sites)) || (rc = d_vol.ensure(4 * (size_t)num_sites)) || (rc = d_den.ensure(4 * (size_t)num_sites)) ||
+        (rc = d_ovf.ensure(4 * (size_t)cap)) || (rc = d_n.ensure(4))) { cleanup(); return rc; }
+    cudaMemsetAsync(d_n.p, 0, 4, c->stream);
+    DevBlock db = dev_block(&t.b);
+    k_cell_volumes<<<cdiv(num_sites, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, c->stream>>>(db, num_sites, mass, d_comp.as<int>(), d_vol.as<float>(), d_den.as<float>(),
+                                                                                  d_ovf.as<uint32_t>(), d_n.as<unsigned int>(), cap);
+    unsigned int n_ovf = 0;
+    cudaMemcpyAsync(&n_ovf, d_n.p, 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(TESSB200_ECUDA, "k_cell_volumes: %s", cudaGetErrorString(e)); }
+    if (n_ovf > cap) { cleanup(); return fail(TESSB200_ELIMIT, "%u sites exceed the fast star workspace", n_ovf); }
+    if (n_ovf) {
+      if ((rc = d_ws.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)n_ovf))) { cleanup(); return rc; }
+      k_cell_volumes_big<<<cdiv(n_ovf, 128), 128, 0, c->stream>>>(db, d_ovf.as<uint32_t>(), (int)n_ovf, d_ws.as<int>(), mass, d_comp.as<int>(),
+                                                                  d_vol.as<float>(), d_den.as<float>());
+    }
+    if (complete) cudaMemcpyAsync(complete, d_comp.p, 4 * (size_t)num_sites, cudaMemcpyDeviceToHost, c->stream);
+    if (volume) cudaMemcpyAsync(volume, d_vol.p, 4 * (size_t)num_sites, cudaMemcpyDeviceToHost, c->stream);
+    if (density) cudaMemcpyAsync(density, d_den.p, 4 * (size_t)num_sites, cudaMemcpyDeviceToHost, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(TESSB200_ECUDA, "cell volumes: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+// ---- WriteGrid / ProjectGrid for one process (src/dense.cpp:751-1023) --------------------------------
+extern "C" int tessb200_write_grid(const char *outfile, const tessb200_dense_params *p, int nblocks, const tessb200_block *blocks)
+{
+  if (!outfile || !p || !blocks || nblocks < 1) return fail(TESSB200_EINVAL, "NULL argument");
+  const size_t gx = p->glo_num_idx[0], gy = p->glo_num_idx[1], gz = p->glo_num_idx[2];
+  std::vector<float> grid(p->project ? gx * gy : gx * gy * gz, 0.0f);
+  if (p->project) {
+    // ProjectGrid: every block with min_idx z != 0 is added, in block order, into the z = 0 block
+    // that shares its (x, y) origin; then only the z = 0 blocks are written
+    std::vector<std::vector<float> > acc(nblocks);
+    for (int i = 0; i < nblocks; i++)
+      if (blocks[i].block_min_idx[2] == 0) {
+        if (!blocks[i].density) return fail(TESSB200_EINVAL, "block gid %d has no density", blocks[i].gid);
+        acc[i].assign(blocks[i].density, blocks[i].density + (size_t)blocks[i].block_num_idx[0] * blocks[i].block_num_idx[1]);
+      }
+    for (int i = 0; i < nblocks; i++) {
+      if (blocks[i].block_min_idx[2] == 0) continue;
+      if (!blocks[i].density) return fail(TESSB200_EINVAL, "block gid %d has no density", blocks[i].gid);
+      int root = -1;
+      for (int j = 0; j < nblocks; j++)
+        if (blocks[j].block_min_idx[2] == 0 && blocks[j].block_min_idx[0] == blocks[i].block_min_idx[0] &&
+            blocks[j].block_min_idx[1] == blocks[i].block_min_idx[1]) root = j; // the last match wins, as in dense.cpp:946-954
+      if (root < 0) continue;
+      size_t n = (size_t)blocks[i].block_num_idx[0] * blocks[i].block_num_idx[1];
+      if (acc[root].size() < n) n = acc[root].size();
+      for (size_t k = 0; k < n; k++) acc[root][k] += blocks[i].density[k];
+    }
+    for (int i = 0; i < nblocks; i++) {
+      if (blocks[i].block_min_idx[2] != 0) continue;
+      const int *mn = blocks[i].block_min_idx, *num = blocks[i].block_num_idx;
+      for (int y = 0; y < num[1]; y++)
+        memcpy(&grid[(size_t)(mn[1] + y) * gx + mn[0]], &acc[i][(size_t)y * num[0]], sizeof(float) * (size_t)num[0]);
+    }
+  } else {
+    for (int i = 0; i < nblocks; i++) {
+      if (!blocks[i].density) return fail(TESSB200_EINVAL, "block gid %d has no density", blocks[i].gid);
+      const int *mn = blocks[i].block_min_idx, *num = blocks[i].block_num_idx;
+      for (int z = 0; z < num[2]; z++)
+        for (int y = 0; y < num[1]; y++)
+          memcpy(&grid[((size_t)(mn[2] + z) * gy + (mn[1] + y)) * gx + mn[0]], &blocks[i].density[((size_t)z * num[1] + y) * num[0]],
+                 sizeof(float) * (size_t)num[0]);
+    }
+  }
+  FILE *f = fopen(outfile, "wb");
+  if (!f) return fail(TESSB200_EIO, "cannot open %s for writing", outfile);
+  size_t w = fwrite(grid.data(), sizeof(float), grid.size(), f);
+  fclose(f);
+  if (w != grid.size()) return fail(TESSB200_EIO, "short write to %s", outfile);
+  return 0;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------
+extern "C" int tessb200_dense_set_layout(tessb200_ctx *c, int n, const int *gids, const float *bounds6, const int *owner_rank)
+{
+  if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
+  c->layout.clear();
+  if (n == 0) return 0;
+  if (!gids || !bounds6 || !owner_rank) return fail(TESSB200_EINVAL, "NULL argument");
+  for (int i = 0; i < n; i++) {
+    LayoutBlock l;
+    l.gid = gids[i];
+    memcpy(l.bmin, bounds6 + 6 * i, 12); memcpy(l.bmax, bounds6 + 6 * i + 3, 12);
+    l.owner = owner_rank[i];
+    if (i && gids[i] <= gids[i - 1]) { c->layout.clear(); return fail(TESSB200_EINVAL, "layout gids must be ascending"); }
+    c->layout.push_back(l);
+  }
+  return 0;
+}
+
+#ifndef TESSB200_WITH_NCCL
+extern "C" int tessb200_comm_unique_id(void *) { return fail(TESSB200_ENCCL, "libtess_b200 was built without NCCL"); }
+extern "C" int tessb200_comm_init(tessb200_ctx *, int, int, const void *) { return fail(TESSB200_ENCCL, "libtess_b200 was built without NCCL"); }
+#else
+#define NC(expr)                                                                                        \
+  do {                                                                                                  \
+    ncclResult_t r_ = (expr);                                                                           \
+    if (r_ != ncclSuccess) return fail(TESSB200_ENCCL, "%s:%d: %s: %s", __FILE__, __LINE__, #expr, ncclw::g.GetErrorString(r_)); \
+  } while (0)
+
+extern "C" int tessb200_comm_unique_id(void *id128)
+{
+  if (!id128) return fail(TESSB200_EINVAL, "NULL argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  if (const char *e = ncclw::load()) return fail(TESSB200_ENCCL, "cannot load NCCL: %s", e);
+  ncclUniqueId id;
+  NC(ncclw::g.GetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+extern "C" int tessb200_comm_init(tessb200_ctx *c, int nranks, int rank, const void *id128)
+{
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(TESSB200_EINVAL, "bad argument");
+  if (nranks > 64) return fail(TESSB200_ELIMIT, "more than 64 ranks");
+  if (const char *e = ncclw::load()) return fail(TESSB200_ENCCL, "cannot load NCCL: %s", e);
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  if (c->comm) { ncclw::g.CommDestroy(c->comm); c->comm = nullptr; }
+  NC(ncclw::g.CommInitRank(&c->comm, nranks, id, rank));
+  c->nranks = nranks;
+  c->rank = rank;
+  return 0;
+}
+
+// Replaces master.exchange() (src/dense.cpp:98): span records whose row belongs to another rank's
+// blocks are partitioned by destination (a stable radix pass on the destination rank), the
+// nranks x nranks count matrix is all-gathered, and the payload moves with grouped
+// ncclSend/ncclRecv over NVLink.  Only boundary cells produce such records.
+__global__ void k_dest_rank(const uint64_t *__restrict__ keys, unsigned long long n, KeyLayout kl, const long long *__restrict__ rank_row_end,
+                            int nranks, uint32_t *__restrict__ dest, unsigned long long *__restrict__ counts)
+{
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long row = (long long)key_row(kl, keys[i]);
+  int r = 0;
+  while (r < nranks - 1 && row >= rank_row_end[r]) r++;
+  dest[i] = (uint32_t)r;
+  atomicAdd(&counts[r], 1ull);
+}
+
+static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned long long *n_spans)
+{
+  cudaStream_t s = c->stream;
+  const int R = c->nranks;
+  // row range end of every rank (blocks of a rank are contiguous in gid order)
+  std::vector<long long> row_end(R, 0);
+  {
+    const std::vector<LayoutBlock> &L = c->layout;
+    for (size_t i = 0; i < L.size(); i++) {
+      long long nrows = G.g.project ? G.boxes[i].b_num[1] : (long long)G.boxes[i].b_num[1] * G.boxes[i].b_num[2];
+      long long end = G.boxes[i].row_base + nrows;
+      if (L[i].owner < 0 || L[i].owner >= R) return fail(TESSB200_EINVAL, "layout owner rank out of range");
+      row_end[L[i].owner] = std::max(row_end[L[i].owner], end);
+    }
+    for (int r = 1; r < R; r++) row_end[r] = std::max(row_end[r], row_end[r - 1]);
+  }
+  unsigned long long n = *n_spans;
+  Buf d_row_end, d_dest, d_dest2, d_counts, d_all;
+  auto cleanup = [&]() { d_row_end.release(); d_dest.release(); d_dest2.release(); d_counts.release(); d_all.release(); };
+  int rc = 0;
+  if ((rc = d_row_end.ensure(8 * R)) || (rc = d_dest.ensure(4 * (size_t)std::max<unsigned long long>(1, n))) ||
+      (rc = d_dest2.ensure(4 * (size_t)std::max<unsigned long long>(1, n))) || (rc = d_counts.ensure(8 * R)) || (rc = d_all.ensure(8 * (size_t)R * R))) {
+    cleanup();
+    return rc;
+  }
+  cudaMemcpyAsync(d_row_end.p, row_end.data(), 8 * R, cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(d_counts.p, 0, 8 * R, s);
+  if (n) k_dest_rank<<<cdiv((long long)n, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n, G.kl, d_row_end.as<long long>(), R, d_dest.as<uint32_t>(),
+                                                            d_counts.as<unsigned long long>());
+  // group records by destination: two stable sorts with the same small key keep keys/data paired
+  if (n) {
+    size_t tb1 = 0, tb2 = 0;
+    int bits = std::max(1, ceil_log2((unsigned long long)R));
+    cub::DeviceRadixSort::SortPairs(nullptr, tb1, d_dest.as<uint32_t>(), d_dest2.as<uint32_t>(), c->keys[cur].as<uint64_t>(), c->keys[cur ^ 1].as<uint64_t>(), (int)n, 0, bits, s);
+    tb2 = tb1;
+    if ((rc = c->cub_tmp.ensure(tb1))) { cleanup(); return rc; }
+    cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb1, d_dest.as<uint32_t>(), d_dest2.as<uint32_t>(), c->keys[cur].as<uint64_t>(), c->keys[cur ^ 1].as<uint64_t>(), (int)n, 0, bits, s);
+    cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb2, d_dest.as<uint32_t>(), d_dest2.as<uint32_t>(), c->data[cur].as<uint64_t>(), c->data[cur ^ 1].as<uint64_t>(), (int)n, 0, bits, s);
+  }
+  ncclResult_t nr = ncclw::g.AllGather(d_counts.p, d_all.p, (size_t)R, ncclUint64, c->comm, s);
+  if (nr != ncclSuccess) { cleanup(); return fail(TESSB200_ENCCL, "ncclAllGather: %s", ncclw::g.GetErrorString(nr)); }
+  std::vector<unsigned long long> all((size_t)R * R);
+  cudaMemcpyAsync(all.data(), d_all.p, 8 * (size_t)R * R, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { cleanup(); return fail(TESSB200_ECUDA, "exchange: %s", cudaGetErrorString(e)); }
+  // all[src * R + dst]
+  unsigned long long recv_total = 0;
+  for (int src = 0; src < R; src++) recv_total += all[(size_t)src * R + c->rank];
+  // receive into the "current" buffers (the partitioned copies live in cur ^ 1)
+  for (int i = 0; i < 2; i++) {
+    // keep the partitioned source intact: only grow the destination side
+  }
+  if ((rc = c->recv_keys.ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total))) ||
+      (rc = c->recv_data.ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total)))) { cleanup(); return rc; }
+  const uint64_t *sk = c->keys[cur ^ 1].as<uint64_t>(), *sd = c->data[cur ^ 1].as<uint64_t>();
+  uint64_t *rk = c->recv_keys.as<uint64_t>(), *rd = c->recv_data.as<uint64_t>();
+  ncclw::g.GroupStart();
+  unsigned long long soff = 0, roff = 0;
+  for (int peer = 0; peer < R; peer++) {
+    unsigned long long ns = all[(size_t)c->rank * R + peer], nrcv = all[(size_t)peer * R + c->rank];
+    if (peer == c->rank) {
+      cudaMemcpyAsync(rk + roff, sk + soff, 8 * (size_t)ns, cudaMemcpyDeviceToDevice, s);
+      cudaMemcpyAsync(rd + roff, sd + soff, 8 * (size_t)ns, cudaMemcpyDeviceToDevice, s);
+    } else {
+      if (ns) { ncclw::g.Send(sk + soff, (size_t)ns, ncclUint64, peer, c->comm, s); ncclw::g.Send(sd + soff, (size_t)ns, ncclUint64, peer, c->comm, s); }
+      if (nrcv) { ncclw::g.Recv(rk + roff, (size_t)nrcv, ncclUint64, peer, c->comm, s); ncclw::g.Recv(rd + roff, (size_t)nrcv, ncclUint64, peer, c->comm, s); }
+    }
+    soff += ns;
+    roff += nrcv;
+  }
+  nr = ncclw::g.GroupEnd();
+  if (nr != ncclSuccess) { cleanup(); return fail(TESSB200_ENCCL, "ncclGroupEnd: %s", ncclw::g.GetErrorString(nr)); }
+  // the received records become the current span list
+  for (int i = 0; i < 2; i++) {
+    if ((rc = c->keys[i].ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total))) ||
+        (rc = c->data[i].ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total)))) { cleanup(); return rc; }
+  }
+  cudaMemcpyAsync(c->keys[cur].p, rk, 8 * (size_t)recv_total, cudaMemcpyDeviceToDevice, s);
+  cudaMemcpyAsync(c->data[cur].p, rd, 8 * (size_t)recv_total, cudaMemcpyDeviceToDevice, s);
+  e = cudaStreamSynchronize(s);
+  cleanup();
+  if (e != cudaSuccess) return fail(TESSB200_ECUDA, "exchange: %s", cudaGetErrorString(e));
+  *n_spans = recv_total;
+  return 0;
+}
+#endif

@@ -1,0 +1,504 @@
+// cell_core.cuh -- per-tet / per-cell arithmetic of the dense stage, shared by every kernel.
+//
+// Everything here is written so that the fp32 results equal the reference's default
+// x86-64 Release build bit for bit: fp32 add/mul/div/sqrt in the
+// reference's operation order, no FMA contraction (the whole library is compiled with
+// -fmad=false; the explicit fadd/fmul helpers below make the intent visible and keep the
+// host-compiled test build, which uses -ffp-contract=off, identical).
+//
+// Functions are __host__ __device__ so that tests/emul (a CPU build of the same logic, test
+// only, never part of libtess_b200.so) can single-step them against the oracle.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define TB_HD __host__ __device__ __forceinline__
+#else
+#define TB_HD inline
+struct int4 { int x, y, z, w; };
+struct float4 { float x, y, z, w; };
+struct float2 { float x, y; };
+#endif
+
+namespace tb
+{
+
+// ---- rounding-exact scalar helpers -------------------------------------------------------
+TB_HD float fadd(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+TB_HD float fsub(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+TB_HD float fmul(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+TB_HD float fdiv(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+TB_HD float fsqrt(float a)
+{
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+
+// ---- grid <-> physical -------------------------------------------------------------------
+struct GridGeom
+{
+  float gmin[3];   // grid_phys_mins
+  float step[3];   // grid_step_size
+  float dmin[3];   // data_mins
+  float dmax[3];   // data_maxs
+  float dext_eps[3]; // (data_max - data_min) * 2.0f * FLT_EPSILON   (src/dense.cpp:1382-1383)
+  int gnum[3];     // glo_num_idx
+  float eps;
+  float mass;
+  float div;       // step_x * step_y [* step_z]   (src/dense.cpp:90-91)
+  int project;
+  int alg;
+};
+
+// idx2phys, src/dense.cpp:1098-1106: pos = idx * step + min (two roundings)
+TB_HD float idx2phys1(int idx, float step, float gmin) { return fadd(fmul((float)idx, step), gmin); }
+// phys2idx, src/dense.cpp:1117-1125: truncation toward zero of (pos - min) / step
+TB_HD int phys2idx1(float pos, float step, float gmin) { return (int)fdiv(fsub(pos, gmin), step); }
+
+// ---- circumcenter, src/tet.cpp:37-66 (norm :122-128, cross :131-136, determinant :139-143) ----
+TB_HD void circumcenter(const float *a, const float *b, const float *c, const float *d, float *center)
+{
+  float t[3], u[3], v[3];
+  for (int i = 0; i < 3; i++) {
+    t[i] = fsub(a[i], d[i]);
+    u[i] = fsub(b[i], d[i]);
+    v[i] = fsub(c[i], d[i]);
+  }
+  // norm(): res = 0; res += x[i]*x[i]
+  float nt = fadd(fadd(fadd(0.0f, fmul(t[0], t[0])), fmul(t[1], t[1])), fmul(t[2], t[2]));
+  float nu = fadd(fadd(fadd(0.0f, fmul(u[0], u[0])), fmul(u[1], u[1])), fmul(u[2], u[2]));
+  float nv = fadd(fadd(fadd(0.0f, fmul(v[0], v[0])), fmul(v[1], v[1])), fmul(v[2], v[2]));
+  // determinant(): t0*u1*v2 + u0*v1*t2 + v0*t1*u2 - v0*u1*t2 - u0*t1*v2 - t0*v1*u2, left to right
+  float det = fmul(fmul(t[0], u[1]), v[2]);
+  det = fadd(det, fmul(fmul(u[0], v[1]), t[2]));
+  det = fadd(det, fmul(fmul(v[0], t[1]), u[2]));
+  det = fsub(det, fmul(fmul(v[0], u[1]), t[2]));
+  det = fsub(det, fmul(fmul(u[0], t[1]), v[2]));
+  det = fsub(det, fmul(fmul(t[0], v[1]), u[2]));
+  float den = fmul(2.0f, det);
+  float uv[3], vt[3], tu[3];
+  uv[0] = fsub(fmul(u[1], v[2]), fmul(u[2], v[1]));
+  uv[1] = fsub(fmul(u[2], v[0]), fmul(u[0], v[2]));
+  uv[2] = fsub(fmul(u[0], v[1]), fmul(u[1], v[0]));
+  vt[0] = fsub(fmul(v[1], t[2]), fmul(v[2], t[1]));
+  vt[1] = fsub(fmul(v[2], t[0]), fmul(v[0], t[2]));
+  vt[2] = fsub(fmul(v[0], t[1]), fmul(v[1], t[0]));
+  tu[0] = fsub(fmul(t[1], u[2]), fmul(t[2], u[1]));
+  tu[1] = fsub(fmul(t[2], u[0]), fmul(t[0], u[2]));
+  tu[2] = fsub(fmul(t[0], u[1]), fmul(t[1], u[0]));
+  for (int i = 0; i < 3; i++) {
+    float num = fadd(fadd(fmul(nt, uv[i]), fmul(nu, vt[i])), fmul(nv, tu[i]));
+    center[i] = fadd(d[i], fdiv(num, den));
+  }
+}
+
+// ---- one plane test of PtInCell, src/dense.cpp:1187-1199 --------------------------------
+// returns +1 / -1 for a significant distance, 0 when |dist| <= eps (NaN counts as 0)
+TB_HD int plane_side(const float *n, const float *f, const float *pt, float eps)
+{
+  float dist = fadd(fadd(fmul(n[0], fsub(pt[0], f[0])), fmul(n[1], fsub(pt[1], f[1]))), fmul(n[2], fsub(pt[2], f[2])));
+  if (fabsf(dist) > eps) return dist >= 0.0f ? 1 : -1;
+  return 0;
+}
+
+// ---- Newell normal accumulation, src/dense.cpp:1139-1149, one (cur, next) term ----------
+TB_HD void newell_term(float *nrm, const float *cur, const float *nxt)
+{
+  nrm[0] = fadd(nrm[0], fmul(fsub(cur[1], nxt[1]), fadd(cur[2], nxt[2])));
+  nrm[1] = fadd(nrm[1], fmul(fsub(cur[2], nxt[2]), fadd(cur[0], nxt[0])));
+  nrm[2] = fadd(nrm[2], fmul(fsub(cur[0], nxt[0]), fadd(cur[1], nxt[1])));
+}
+// normalise + invert (src/dense.cpp:1151-1161), then orient away from the site (:722-731)
+TB_HD void newell_finish(float *nrm, const float *v0, const float *site)
+{
+  float mag = fsqrt(fadd(fadd(fmul(nrm[0], nrm[0]), fmul(nrm[1], nrm[1])), fmul(nrm[2], nrm[2])));
+  for (int i = 0; i < 3; i++) nrm[i] = -fdiv(nrm[i], mag);
+  float v[3] = {fsub(v0[0], site[0]), fsub(v0[1], site[1]), fsub(v0[2], site[2])};
+  float dotp = fadd(fadd(fmul(v[0], nrm[0]), fmul(v[1], nrm[1])), fmul(v[2], nrm[2]));
+  if (dotp < 0.0f) { nrm[0] = -nrm[0]; nrm[1] = -nrm[1]; nrm[2] = -nrm[2]; }
+}
+
+// ---- star walk -----------------------------------------------------------------------------
+// Status of one cell after the topology pass
+enum CellStatus
+{
+  CELL_OK = 0,
+  CELL_NO_TET = 1,      // vert_to_tet == -1                       (src/dense.cpp:251)
+  CELL_INCOMPLETE = 2,  // complete() == 0                          (src/dense.cpp:252, src/tet.cpp:337-378)
+  CELL_OUTSIDE = 3,     // bbox outside the data bounds             (src/dense.cpp:1385-1392)
+  CELL_OVERFLOW = 4,    // star / neighbour list exceeds the workspace: retry in the large workspace
+  CELL_BAD_MESH = 5     // circulation did not close within the step limit
+};
+
+// Workspace: three int arrays reached through accessors so that the same code runs on a
+// shared-memory slice (stride = blockDim), a global slice or plain host arrays.
+//   star(i) : tets of the star of the site in BFS order (doubles as the FIFO queue)
+//   nu(i)   : Delaunay neighbours in first-seen order;  nt(i): the star tet where nu(i) was first seen
+template <class WS>
+TB_HD int star_and_neighbors(int site, int t0, const int4 *tets, WS &ws, int star_cap, int nbr_cap, int *n_star, int *n_nbr)
+{
+  // src/tet.cpp:228-270 (neighbor_edges) + :337-378 (complete).  The reference pushes every
+  // neighbour tet and skips repeats when they are popped; with a FIFO queue the order of first
+  // pops equals the order of first pushes, so repeats are dropped at push time and the queue
+  // is the visited list itself.
+  int ns = 1, nn = 0;
+  ws.star(0) = t0;
+  for (int head = 0; head < ns; head++) {
+    int t = ws.star(head);
+    int4 v = tets[2 * (size_t)t];
+    int4 nb = tets[2 * (size_t)t + 1];
+    int vv[4] = {v.x, v.y, v.z, v.w};
+    int bb[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int u = vv[i];
+      if (u == site) continue;
+      bool seen = false;
+      for (int j = 0; j < nn; j++)
+        if (ws.nu(j) == u) { seen = true; break; }
+      if (!seen) {
+        if (nn >= nbr_cap) return CELL_OVERFLOW;
+        ws.nu(nn) = u;
+        ws.nt(nn) = t;
+        nn++;
+      }
+      int next = bb[i];
+      if (next < 0) return CELL_INCOMPLETE;
+      seen = false;
+      for (int j = 0; j < ns; j++)
+        if (ws.star(j) == next) { seen = true; break; }
+      if (!seen) {
+        if (ns >= star_cap) return CELL_OVERFLOW;
+        ws.star(ns++) = next;
+      }
+    }
+  }
+  *n_star = ns;
+  *n_nbr = nn;
+  return CELL_OK;
+}
+
+#define TB_MAX_LINK 4096
+
+// Walks the tets around Delaunay edge (site, u) starting at ut, in the reference's order
+// (fill_edge_link src/tet.cpp:389-409, circulate_start :164-173, circulate_next :186-215) and
+// hands every circumcenter to `visit(k, cc)`.  Returns the link length, or -1 if it did not close.
+template <class Visit>
+TB_HD int walk_edge_link(int site, int u, int ut, const int4 *tets, const float4 *cc, Visit &visit)
+{
+  int4 v = tets[2 * (size_t)ut];
+  int4 nb = tets[2 * (size_t)ut + 1];
+  int wi;
+  if (v.x != site && v.x != u) wi = 0;
+  else if (v.y != site && v.y != u) wi = 1;
+  else if (v.z != site && v.z != u) wi = 2;
+  else wi = 3;
+  int t = ut;
+  for (int k = 0; k < TB_MAX_LINK; k++) {
+    float4 c = cc[t];
+    visit(k, c);
+    int vv[4] = {v.x, v.y, v.z, v.w};
+    int nv = -1;
+#pragma unroll
+    for (int i = 3; i >= 0; i--)
+      if (i != wi && vv[i] != site && vv[i] != u) nv = vv[i]; // lowest such slot wins, as the reference's break does
+    int next_t = wi == 0 ? nb.x : wi == 1 ? nb.y : wi == 2 ? nb.z : nb.w;
+    if (next_t == ut || next_t < 0) return k + 1;
+    v = tets[2 * (size_t)next_t];
+    nb = tets[2 * (size_t)next_t + 1];
+    wi = (v.x == nv) ? 0 : (v.y == nv) ? 1 : (v.z == nv) ? 2 : 3;
+    t = next_t;
+  }
+  return -1;
+}
+
+// One Voronoi face for the dense stage (src/dense.cpp:682-735): circumcenters around the edge ->
+// Newell normal, first vertex, running bbox.
+struct FaceAccum
+{
+  float nrm[3], v0[3], prev[3];
+  float *cmin, *cmax;
+  bool *first_of_cell;
+  TB_HD void operator()(int k, const float4 &c)
+  {
+    float cur[3] = {c.x, c.y, c.z};
+    if (*first_of_cell) {
+      for (int d = 0; d < 3; d++) { cmin[d] = cur[d]; cmax[d] = cur[d]; }
+      *first_of_cell = false;
+    } else {
+      for (int d = 0; d < 3; d++) {
+        if (cur[d] < cmin[d]) cmin[d] = cur[d];
+        if (cur[d] > cmax[d]) cmax[d] = cur[d];
+      }
+    }
+    if (k == 0) {
+      for (int d = 0; d < 3; d++) { v0[d] = cur[d]; nrm[d] = 0.0f; }
+    } else {
+      newell_term(nrm, prev, cur);
+    }
+    for (int d = 0; d < 3; d++) prev[d] = cur[d];
+  }
+};
+
+// One Voronoi face for volume() (src/volume.cpp:31-47): fan triangulation from the first
+// circumcenter; the area sum goes through double because `sqrt(norm(cp))/2` is the double sqrt
+// there.
+struct AreaAccum
+{
+  float a[3], b[3];
+  float area;
+  TB_HD void operator()(int k, const float4 &c)
+  {
+    float cur[3] = {c.x, c.y, c.z};
+    if (k == 0) {
+      for (int d = 0; d < 3; d++) a[d] = cur[d];
+      area = 0.0f;
+    } else if (k == 1) {
+      for (int d = 0; d < 3; d++) b[d] = cur[d];
+    } else {
+      float ab[3], ac[3], cp[3];
+      for (int d = 0; d < 3; d++) { ab[d] = fsub(b[d], a[d]); ac[d] = fsub(cur[d], a[d]); }
+      cp[0] = fsub(fmul(ab[1], ac[2]), fmul(ab[2], ac[1]));
+      cp[1] = fsub(fmul(ab[2], ac[0]), fmul(ab[0], ac[2]));
+      cp[2] = fsub(fmul(ab[0], ac[1]), fmul(ab[1], ac[0]));
+      float n2 = fadd(fadd(fadd(0.0f, fmul(cp[0], cp[0])), fmul(cp[1], cp[1])), fmul(cp[2], cp[2]));
+      area = (float)((double)area + sqrt((double)n2) / 2.0);
+      for (int d = 0; d < 3; d++) b[d] = cur[d];
+    }
+  }
+};
+
+// ---- the scan-line state machine, src/dense.cpp:1475-1676 ---------------------------------
+// `inside(i,j,k)` answers PtInCell for local bbox index (i,j,k); `line(j,k,min_xi,max_xi)` is
+// called for every non-empty scan line in (z,y) order.  Returns the number of interior points.
+template <class Inside, class Line>
+TB_HD int scan_cell(int nx, int ny, int nz, Inside &inside, Line &line)
+{
+  int tot = 0;
+  int x_left = nx / 2, x_right = nx / 2, y_start = 0, first_x = 0;
+  for (int zi = 0; zi < nz; zi++) {
+    bool border_found = false, z_step_done = false;
+    for (int yi = y_start; yi < ny; yi++) {
+      // the reference tests x_left three times per line (init, left walk, right walk when
+      // x_right == x_left); PtInCell is pure, so the first answer is reused
+      bool in0 = inside(x_left, yi, zi);
+      bool x_in = in0;
+      int min_xi = nx - 1, max_xi = 0;
+      int xl0 = x_left;
+      int xi;
+      for (xi = x_left; xi >= 0 && xi < nx;) {
+        bool in = (xi == xl0) ? in0 : inside(xi, yi, zi);
+        if (in) {
+          if (xi < min_xi) min_xi = xi;
+          if (xi > max_xi) max_xi = xi;
+          if (x_in) xi--;
+          else { x_left = xi; break; }
+        } else {
+          if (!x_in) xi++;
+          else { x_left = xi; break; }
+        }
+      }
+      for (xi = x_right; xi >= 0 && xi < nx;) {
+        bool in = (xi == xl0) ? in0 : inside(xi, yi, zi);
+        if (in) {
+          if (xi < min_xi) min_xi = xi;
+          if (xi > max_xi) max_xi = xi;
+          if (x_in) xi++;
+          else { x_right = xi; break; }
+        } else {
+          if (!x_in) xi--;
+          else { x_right = xi; break; }
+        }
+      }
+      bool found = min_xi <= max_xi;
+      if (found) {
+        tot += max_xi - min_xi + 1;
+        if (yi == y_start) first_x = (min_xi + max_xi) / 2;
+        line(yi, zi, min_xi, max_xi);
+      }
+      int first_y = y_start;
+      if (found && !border_found) { first_y = yi; border_found = true; }
+      if (!found && border_found) z_step_done = true;
+      if ((yi == ny - 1 || z_step_done) && zi + 1 < nz) {
+        int yj;
+        for (yj = first_y; yj > 0; yj--)
+          if (!inside(first_x, yj, zi + 1)) break;
+        y_start = yj;
+      }
+      if (z_step_done) break;
+    }
+  }
+  return tot;
+}
+
+// ---- cloud-in-cell weights, src/dense.cpp:1787-1872 --------------------------------------
+// idx0 = truncated index of the point; vals[8] in z-outer, x-inner order = weight * scalar
+TB_HD void cic_weights(const float *pt, float scalar, const GridGeom &g, int *idx0, float *vals)
+{
+  for (int d = 0; d < 3; d++) idx0[d] = phys2idx1(pt[d], g.step[d], g.gmin[d]);
+  float w[8];
+  float tot = 0.0f, v0 = 0.0f;
+  int n = 0;
+  float two_eps = fmul(2.0f, g.eps);
+  for (int dz = 0; dz < 2; dz++)
+    for (int dy = 0; dy < 2; dy++)
+      for (int dx = 0; dx < 2; dx++) {
+        int ijk[3] = {idx0[0] + dx, idx0[1] + dy, idx0[2] + dz};
+        float gp[3], p[3];
+        for (int d = 0; d < 3; d++) {
+          gp[d] = idx2phys1(ijk[d], g.step[d], g.gmin[d]);
+          p[d] = pt[d];
+          if (fabsf(fsub(p[d], gp[d])) < g.eps) p[d] = fadd(p[d], two_eps);
+        }
+        float vol = fabsf(fmul(fmul(fsub(gp[0], p[0]), fsub(gp[1], p[1])), fsub(gp[2], p[2])));
+        if (v0 == 0.0f) v0 = vol;
+        float v = fdiv(v0, vol);
+        w[n++] = v;
+        tot = fadd(tot, v);
+      }
+  for (int i = 0; i < 8; i++) vals[i] = fmul(fdiv(w[i], tot), scalar);
+}
+
+// ---- span records ----------------------------------------------------------------------------
+// One x-run of deposits in one row of one block's density array.
+//   key  = (((row << 1 | remote) << cell_bits | cell) << z_bits) | zslot      (sorted ascending)
+//   data = x0 | len << 16 | float_path << 31 | (uint64)float_bits(value) << 32
+struct KeyLayout
+{
+  int cell_bits, z_bits;
+};
+TB_HD uint64_t make_key(const KeyLayout &kl, uint64_t row, int remote, uint32_t cell, uint32_t zslot)
+{
+  return ((((row << 1) | (uint64_t)remote) << kl.cell_bits | cell) << kl.z_bits) | zslot;
+}
+TB_HD uint64_t key_row(const KeyLayout &kl, uint64_t key) { return key >> (kl.z_bits + kl.cell_bits + 1); }
+
+TB_HD uint32_t f2u(float f)
+{
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c;
+  c.f = f;
+  return c.u;
+#endif
+}
+TB_HD float u2f(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c;
+  c.u = u;
+  return c.f;
+#endif
+}
+TB_HD uint64_t make_data(int x0, int len, int float_path, float value)
+{
+  return (uint64_t)(uint32_t)x0 | ((uint64_t)(uint32_t)len << 16) | ((uint64_t)(float_path & 1) << 31) | ((uint64_t)f2u(value) << 32);
+}
+
+// The reference's accumulate step (src/dense.cpp:290,193 double path; :539 float path)
+TB_HD float accumulate(float cur, float m, float div, int float_path)
+{
+  if (float_path) return fadd(cur, fdiv(m, div));
+  return (float)((double)cur + (double)m / (double)div);
+}
+
+// Integer description of one block for the deposit logic (all boxes inclusive lo, inclusive hi):
+//   P = { idx : idx2phys(idx) inside the block's closed bounds }  (src/dense.cpp:279-284)
+//   B = the block's sub-grid [block_min_idx, block_min_idx + block_num_idx)   (BlockGridParams)
+struct BlockBox
+{
+  int p_lo[3], p_hi[3];
+  int b_lo[3], b_num[3];
+  long long row_base;    // first row id of this block
+};
+
+// Emits the records of one scan line [xa, xb] x {y} x {z} (global indices) of a cell owned by
+// block `e`.  `emit(key, data)` receives every record.  Mirrors src/dense.cpp:276-305: a point
+// whose position lies in the emitting block's closed bounds is local, otherwise it goes to every
+// other block whose closed bounds contain it; in both cases only indices inside the target's
+// sub-grid are kept (the reference writes out of bounds there).
+template <class Emit>
+TB_HD void emit_line(const BlockBox *boxes, int nblocks, int e, const KeyLayout &kl, int project, uint32_t cell,
+                     int xa, int xb, int y, int z, int float_path_local, float value, Emit &emit)
+{
+  const BlockBox &be = boxes[e];
+  bool yz_local = y >= be.p_lo[1] && y <= be.p_hi[1] && z >= be.p_lo[2] && z <= be.p_hi[2];
+  // local part: x in P_e (and inside B_e)
+  int la = xa, lb = xa - 1;
+  if (yz_local) {
+    la = xa > be.p_lo[0] ? xa : be.p_lo[0];
+    lb = xb < be.p_hi[0] ? xb : be.p_hi[0];
+  }
+  if (la <= lb) {
+    int ly = y - be.b_lo[1], lz = z - be.b_lo[2];
+    if (ly >= 0 && ly < be.b_num[1] && (project || (lz >= 0 && lz < be.b_num[2]))) {
+      int a = la > be.b_lo[0] ? la : be.b_lo[0];
+      int b = lb < be.b_lo[0] + be.b_num[0] - 1 ? lb : be.b_lo[0] + be.b_num[0] - 1;
+      if (a <= b) {
+        uint64_t row = (uint64_t)(be.row_base + (project ? (long long)ly : (long long)lz * be.b_num[1] + ly));
+        emit(make_key(kl, row, 0, cell, project ? (uint32_t)z : 0u), make_data(a - be.b_lo[0], b - a + 1, float_path_local, value));
+      }
+    }
+  }
+  if (la <= lb && la == xa && lb == xb) return; // whole line was local
+  // remote parts: the pieces of [xa, xb] outside [la, lb] (all of it when the line is not local)
+  for (int j = 0; j < nblocks; j++) {
+    if (j == e) continue;
+    const BlockBox &bj = boxes[j];
+    if (y < bj.p_lo[1] || y > bj.p_hi[1] || z < bj.p_lo[2] || z > bj.p_hi[2]) continue;
+    int ly = y - bj.b_lo[1], lz = z - bj.b_lo[2];
+    if (ly < 0 || ly >= bj.b_num[1] || (!project && (lz < 0 || lz >= bj.b_num[2]))) continue;
+    int a0 = xa > bj.p_lo[0] ? xa : bj.p_lo[0];
+    int b0 = xb < bj.p_hi[0] ? xb : bj.p_hi[0];
+    a0 = a0 > bj.b_lo[0] ? a0 : bj.b_lo[0];
+    b0 = b0 < bj.b_lo[0] + bj.b_num[0] - 1 ? b0 : bj.b_lo[0] + bj.b_num[0] - 1;
+    uint64_t row = (uint64_t)(bj.row_base + (project ? (long long)ly : (long long)lz * bj.b_num[1] + ly));
+    // pieces of [a0, b0] not in the local range [la, lb]
+    int pa[2] = {a0, a0}, pb[2] = {b0, a0 - 1};
+    if (la <= lb) {
+      pa[0] = a0; pb[0] = b0 < la - 1 ? b0 : la - 1;
+      pa[1] = a0 > lb + 1 ? a0 : lb + 1; pb[1] = b0;
+    }
+    for (int s = 0; s < 2; s++)
+      if (pa[s] <= pb[s])
+        emit(make_key(kl, row, 1, cell, project ? (uint32_t)z : 0u), make_data(pa[s] - bj.b_lo[0], pb[s] - pa[s] + 1, 0, value));
+  }
+}
+
+} // namespace tb

@@ -1,0 +1,307 @@
+// CPU single-stepping of the __host__ __device__ logic in tess2_b200/csrc/cell_core.cuh and
+// host_geom.hpp -- TEST ONLY.  It exists because the development container has no GPU: the same
+// functions the kernels call (star walk, edge circulation, Newell normals, plane tests, the
+// scan-line state machine, CIC weights, span emission, the accumulate step) are driven here in
+// the kernels' order so that logic errors show up against the oracle before a GPU run.
+// This file is never linked into libtess_b200.so and is not a fallback: the product has none.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../tess2_b200/csrc/host_geom.hpp"
+
+using namespace tb;
+
+extern "C" {
+struct emu_block_t
+{
+  int gid, num_orig_particles, num_particles;
+  const float *particles;
+  int num_tets;
+  const int *tets;
+  const int *vert_to_tet;
+  float bounds_min[3], bounds_max[3];
+  float *density;
+  long long density_capacity;
+  int block_min_idx[3], block_num_idx[3];
+  int num_grid_pts;
+};
+struct emu_params_t
+{
+  int alg, num_given_bounds;
+  float given_mins[3], given_maxs[3];
+  int project;
+  float proj_plane[3];
+  float mass, eps;
+  int glo_num_idx[3];
+  float data_mins[3], data_maxs[3], grid_phys_mins[3], grid_phys_maxs[3], grid_step_size[3];
+  double seconds;
+};
+}
+
+struct HostWS
+{
+  std::vector<int> s, u, t;
+  HostWS() : s(4096), u(1024), t(1024) {}
+  int &star(int i) { return s[i]; }
+  int &nu(int i) { return u[i]; }
+  int &nt(int i) { return t[i]; }
+};
+
+struct Rec { uint64_t key, data; };
+struct VecEmit
+{
+  std::vector<Rec> *v;
+  void operator()(uint64_t k, uint64_t d) { v->push_back(Rec{k, d}); }
+};
+
+struct BitsIn
+{
+  const std::vector<unsigned char> *bits;
+  int nx, ny;
+  bool operator()(int i, int j, int k) const { return (*bits)[((size_t)k * ny + j) * nx + i] != 0; }
+};
+
+struct LineEmit
+{
+  const std::vector<BlockBox> *boxes;
+  KeyLayout kl;
+  int project, e;
+  uint32_t cell;
+  const int *lo;
+  float value;
+  VecEmit *emit; // null: count only
+  int nrec;
+  void operator()(int yi, int zi, int min_xi, int max_xi)
+  {
+    std::vector<Rec> tmp;
+    VecEmit te{&tmp};
+    emit_line(boxes->data(), (int)boxes->size(), e, kl, project, cell, lo[0] + min_xi, lo[0] + max_xi, lo[1] + yi, lo[2] + zi, 0, value, te);
+    nrec += (int)tmp.size();
+    if (emit) for (auto &r : tmp) (*emit)(r.key, r.data);
+  }
+};
+
+extern "C" void emu_fill_vert_to_tet(int num_particles, int num_tets, const int *tets, int *v2t)
+{
+  for (int p = 0; p < num_particles; p++) v2t[p] = -1;
+  for (int t = 0; t < num_tets; t++)
+    for (int v = 0; v < 4; v++) v2t[tets[8 * t + v]] = std::max(v2t[tets[8 * t + v]], t); // atomicMax in k_vert_to_tet
+}
+
+extern "C" void emu_circumcenters(int num_tets, const int *tets, const float *particles, float *out)
+{
+  for (int t = 0; t < num_tets; t++) {
+    const int *v = &tets[8 * t];
+    circumcenter(&particles[3 * v[0]], &particles[3 * v[1]], &particles[3 * v[2]], &particles[3 * v[3]], &out[3 * t]);
+  }
+}
+
+static std::vector<float4> make_cc(int num_tets, const int *tets, const float *particles)
+{
+  std::vector<float4> cc(num_tets);
+  for (int t = 0; t < num_tets; t++) {
+    const int *v = &tets[8 * t];
+    float o[3];
+    circumcenter(&particles[3 * v[0]], &particles[3 * v[1]], &particles[3 * v[2]], &particles[3 * v[3]], o);
+    cc[t] = float4{o[0], o[1], o[2], 0.0f};
+  }
+  return cc;
+}
+
+extern "C" void emu_complete(int num_verts, int num_tets, const int *tets, const int *v2t, int *out)
+{
+  (void)num_tets;
+  HostWS ws;
+  for (int v = 0; v < num_verts; v++) {
+    if (v2t[v] < 0) { out[v] = -1; continue; }
+    int ns, nn;
+    int st = star_and_neighbors(v, v2t[v], (const int4 *)tets, ws, 4096, 1024, &ns, &nn);
+    out[v] = st == CELL_OK ? 1 : 0;
+  }
+}
+
+extern "C" void emu_volumes(int num_verts, int num_tets, const int *tets, const float *particles, const int *v2t, float *out)
+{
+  std::vector<float4> cc = make_cc(num_tets, tets, particles);
+  HostWS ws;
+  for (int v = 0; v < num_verts; v++) {
+    if (v2t[v] < 0) { out[v] = -2.0f; continue; }
+    int ns, nn;
+    int st = star_and_neighbors(v, v2t[v], (const int4 *)tets, ws, 4096, 1024, &ns, &nn);
+    if (st != CELL_OK) { out[v] = -1.0f; continue; }
+    float vol = 0.0f;
+    for (int k = 0; k < nn; k++) {
+      AreaAccum aa;
+      aa.area = 0.0f;
+      int u = ws.nu(k);
+      walk_edge_link(v, u, ws.nt(k), (const int4 *)tets, cc.data(), aa);
+      float n = 0.0f;
+      for (int d = 0; d < 3; d++) {
+        float df = fsub(particles[3 * u + d], particles[3 * v + d]);
+        n = fadd(n, fmul(df, df));
+      }
+      vol = fadd(vol, fdiv(fmul(aa.area, fsqrt(n)), 6.0f));
+    }
+    out[v] = vol;
+  }
+}
+
+extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int only_gid, const char *outfile)
+{
+  (void)outfile;
+  tessb200_dense_params p;
+  memset(&p, 0, sizeof(p));
+  p.alg = ep->alg; p.num_given_bounds = ep->num_given_bounds; p.project = ep->project;
+  p.mass = ep->mass; p.eps = ep->eps;
+  for (int d = 0; d < 3; d++) {
+    p.given_mins[d] = ep->given_mins[d]; p.given_maxs[d] = ep->given_maxs[d];
+    p.proj_plane[d] = ep->proj_plane[d]; p.glo_num_idx[d] = ep->glo_num_idx[d];
+  }
+  for (int i = 0; i < nblocks; i++)
+    for (int d = 0; d < 3; d++) {
+      if (i == 0 || blocks[i].bounds_min[d] < p.data_mins[d]) p.data_mins[d] = blocks[i].bounds_min[d];
+      if (i == 0 || blocks[i].bounds_max[d] > p.data_maxs[d]) p.data_maxs[d] = blocks[i].bounds_max[d];
+    }
+  grid_step_params(&p);
+  GridGeom g;
+  for (int d = 0; d < 3; d++) {
+    g.gmin[d] = p.grid_phys_mins[d]; g.step[d] = p.grid_step_size[d]; g.dmin[d] = p.data_mins[d]; g.dmax[d] = p.data_maxs[d];
+    g.dext_eps[d] = (p.data_maxs[d] - p.data_mins[d]) * 2.0f * FLT_EPSILON; g.gnum[d] = p.glo_num_idx[d];
+  }
+  g.eps = p.eps; g.mass = p.mass; g.project = p.project ? 1 : 0; g.alg = p.alg;
+  g.div = p.project ? g.step[0] * g.step[1] : g.step[0] * g.step[1] * g.step[2];
+
+  std::vector<BlockBox> boxes(nblocks);
+  std::vector<uint32_t> cell_base(nblocks);
+  long long row_base = 0;
+  unsigned long long cb = 0;
+  int rc = 0;
+  for (int i = 0; i < nblocks; i++) {
+    BlockBox &bx = boxes[i];
+    block_grid_params(blocks[i].bounds_min, blocks[i].bounds_max, &p, bx.b_lo, bx.b_num);
+    phys_box(blocks[i].bounds_min, blocks[i].bounds_max, &p, bx.p_lo, bx.p_hi);
+    bx.row_base = row_base;
+    long long nrows = p.project ? bx.b_num[1] : (long long)bx.b_num[1] * bx.b_num[2];
+    row_base += nrows;
+    cell_base[i] = (uint32_t)cb;
+    cb += (unsigned long long)blocks[i].num_orig_particles;
+    long long npts = nrows * bx.b_num[0];
+    for (int d = 0; d < 3; d++) { blocks[i].block_min_idx[d] = bx.b_lo[d]; blocks[i].block_num_idx[d] = bx.b_num[d]; }
+    blocks[i].num_grid_pts = (int)npts;
+    if (npts > blocks[i].density_capacity) rc = -1;
+  }
+  if (rc) return rc;
+  KeyLayout kl;
+  kl.cell_bits = ceil_log2(cb + 1);
+  kl.z_bits = p.project ? ceil_log2((unsigned long long)p.glo_num_idx[2] + 2) : 0;
+
+  std::vector<Rec> recs;
+  VecEmit emit{&recs};
+  HostWS ws;
+  for (int bi = 0; bi < nblocks; bi++) {
+    emu_block_t &b = blocks[bi];
+    if (only_gid >= 0 && b.gid != only_gid) continue;
+    std::vector<int> v2t_own;
+    const int *v2t = b.vert_to_tet;
+    if (!v2t) {
+      v2t_own.resize(b.num_particles);
+      emu_fill_vert_to_tet(b.num_particles, b.num_tets, b.tets, v2t_own.data());
+      v2t = v2t_own.data();
+    }
+    if (p.alg == TESSB200_DENSE_CIC) {
+      for (int cell = 0; cell < b.num_orig_particles; cell++) {
+        int i0[3];
+        float vals[8];
+        cic_weights(&b.particles[3 * cell], g.mass, g, i0, vals);
+        int n = 0;
+        for (int dz = 0; dz < 2; dz++)
+          for (int dy = 0; dy < 2; dy++)
+            for (int dx = 0; dx < 2; dx++, n++)
+              emit_line(boxes.data(), nblocks, bi, kl, g.project, cell_base[bi] + cell, i0[0] + dx, i0[0] + dx, i0[1] + dy, i0[2] + dz, 1, vals[n], emit);
+      }
+      continue;
+    }
+    std::vector<float4> cc = make_cc(b.num_tets, b.tets, b.particles);
+    for (int cell = 0; cell < b.num_orig_particles; cell++) {
+      if (v2t[cell] < 0) continue;
+      int ns, nn;
+      int st = star_and_neighbors(cell, v2t[cell], (const int4 *)b.tets, ws, 4096, 1024, &ns, &nn);
+      if (st != CELL_OK) continue;
+      float cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
+      bool first = true;
+      const float *site = &b.particles[3 * cell];
+      std::vector<float> planes(6 * nn);
+      bool bad = false;
+      for (int k = 0; k < nn; k++) {
+        FaceAccum fa;
+        fa.cmin = cmin; fa.cmax = cmax; fa.first_of_cell = &first;
+        int n = walk_edge_link(cell, ws.nu(k), ws.nt(k), (const int4 *)b.tets, cc.data(), fa);
+        if (n < 0) { bad = true; break; }
+        newell_term(fa.nrm, fa.prev, fa.v0);
+        newell_finish(fa.nrm, fa.v0, site);
+        for (int d = 0; d < 3; d++) { planes[6 * k + d] = fa.nrm[d]; planes[6 * k + 3 + d] = fa.v0[d]; }
+      }
+      if (bad) continue;
+      bool outside = false;
+      for (int d = 0; d < 3; d++)
+        if (cmin[d] < fsub(g.dmin[d], g.dext_eps[d]) || cmax[d] > fadd(g.dmax[d], g.dext_eps[d])) outside = true;
+      if (outside) continue;
+      int lo[3], n3[3];
+      for (int d = 0; d < 3; d++) {
+        lo[d] = phys2idx1(cmin[d], g.step[d], g.gmin[d]);
+        n3[d] = phys2idx1(cmax[d], g.step[d], g.gmin[d]) - lo[d] + 1;
+      }
+      std::vector<unsigned char> bits((size_t)n3[0] * n3[1] * n3[2]);
+      for (int k = 0; k < n3[2]; k++)
+        for (int j = 0; j < n3[1]; j++)
+          for (int i = 0; i < n3[0]; i++) {
+            float pt[3] = {fadd(idx2phys1(lo[0], g.step[0], g.gmin[0]), fmul((float)i, g.step[0])),
+                           fadd(idx2phys1(lo[1], g.step[1], g.gmin[1]), fmul((float)j, g.step[1])),
+                           fadd(idx2phys1(lo[2], g.step[2], g.gmin[2]), fmul((float)k, g.step[2]))};
+            bool pos = false, neg = false;
+            for (int f = 0; f < nn && !(pos && neg); f++) {
+              int sd = plane_side(&planes[6 * f], &planes[6 * f + 3], pt, g.eps);
+              pos |= sd > 0;
+              neg |= sd < 0;
+            }
+            bits[((size_t)k * n3[1] + j) * n3[0] + i] = !(pos && neg);
+          }
+      BitsIn inside{&bits, n3[0], n3[1]};
+      LineEmit cnt{&boxes, kl, g.project, bi, cell_base[bi] + (uint32_t)cell, lo, 0.0f, nullptr, 0};
+      int tot = scan_cell(n3[0], n3[1], n3[2], inside, cnt);
+      if (tot > 0) {
+        LineEmit le{&boxes, kl, g.project, bi, cell_base[bi] + (uint32_t)cell, lo, fdiv(g.mass, (float)tot), &emit, 0};
+        scan_cell(n3[0], n3[1], n3[2], inside, le);
+      } else {
+        int i0[3];
+        float vals[8];
+        cic_weights(site, g.mass, g, i0, vals);
+        int n = 0;
+        for (int dz = 0; dz < 2; dz++)
+          for (int dy = 0; dy < 2; dy++)
+            for (int dx = 0; dx < 2; dx++, n++)
+              emit_line(boxes.data(), nblocks, bi, kl, g.project, cell_base[bi] + cell, i0[0] + dx, i0[0] + dx, i0[1] + dy, i0[2] + dz, 0, vals[n], emit);
+      }
+    }
+  }
+  std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.key < b.key; });
+  for (int i = 0; i < nblocks; i++) memset(blocks[i].density, 0, sizeof(float) * (size_t)blocks[i].num_grid_pts);
+  for (const Rec &r : recs) {
+    long long row = (long long)key_row(kl, r.key);
+    int bi = nblocks - 1;
+    while (bi > 0 && boxes[bi].row_base > row) bi--;
+    int nx = boxes[bi].b_num[0];
+    float *dst = blocks[bi].density + (row - boxes[bi].row_base) * nx;
+    int x0 = (int)(r.data & 0xffffu), len = (int)((r.data >> 16) & 0x7fffu), fp = (int)((r.data >> 31) & 1u);
+    float m = u2f((uint32_t)(r.data >> 32));
+    for (int x = 0; x < len; x++) dst[x0 + x] = accumulate(dst[x0 + x], m, g.div, fp);
+  }
+  for (int d = 0; d < 3; d++) {
+    ep->data_mins[d] = p.data_mins[d]; ep->data_maxs[d] = p.data_maxs[d];
+    ep->grid_phys_mins[d] = p.grid_phys_mins[d]; ep->grid_phys_maxs[d] = p.grid_phys_maxs[d];
+    ep->grid_step_size[d] = p.grid_step_size[d];
+  }
+  ep->seconds = 0;
+  return 0;
+}

@@ -1,0 +1,78 @@
+"""The C-ABI library: loads, exports every symbol include/tess_b200.h declares, and fails loudly
+(no CPU fallback) when there is no CUDA device.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "tess_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tessb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_expected_entry_points():
+    from tess2_b200 import lib
+    assert header_symbols() == sorted(lib.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    from tess2_b200 import lib
+    l = lib.load()
+    for name in header_symbols():
+        assert hasattr(l, name), f"libtess_b200.so does not export {name}"
+    assert l.tessb200_version() == 1
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    # sizeof/offsetof as the C compiler sees the header vs the ctypes mirror: drift would corrupt memory
+    import subprocess
+    from tess2_b200 import lib
+    src = tmp_path / "sz.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "tess_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(tessb200_block), sizeof(tessb200_dense_params), sizeof(tessb200_dense_stats),
+         offsetof(tessb200_block, density), offsetof(tessb200_block, num_grid_pts),
+         offsetof(tessb200_dense_params, data_mins), offsetof(tessb200_dense_stats, ms_upload));
+  return 0; }''')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(lib.Block), C.sizeof(lib.DenseParams), C.sizeof(lib.DenseStats), lib.Block.density.offset,
+            lib.Block.num_grid_pts.offset, lib.DenseParams.data_mins.offset, lib.DenseStats.ms_upload.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    from tess2_b200 import lib
+    l = lib.load()
+    h = C.c_void_p()
+    rc = l.tessb200_create(C.byref(h), 0)
+    if torch.cuda.is_available():
+        assert rc == 0
+        l.tessb200_destroy(h)
+    else:
+        assert rc == -2 and not h.value            # TESSB200_ECUDA
+        assert b"no CPU fallback" in l.tessb200_last_error()
+        from tess2_b200 import Context, TessB200Error
+        with pytest.raises(TessB200Error):
+            Context(0)
+
+
+def test_product_does_not_import_the_oracle():
+    # the oracle is test infrastructure: nothing under tess2_b200/ may reference it
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "tess2_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                s = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"(from|import)\s+oracle|oracle/|libtess_oracle|libtess_ref|dense_oracle", s):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
