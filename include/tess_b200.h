@@ -108,6 +108,7 @@ typedef struct tessb200_dense_stats
   int64_t num_spans;          /* x-run records handed to the deposit kernel */
   int64_t num_tets;           /* tets handed over, all blocks */
   int64_t num_grid_pts;       /* grid points owned by this context's blocks */
+  int64_t num_kernel_launches;/* this library's own kernels launched by the run (the CUB sort passes are not counted) */
   double tot_mass;            /* sum over the final grid of value * div (== deposited mass) */
   float max_dense;            /* max over the final grid */
   float ms_upload, ms_circumcenters, ms_cells, ms_scan, ms_sort, ms_deposit, ms_exchange, ms_download;

@@ -90,7 +90,7 @@ class Checker:
 
     # ---- the dense stage ---------------------------------------------------
     def dense(self, blocks, gsize, alg=0, mass=1.0, eps=1e-4, project=False, proj_plane=(0.0, 0.0, 1.0),
-              given_bounds=None, only_gid=-1, outfile=None):
+              given_bounds=None, only_gid=-1, outfile=None, max_cells=-1):
         """blocks: list of dicts (gid, particles, num_orig, tets, bounds_min, bounds_max[, vert_to_tet]).
         Returns dict(grid=global [gz,gy,gx] (or [gy,gx] when projected... per-block arrays only),
         block_density=[...], block_min_idx, block_num_idx, params)."""
@@ -117,7 +117,7 @@ class Checker:
             for d in range(3):
                 arr[i].bounds_min[d] = float(b["bounds_min"][d])
                 arr[i].bounds_max[d] = float(b["bounds_max"][d])
-            dens = np.zeros(cap if nb * cap <= (1 << 27) else min(cap, self._block_cap(b, blocks, gs)), dtype=np.float32)
+            dens = np.zeros(cap if nb * cap <= (1 << 24) else min(cap, self._block_cap(b, blocks, gs)), dtype=np.float32)
             keep.append(dens)
             arr[i].density = _fp(dens)
             arr[i].density_capacity = len(dens)
@@ -137,7 +137,7 @@ class Checker:
         p.mass = mass
         p.eps = eps
         rc = self._f("dense")(C.byref(p), C.c_int(nb), arr, C.c_int(only_gid),
-                              outfile.encode() if outfile else None)
+                              outfile.encode() if outfile else None, C.c_int(max_cells))
         if rc != 0:
             raise RuntimeError(f"{self.prefix}dense failed: {rc}")
         out = dict(params=p, seconds=p.seconds, block_density=[], block_min_idx=[], block_num_idx=[])
@@ -162,10 +162,9 @@ class Checker:
         # generous bound on a block's sub-grid: fraction of the domain per axis, plus slack
         lo = np.min([bb["bounds_min"] for bb in blocks], axis=0).astype(np.float64)
         hi = np.max([bb["bounds_max"] for bb in blocks], axis=0).astype(np.float64)
-        ext = float(np.max(hi - lo))
         n = 1
         for d in range(3):
-            frac = (float(b["bounds_max"][d]) - float(b["bounds_min"][d])) / ext
+            frac = (float(b["bounds_max"][d]) - float(b["bounds_min"][d])) / max(float(hi[d] - lo[d]), 1e-30)
             n *= min(gs[d], int(frac * gs[d]) + 4)
         return n
 

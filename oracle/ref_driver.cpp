@@ -120,7 +120,8 @@ static void fill_dblock(DBlock *b, const ref_block_t *rb, std::vector<int> &v2t_
 // only_gid >= 0: every other block is given zero original particles (its cells are
 // skipped) -- used to time one block per OS process for the multi-core CPU baseline.
 // outfile != NULL: also run the reference's WriteGrid (dense.cpp:751-870).
-int ref_dense(ref_params_t *p, int nblocks, ref_block_t *blocks, int only_gid, const char *outfile)
+// max_cells >= 0: only the first max_cells cells of every (selected) block are visited.
+int ref_dense(ref_params_t *p, int nblocks, ref_block_t *blocks, int only_gid, const char *outfile, int max_cells)
 {
   diy::Master master;
   std::vector<DBlock *> dblocks(nblocks);
@@ -138,6 +139,8 @@ int ref_dense(ref_params_t *p, int nblocks, ref_block_t *blocks, int only_gid, c
     fill_dblock(b, &blocks[i], v2t[i]);
     if (only_gid >= 0 && blocks[i].gid != only_gid)
       b->num_orig_particles = 0;
+    if (max_cells >= 0 && b->num_orig_particles > max_cells)
+      b->num_orig_particles = max_cells; // bounded sample for the timed CPU baseline: cells [0, max_cells)
     for (int d = 0; d < 3; d++) {
       b->data_bounds.min[d] = dmin[d];
       b->data_bounds.max[d] = dmax[d];

@@ -82,6 +82,7 @@ static int fail(int code, const char *fmt, ...)
     if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? TESSB200_ENOMEM : TESSB200_ECUDA, \
                                        "%s:%d: %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
   } while (0)
+#define COUNT_LAUNCH(c, n) ((c)->launches += (n))
 #define TRY(expr)            \
   do {                       \
     int rc_ = (expr);        \
@@ -159,6 +160,7 @@ struct tessb200_ctx
   float *h_max = nullptr;
   cudaEvent_t ev[12];
   bool ran = false;
+  long long launches = 0;           // kernels launched by the current run
   tessb200_dense_params last_params;
   long long out_floats = 0;
   ~tessb200_ctx() {}
@@ -317,7 +319,7 @@ static int make_geometry(tessb200_ctx *c, tessb200_dense_params *p, Geometry *G)
       RowBlock rb;
       rb.row_base = row_base; rb.nrows = nrows; rb.out_off = out_off; rb.nx = bx.b_num[0]; rb.pad = 0;
       G->rblocks.push_back(rb);
-      out_off += (b->npts + 3) & ~3LL;
+      out_off += b->npts;
       G->nrows += (unsigned long long)nrows;
       if (bx.b_num[0] > G->nx_max) G->nx_max = bx.b_num[0];
       cell_base += (unsigned long long)b->num_orig;
@@ -412,10 +414,13 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b)
   // vert_to_tet (if not given) and circumcenters for one resident block
   if (!b->have_v2t && b->num_particles) {
     k_fill_i32<<<cdiv(b->num_particles, 256), 256, 0, c->stream>>>((int *)b->v2t.p, b->num_particles, -1);
-    if (b->num_tets) k_vert_to_tet<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (int *)b->v2t.p);
+    COUNT_LAUNCH(c, 1);
+    if (b->num_tets) { k_vert_to_tet<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (int *)b->v2t.p); COUNT_LAUNCH(c, 1); }
   }
-  if (b->num_tets)
+  if (b->num_tets) {
     k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, (float4 *)b->cc.p);
+    COUNT_LAUNCH(c, 1);
+  }
   CU(cudaGetLastError());
   return 0;
 }
@@ -440,7 +445,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   Geometry G;
   TRY(make_geometry(c, p, &G));
   cudaStream_t s = c->stream;
-  const int nloc = (int)c->blocks.size();
+  c->launches = 0;
   const int nall = (int)G.boxes.size();
   long long cells = 0, tets = 0;
   for (BlockRes *b : c->blocks) { cells += b->num_orig; tets += b->num_tets; }
@@ -496,6 +501,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
       const DevBlock &db = hblocks[i];
       if (db.num_orig == 0) continue;
       k_cell_topo<<<cdiv(db.num_orig, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, s>>>(db, i, G.g, to);
+      COUNT_LAUNCH(c, 1);
     }
     CU(cudaGetLastError());
     TRY(read_counters(c));
@@ -505,6 +511,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
       int n = (int)c->h_cnt->n_overflow;
       TRY(c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)((n + 127) & ~127)));
       k_cell_topo_big<<<cdiv(n, 128), 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>(), n, c->ws_big.as<int>());
+      COUNT_LAUNCH(c, 1);
       CU(cudaGetLastError());
       TRY(read_counters(c));
     }
@@ -515,6 +522,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells)));
     for (int attempt = 0; attempt < 2; attempt++) {
       SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
+      COUNT_LAUNCH(c, (n_small ? 1 : 0) + (n_big ? 1 : 0));
       if (n_small)
         k_cell_scan<<<cdiv(n_small, SCAN_CELLS), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), cnt, to.cap_small, c->plane_pool.as<float>(),
                                                                               c->d_blocks.as<DevBlock>(), sc, G.g, so);
@@ -544,6 +552,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
       const DevBlock &db = hblocks[i];
       if (db.num_orig == 0) continue;
       k_cic<<<cdiv(db.num_orig, 256), 256, 0, s>>>(db, i, sc, G.g, so);
+      COUNT_LAUNCH(c, 1);
     }
     CU(cudaGetLastError());
     TRY(read_counters(c));
@@ -576,6 +585,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   // deposit
   TRY(c->row_start.ensure(8 * (size_t)(G.nrows + 2)));
   TRY(c->out.ensure(sizeof(float) * (size_t)std::max<long long>(4, G.out_floats)));
+  COUNT_LAUNCH(c, 2);
   k_row_starts<<<cdiv((long long)n_spans + 1, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows,
                                                                  c->row_start.as<unsigned long long>());
   {
@@ -590,14 +600,13 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
 
   if (st) {
     // dense_stats (src/dense.cpp:1284-1333): max density and total mass, from the final grid
-    const int nb = 512;
+    const int nb = 592;  // 4 CTAs per SM
     TRY(c->stat_sum.ensure(sizeof(double) * nb));
     TRY(c->stat_max.ensure(sizeof(float) * nb));
     double tot = 0.0;
     float mx = 0.0f;
-    for (BlockRes *b : c->blocks) {
-      if (!b->npts) continue;
-      k_grid_stats<<<nb, 256, 0, s>>>(c->out.as<float>() + b->out_off, (unsigned long long)b->npts, c->stat_sum.as<double>(), c->stat_max.as<float>());
+    if (G.out_floats) {
+      k_grid_stats<<<nb, 256, 0, s>>>(c->out.as<float>(), (unsigned long long)G.out_floats, c->stat_sum.as<double>(), c->stat_max.as<float>());
       CU(cudaMemcpyAsync(c->h_sum, c->stat_sum.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
       CU(cudaMemcpyAsync(c->h_max, c->stat_max.p, sizeof(float) * nb, cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
@@ -621,6 +630,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     st->num_cic_fallback = (int64_t)c->h_cnt->n_cic_fallback;
     st->num_spans = (int64_t)n_spans;
     st->num_tets = tets;
+    st->num_kernel_launches = c->launches;
     st->num_grid_pts = 0;
     for (BlockRes *b : c->blocks) st->num_grid_pts += b->npts;
     auto ms = [&](int a, int b) { float m = 0; cudaEventElapsedTime(&m, c->ev[a], c->ev[b]); return m; };

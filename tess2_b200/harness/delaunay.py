@@ -37,7 +37,7 @@ def _circumspheres64(p, simplices):
     return d + rel, np.sqrt(np.einsum("ij,ij->i", rel, rel))
 
 
-def tessellate_block(points, owner, gid, bmin, bmax, dmin, dmax, margin0=None, max_rounds=6):
+def tessellate_block(points, owner, gid, bmin, bmax, dmin, dmax, margin0=None, max_rounds=3, max_growth=2.5):
     """Delaunay of block gid's originals + ghosts.  Returns dict(particles f32 [n,3] originals
     first, num_orig, tets int32 [T,8], margin, rounds)."""
     from scipy.spatial import Delaunay
@@ -90,9 +90,9 @@ def tessellate_block(points, owner, gid, bmin, bmax, dmin, dmax, margin0=None, m
         hi_cap = dmax - bmax
         req = max(float(np.minimum(lo_need, lo_cap).max(initial=0.0)),
                   float(np.minimum(hi_need, hi_cap).max(initial=0.0)), 2.0 * margin if grow else 0.0)
-        if req <= margin:
+        if req <= margin or margin >= max_growth * margin0:
             break
-        margin = req * 1.05
+        margin = min(req * 1.05, max_growth * margin0)
     tets = np.ascontiguousarray(np.concatenate([simp, nbr], axis=1).astype(np.int32))
     return dict(gid=gid, particles=np.ascontiguousarray(allp), num_orig=n_orig, tets=tets,
                 margin=margin, rounds=rounds,
@@ -105,13 +105,14 @@ _G = {}
 def _worker(gid):
     g = _G
     mn, mx = g["bounds"][gid]
-    return tessellate_block(g["points"], g["owner"], gid, mn, mx, g["dmin"], g["dmax"], g["margin0"])
+    return tessellate_block(g["points"], g["owner"], gid, mn, mx, g["dmin"], g["dmax"], g["margin0"],
+                            max_growth=g.get("max_growth", 2.5))
 
 
-def tessellate(points, owner, bounds, domain_min, domain_max, workers=None, margin0=None):
+def tessellate(points, owner, bounds, domain_min, domain_max, workers=None, margin0=None, max_growth=2.5):
     """Tessellate every block (one process per block, up to `workers`)."""
     nblocks = len(bounds)
-    _G.update(points=points, owner=owner, bounds=bounds, dmin=domain_min, dmax=domain_max, margin0=margin0)
+    _G.update(points=points, owner=owner, bounds=bounds, dmin=domain_min, dmax=domain_max, margin0=margin0, max_growth=max_growth)
     if workers is None:
         workers = min(nblocks, os.cpu_count() or 1)
     if workers <= 1 or nblocks == 1:
@@ -119,3 +120,15 @@ def tessellate(points, owner, bounds, domain_min, domain_max, workers=None, marg
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
         return pool.map(_worker, range(nblocks), chunksize=1)
+
+
+def tessellate_gids(gids, workers=None):
+    """Tessellate the given gids using the shared state already placed in _G (bounds keyed by gid)."""
+    gids = list(gids)
+    if workers is None:
+        workers = min(len(gids), os.cpu_count() or 1)
+    if workers <= 1 or len(gids) == 1:
+        return [_worker(g) for g in gids]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        return pool.map(_worker, gids, chunksize=1)

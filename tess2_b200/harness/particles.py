@@ -24,6 +24,25 @@ def _glibc():
 
 
 RAND_MAX = 2147483647
+_crand = None
+
+
+def _rand_stream(seed, n):
+    """n values of glibc rand() after srand(seed): through the small C helper crand.c when it has
+    been built (build() does), else one ctypes call per value."""
+    global _crand
+    import os
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_crand.so")
+    if _crand is None and os.path.exists(so):
+        _crand = ctypes.CDLL(so)
+        _crand.crand_fill.argtypes = [ctypes.c_uint, ctypes.c_longlong, ctypes.c_void_p]
+    if _crand is not None:
+        out = np.empty(n, dtype=np.int32)
+        _crand.crand_fill(seed, n, out.ctypes.data)
+        return out.astype(np.int64)
+    libc = _glibc()
+    libc.srand(seed)
+    return np.fromiter((libc.rand() for _ in range(n)), dtype=np.int64, count=n)
 
 
 def gen_particles(gid, bounds_min, bounds_max):
@@ -32,9 +51,7 @@ def gen_particles(gid, bounds_min, bounds_max):
     bmax = np.asarray(bounds_max, dtype=np.float32)
     sizes = [int(np.float32(bmax[i] - bmin[i]) + np.float32(1)) for i in range(3)]
     n = sizes[0] * sizes[1] * sizes[2]
-    libc = _glibc()
-    libc.srand(gid)
-    r = np.fromiter((libc.rand() for _ in range(3 * n)), dtype=np.int64, count=3 * n)
+    r = _rand_stream(gid, 3 * n)
     # (float)rand() / RAND_MAX : int -> float (rounded), RAND_MAX -> float (2^31), float division
     t = r.astype(np.float32) / np.float32(RAND_MAX)
     t = t.reshape(n, 3)

@@ -59,7 +59,7 @@ class DenseStats(C.Structure):
         ("num_cells", C.c_int64), ("num_no_tet", C.c_int64), ("num_incomplete", C.c_int64),
         ("num_outside", C.c_int64), ("num_deposit_cells", C.c_int64), ("num_cic_fallback", C.c_int64),
         ("num_slow_cells", C.c_int64), ("num_spans", C.c_int64), ("num_tets", C.c_int64),
-        ("num_grid_pts", C.c_int64), ("tot_mass", C.c_double), ("max_dense", C.c_float),
+        ("num_grid_pts", C.c_int64), ("num_kernel_launches", C.c_int64), ("tot_mass", C.c_double), ("max_dense", C.c_float),
         ("ms_upload", C.c_float), ("ms_circumcenters", C.c_float), ("ms_cells", C.c_float),
         ("ms_scan", C.c_float), ("ms_sort", C.c_float), ("ms_deposit", C.c_float),
         ("ms_exchange", C.c_float), ("ms_download", C.c_float), ("ms_total_device", C.c_float),

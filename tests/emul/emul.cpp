@@ -147,9 +147,10 @@ extern "C" void emu_volumes(int num_verts, int num_tets, const int *tets, const 
   }
 }
 
-extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int only_gid, const char *outfile)
+extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int only_gid, const char *outfile, int max_cells)
 {
   (void)outfile;
+  (void)max_cells;
   tessb200_dense_params p;
   memset(&p, 0, sizeof(p));
   p.alg = ep->alg; p.num_given_bounds = ep->num_given_bounds; p.project = ep->project;

@@ -1,0 +1,213 @@
+"""Parity of the CUDA path (through the C ABI, include/tess_b200.h) with the oracle on the same
+inputs.  The bar: bit-exact for indices / flags; for fp32 results the tolerance north_star states
+is 1e-5 relative -- the arithmetic is kept in the reference's order without FMA, so the tests ask
+for bit equality and report the relative error if that ever fails."""
+import hashlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import dataset, assert_same_bits
+from golden_util import load_small, load_c1
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: cell volumes, densities and grid values within 1e-5 relative (fp32)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import tess2_b200
+    c = tess2_b200.Context(0)
+    yield c
+    c.close()
+
+
+def run_gpu(ctx, blocks, gs, alg=0, project=False, given_bounds=None, eps=1e-4, mass=1.0):
+    ng = 0 if given_bounds is None else 3
+    gmin = given_bounds[0] if given_bounds else None
+    gmax = given_bounds[1] if given_bounds else None
+    return ctx.dense(alg, ng, gmin, gmax, project, (0.0, 0.0, 1.0), mass, eps, gs, blocks)
+
+
+def compare_dense(res, o, what):
+    assert res.block_min_idx == o["block_min_idx"], what
+    assert res.block_num_idx == o["block_num_idx"], what
+    assert_same_bits(res.grid_step_size, o["step"], what + " step")
+    assert_same_bits(res.grid_phys_mins, o["grid_phys_mins"], what + " grid_phys_mins")
+    for i, (d1, d2) in enumerate(zip(res.block_density, o["block_density"])):
+        assert_same_bits(d1, d2, f"{what} block {i}")
+    if res.grid is not None:
+        assert_same_bits(res.grid, o["grid"], what + " global grid")
+
+
+# ---- per-tet / per-site ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "clump8", "tiny"])
+def test_vert_to_tet_circumcenters_volumes(ctx, port, name):
+    for b in dataset(name)[:2]:
+        n = len(b["particles"])
+        assert np.array_equal(ctx.fill_vert_to_tet(n, b["tets"]), b["vert_to_tet"])
+        assert_same_bits(ctx.fill_circumcenters(b["tets"], b["particles"]), port.circumcenters(b["tets"], b["particles"]), "circumcenters")
+        comp, vol, den = ctx.cell_volumes(n, b["tets"], b["particles"], b["vert_to_tet"])
+        assert np.array_equal(comp, port.complete(n, b["tets"], b["vert_to_tet"]))
+        ref_vol = port.volumes(n, b["tets"], b["particles"], b["vert_to_tet"])
+        assert_same_bits(vol, ref_vol, "volumes")
+        fin = ref_vol > 0
+        assert np.allclose(den[fin], 1.0 / ref_vol[fin], rtol=TOL, atol=0)
+        # vert_to_tet recomputed on the device when NULL
+        comp2, vol2, _ = ctx.cell_volumes(n, b["tets"], b["particles"], None)
+        assert np.array_equal(comp2, comp) and np.array_equal(vol2.view(np.uint32), vol.view(np.uint32))
+
+
+# ---- the dense stage -----------------------------------------------------------------------------
+@pytest.mark.parametrize("name,gs", [("c1", (64, 64, 64)), ("u16x8", (32, 32, 32)), ("clump8", (48, 48, 48)),
+                                     ("aniso", (40, 28, 17)), ("tiny", (8, 8, 8))])
+@pytest.mark.parametrize("alg", [0, 1])
+@pytest.mark.parametrize("project", [False, True])
+def test_dense_matches_oracle(ctx, port, name, gs, alg, project):
+    blocks = dataset(name)
+    o = port.dense(blocks, gs, alg=alg, project=project)
+    res = run_gpu(ctx, blocks, gs, alg=alg, project=project)
+    compare_dense(res, o, f"{name} alg{alg} proj{project}")
+
+
+def test_dense_matches_golden_small(ctx):
+    z, blocks, gs = load_small()
+    for alg in (0, 1):
+        for proj in (0, 1):
+            res = run_gpu(ctx, blocks, gs, alg=alg, project=bool(proj))
+            for i in range(len(blocks)):
+                assert res.block_min_idx[i] == list(z[f"alg{alg}_proj{proj}_b{i}_min_idx"])
+                assert_same_bits(res.block_density[i], z[f"alg{alg}_proj{proj}_b{i}_density"], f"golden alg{alg} proj{proj} block {i}")
+            # WriteGrid: same bytes as the reference's MPI-IO writer produced
+            with tempfile.TemporaryDirectory() as td:
+                import tess2_b200
+                f = os.path.join(td, "dense.raw")
+                tess2_b200.WriteGrid(f, res)
+                raw = np.fromfile(f, dtype=np.float32)
+            assert_same_bits(raw, z[f"alg{alg}_proj{proj}_raw"], f"dense.raw alg{alg} proj{proj}")
+
+
+def test_dense_matches_golden_config1(ctx):
+    c1 = load_c1()
+    blk = dataset("c1")[0]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    if sha(blk["tets"]) != str(c1["tets_sha"]):
+        pytest.skip("this SciPy/Qhull produced different tets than the fixture's")
+    assert sha(ctx.fill_circumcenters(blk["tets"], blk["particles"])) == str(c1["cc_sha"])
+    assert sha(ctx.cell_volumes(blk["num_orig"], blk["tets"], blk["particles"], blk["vert_to_tet"])[1]) == str(c1["volume_sha"])
+    for alg in (0, 1):
+        res = run_gpu(ctx, [blk], (64, 64, 64), alg=alg)
+        assert sha(res.grid.reshape(-1)) == str(c1[f"alg{alg}_grid_sha"])
+
+
+def test_vert_to_tet_null_and_given_bounds(ctx, port):
+    blocks = [dict(b) for b in dataset("u16x8")]
+    for b in blocks:
+        b.pop("vert_to_tet")
+    gb = ([-1.0, -2.0, -0.5], [17.0, 16.5, 15.5])
+    for alg in (0, 1):
+        o = port.dense(blocks, (30, 26, 22), alg=alg, given_bounds=gb, eps=1e-3, mass=2.5)
+        res = run_gpu(ctx, blocks, (30, 26, 22), alg=alg, given_bounds=gb, eps=1e-3, mass=2.5)
+        compare_dense(res, o, f"given bounds alg{alg}")
+
+
+def test_stats_and_mass_conservation(ctx, port):
+    blk = dataset("c1")[0]
+    res = run_gpu(ctx, [blk], (64, 64, 64))
+    st = res.stats
+    comp = port.complete(blk["num_orig"], blk["tets"], blk["vert_to_tet"])
+    assert st.num_cells == blk["num_orig"]
+    assert st.num_incomplete == int((comp == 0).sum())
+    assert st.num_no_tet == int((comp == -1).sum())
+    assert st.num_deposit_cells + st.num_outside + st.num_incomplete + st.num_no_tet == st.num_cells
+    # total deposited mass == number of depositing cells (mass 1), to 1e-6 (north_star)
+    assert abs(st.tot_mass - st.num_deposit_cells) <= 1e-6 * st.num_deposit_cells
+    tot = res.grid.astype(np.float64).sum() * float(res.div)
+    assert abs(tot - st.num_deposit_cells) <= 1e-6 * st.num_deposit_cells
+    assert st.max_dense == res.grid.max()
+    assert st.num_tets == len(blk["tets"])
+
+
+def test_big_cells_and_many_faces(ctx, port):
+    # sparse particles on a fine grid: every index box exceeds the shared-memory scan kernel's
+    # 2048-point limit, so the large-cell kernel does the work
+    from tess2_b200.harness import particles, decomp, delaunay
+    dom = ([0, 0, 0], [7, 7, 7])
+    p = particles.uniform_particles(300, *dom, seed=3)
+    b = decomp.regular_blocks(*dom, 1)
+    blocks = delaunay.tessellate(p, decomp.assign_regular(p, b), b, *dom, workers=1)
+    o = port.dense(blocks, (96, 96, 96))
+    res = run_gpu(ctx, blocks, (96, 96, 96))
+    assert res.stats.num_slow_cells > 0
+    compare_dense(res, o, "big cells")
+    # a site with a very large star: points on a sphere around a centre (degenerate, many faces)
+    rng = np.random.default_rng(9)
+    v = rng.standard_normal((400, 3))
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    shell = (4.0 + 1.5 * v * (1 + 1e-3 * rng.standard_normal((400, 1)))).astype(np.float32)
+    outer = (4.0 + 3.4 * v[:200]).astype(np.float32)
+    pts = np.concatenate([[[4.0, 4.0, 4.0]], shell, outer]).astype(np.float32)
+    blocks = delaunay.tessellate(pts, np.zeros(len(pts), np.int32), [(np.zeros(3, np.float32), np.full(3, 8, np.float32))],
+                                 [0, 0, 0], [8, 8, 8], workers=1)
+    o = port.dense(blocks, (40, 40, 40))
+    res = run_gpu(ctx, blocks, (40, 40, 40))
+    compare_dense(res, o, "large star")
+    comp, vol, _ = ctx.cell_volumes(len(pts), blocks[0]["tets"], blocks[0]["particles"], None)
+    assert_same_bits(vol, port.volumes(len(pts), blocks[0]["tets"], blocks[0]["particles"],
+                                        port.fill_vert_to_tet(len(pts), blocks[0]["tets"])), "large star volume")
+
+
+def test_edge_cases(ctx):
+    import tess2_b200
+    # a block with particles but no tets, next to a normal block: nothing deposits from it
+    blocks = [dict(b) for b in dataset("u16x8")]
+    blocks[3] = dict(blocks[3], tets=np.zeros((0, 8), np.int32), vert_to_tet=None)
+    res = run_gpu(ctx, blocks, (32, 32, 32))
+    assert res.stats.num_no_tet >= blocks[3]["num_orig"]
+    assert np.isfinite(res.grid).all()
+    # bad arguments come back as error codes, not crashes
+    with pytest.raises(tess2_b200.TessB200Error):
+        run_gpu(ctx, blocks, (1, 32, 32))
+    with pytest.raises(tess2_b200.TessB200Error):
+        ctx.dense(7, 0, None, None, False, None, 1.0, 1e-4, (32, 32, 32), blocks)
+    with pytest.raises(tess2_b200.TessB200Error):
+        ctx.dense(0, 0, None, None, True, (1.0, 0.0, 0.0), 1.0, 1e-4, (32, 32, 32), blocks)
+
+
+def test_repeatability(ctx):
+    # two runs on the same inputs give the same bytes (no atomics on values, ordered accumulation)
+    blocks = dataset("clump8")
+    a = run_gpu(ctx, blocks, (48, 48, 48))
+    b = run_gpu(ctx, blocks, (48, 48, 48))
+    assert_same_bits(a.grid, b.grid, "repeatability")
+
+
+def test_full_size_properties(ctx, port):
+    """BASELINE config 2 shape at a size the CPU can still tessellate in the test budget
+    (64^3 particles in 8 regular blocks -> 128^3 grid): size-independent properties + a sampled
+    comparison with the oracle on one block."""
+    from tess2_b200.harness import particles, decomp, delaunay
+    n = int(os.environ.get("TESSB200_TEST_N", "64"))
+    dom = ([0, 0, 0], [n - 1] * 3)
+    b = decomp.regular_blocks(*dom, 8)
+    ps = [particles.gen_particles(g, mn, mx) for g, (mn, mx) in enumerate(b)]
+    allp = np.concatenate(ps)
+    owner = np.concatenate([np.full(len(q), g, np.int32) for g, q in enumerate(ps)])
+    blocks = delaunay.tessellate(allp, owner, b, *dom)
+    gs = (2 * n, 2 * n, 2 * n)
+    res = run_gpu(ctx, blocks, gs)
+    st = res.stats
+    assert abs(st.tot_mass - st.num_deposit_cells) <= 1e-6 * st.num_deposit_cells
+    assert st.num_deposit_cells > 0.9 * st.num_cells
+    # CIC conserves all mass that lands inside the grid
+    cic = run_gpu(ctx, blocks, gs, alg=1)
+    assert abs(cic.stats.tot_mass - st.num_cells) <= 1e-4 * st.num_cells
+    # linearity in the particle mass: exactly 2x for a power-of-two factor
+    res2 = run_gpu(ctx, blocks, gs, mass=2.0)
+    assert_same_bits(res2.grid, (res.grid * np.float32(2.0)).astype(np.float32), "linearity in mass")
+    # the oracle on the same inputs (a few seconds per block): bit equality of the whole grid
+    o = port.dense(blocks, gs)
+    compare_dense(res, o, "config-2 shape")
