@@ -153,7 +153,7 @@ struct tessb200_ctx
 #ifdef TESSB200_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
-  Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
+  Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
   Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data;
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
@@ -190,7 +190,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   CU(cudaMallocHost(&c->h_max, sizeof(float) * 1024));
   for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
   CU(cudaFuncSetAttribute(k_cell_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
-  CU(cudaFuncSetAttribute(k_cell_topo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
   CU(cudaFuncSetAttribute(k_cell_volumes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
   *out = c;
   return 0;
@@ -211,7 +211,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_blocks(c);
-  Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
+  Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
                  &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data};
   for (Buf *b : bufs) b->release();
@@ -486,6 +486,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     CU(cudaEventRecord(c->ev[4], s));
     // K3a part 1
     TRY(c->plane_pool.ensure(48 * ((size_t)2 * tets + (size_t)cells + 64)));   // sum of faces <= 4 T
+    TRY(c->face_list.ensure(32 * ((size_t)2 * tets + (size_t)cells + 64)));
     TRY(c->hdr_small.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
     TRY(c->hdr_big.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
     TRY(c->big_bitoff.ensure(8 * (size_t)std::max<long long>(1, cells)));
@@ -494,13 +495,13 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     TopoOut to;
     to.small = c->hdr_small.as<CellHdr>(); to.big = c->hdr_big.as<CellHdr>();
     to.big_bit_off = c->big_bitoff.as<unsigned long long>();
-    to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.cnt = cnt;
+    to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.faces = c->face_list.as<FaceRef>(); to.cnt = cnt;
     to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
     for (int i = 0; i < nall; i++) {
       if (G.local_of[i] < 0) continue;
       const DevBlock &db = hblocks[i];
       if (db.num_orig == 0) continue;
-      k_cell_topo<<<cdiv(db.num_orig, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, s>>>(db, i, G.g, to);
+      k_cell_bfs<<<cdiv(db.num_orig, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, s>>>(db, i, G.g, to);
       COUNT_LAUNCH(c, 1);
     }
     CU(cudaGetLastError());
@@ -509,11 +510,17 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     long long n_slow = c->h_cnt->n_overflow;
     if (c->h_cnt->n_overflow) {
       int n = (int)c->h_cnt->n_overflow;
-      TRY(c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)((n + 127) & ~127)));
-      k_cell_topo_big<<<cdiv(n, 128), 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>(), n, c->ws_big.as<int>());
+      TRY(c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)n));
+      k_cell_bfs_big<<<cdiv((long long)n * 32, 128), 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>(), n, c->ws_big.as<int>());
       COUNT_LAUNCH(c, 1);
       CU(cudaGetLastError());
       TRY(read_counters(c));
+    }
+    if (c->h_cnt->plane_cursor) {
+      k_cell_faces<<<cdiv((long long)c->h_cnt->plane_cursor * 2, 256), 256, 0, s>>>(c->face_list.as<FaceRef>(), cnt, c->d_blocks.as<DevBlock>(),
+                                                                                 c->plane_pool.as<float>(), cnt);
+      COUNT_LAUNCH(c, 1);
+      CU(cudaGetLastError());
     }
     CU(cudaEventRecord(c->ev[5], s));
     const unsigned n_small = c->h_cnt->n_small, n_big = c->h_cnt->n_big;
@@ -524,7 +531,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
       SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
       COUNT_LAUNCH(c, (n_small ? 1 : 0) + (n_big ? 1 : 0));
       if (n_small)
-        k_cell_scan<<<cdiv(n_small, SCAN_CELLS), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), cnt, to.cap_small, c->plane_pool.as<float>(),
+        k_cell_scan<<<cdiv(n_small, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), cnt, to.cap_small, c->plane_pool.as<float>(),
                                                                               c->d_blocks.as<DevBlock>(), sc, G.g, so);
       if (n_big)
         k_cell_scan_big<<<n_big, 128, 0, s>>>(c->hdr_big.as<CellHdr>(), c->big_bitoff.as<unsigned long long>(), (int)n_big, c->plane_pool.as<float>(),

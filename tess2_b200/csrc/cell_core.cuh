@@ -211,6 +211,173 @@ TB_HD int star_and_neighbors(int site, int t0, const int4 *tets, WS &ws, int sta
   return CELL_OK;
 }
 
+// Same result as star_and_neighbors (same BFS order, same first-seen tets), but the two
+// "already seen?" questions are answered by 64-slot open-addressing byte tables instead of linear
+// searches (57% of k_cell_topo's instructions in the first profile, profiles/r01_*).  The tables
+// hold indices into star() / nu(); 0xFF = empty.  Requires star_cap, nbr_cap < 64.
+//   ws.vis_hash(h), ws.nbr_hash(h): uint8 slots;  ws.nt_idx(i): uint8 index into star() of the tet
+//   where nu(i) was first seen;  ws.hash_clear() empties both tables.
+template <class WS>
+TB_HD int hash_find_or_insert(WS &ws, bool vertex_table, int key, int *count, int cap)
+{
+  unsigned h = ((unsigned)key * 0x9E3779B1u) >> 26;
+  for (;;) {
+    unsigned idx = vertex_table ? ws.nbr_hash(h) : ws.vis_hash(h);
+    if (idx == 0xFFu) {
+      if (*count >= cap) return -1;
+      if (vertex_table) { ws.nbr_hash(h) = (unsigned char)*count; ws.nu(*count) = key; }
+      else { ws.vis_hash(h) = (unsigned char)*count; ws.star(*count) = key; }
+      (*count)++;
+      return 1;
+    }
+    int have = vertex_table ? ws.nu((int)idx) : ws.star((int)idx);
+    if (have == key) return 0;
+    h = (h + 1u) & 63u;
+  }
+}
+
+// In a manifold star the tet popped at `head` shares with its BFS parent the face opposite the slot
+// whose neighbour is the parent; the other vertices of that face were recorded when the parent was
+// popped, so only the vertex AT that slot can be new, and the parent itself needs no visited test.
+// That halves the table operations (3 instead of 6 per popped tet).  ws.parent_idx(i): uint8 index
+// into star() of the tet from which star(i) was first pushed.
+template <class WS>
+TB_HD int star_and_neighbors_hashed(int site, int t0, const int4 *tets, WS &ws, int star_cap, int nbr_cap, int *n_star, int *n_nbr)
+{
+  ws.hash_clear();
+  int ns = 0, nn = 0;
+  hash_find_or_insert(ws, false, t0, &ns, star_cap);
+  for (int head = 0; head < ns; head++) {
+    int t = ws.star(head);
+    int4 v = tets[2 * (size_t)t];
+    int4 nb = tets[2 * (size_t)t + 1];
+    int vv[4] = {v.x, v.y, v.z, v.w};
+    int bb[4] = {nb.x, nb.y, nb.z, nb.w};
+    const int par = head ? ws.star((int)ws.parent_idx(head)) : -2;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int u = vv[i];
+      if (u == site) continue;
+      int next = bb[i];
+      const bool to_parent = next == par;
+      if (head == 0 || to_parent) {
+        int before = nn;
+        int r = hash_find_or_insert(ws, true, u, &nn, nbr_cap);
+        if (r < 0) return CELL_OVERFLOW;
+        if (r > 0) ws.nt_idx(before) = (unsigned char)head;
+      }
+      if (next < 0) return CELL_INCOMPLETE;
+      if (to_parent) continue;
+      int before_s = ns;
+      int r2 = hash_find_or_insert(ws, false, next, &ns, star_cap);
+      if (r2 < 0) return CELL_OVERFLOW;
+      if (r2 > 0) ws.parent_idx(before_s) = (unsigned char)head;
+    }
+  }
+  *n_star = ns;
+  *n_nbr = nn;
+  return CELL_OK;
+}
+
+TB_HD int tb_clz(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+TB_HD int tb_ffs(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x);
+#else
+  return __builtin_ffs((int)x);
+#endif
+}
+
+// The BFS of k_cell_bfs: same order and same (u, first tet) pairs as star_and_neighbors_hashed,
+// restructured so that every popped tet runs the SAME three table operations (one vertex, two
+// tets) -- the lanes of a warp stay converged -- and the cell's bounding box is accumulated on
+// the way: the vertices of all Voronoi faces of the cell are exactly the circumcenters of the
+// star's tets, so min/max over the star equals the face loop of CellBounds (src/dense.cpp:700-714).
+// A star that is not a manifold around `site` (no slot leads back to the BFS parent) is reported
+// as CELL_OVERFLOW, which reroutes the cell to the general (linear-search) kernel.
+TB_HD int tb_sel4(int a, int b, int c, int d, int s) { return s == 0 ? a : (s == 1 ? b : (s == 2 ? c : d)); }
+
+template <class WS>
+TB_HD int star_bfs_uniform(int site, int t0, const int4 *tets, const float4 *cc, WS &ws, int star_cap, int nbr_cap,
+                           int *n_star, int *n_nbr, float *cmin, float *cmax)
+{
+  ws.hash_clear();
+  int ns = 0, nn = 0;
+  hash_find_or_insert(ws, false, t0, &ns, star_cap);
+  {
+    // root: its three non-site vertices are new, its three neighbours are pushed in slot order
+    int4 v = tets[2 * (size_t)t0];
+    int4 nb = tets[2 * (size_t)t0 + 1];
+    float4 c = cc[t0];
+    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
+    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+    int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
+    if (is < 0) return CELL_OVERFLOW;
+    for (int q = 0; q < 3; q++) {
+      int s = q + (q >= is ? 1 : 0);
+      int u = tb_sel4(v.x, v.y, v.z, v.w, s);
+      int next = tb_sel4(nb.x, nb.y, nb.z, nb.w, s);
+      int before = nn;
+      int r = hash_find_or_insert(ws, true, u, &nn, nbr_cap);
+      if (r < 0) return CELL_OVERFLOW;
+      if (r > 0) ws.nt_idx(before) = 0;
+      if (next < 0) return CELL_INCOMPLETE;
+      int before_s = ns;
+      int r2 = hash_find_or_insert(ws, false, next, &ns, star_cap);
+      if (r2 < 0) return CELL_OVERFLOW;
+      if (r2 > 0) ws.parent_idx(before_s) = 0;
+    }
+  }
+  for (int head = 1; head < ns; head++) {
+    int t = ws.star(head);
+    int4 v = tets[2 * (size_t)t];
+    int4 nb = tets[2 * (size_t)t + 1];
+    float4 c = cc[t];
+    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
+    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+    const int par = ws.star((int)ws.parent_idx(head));
+    const int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
+    const int ip = nb.x == par ? 0 : (nb.y == par ? 1 : (nb.z == par ? 2 : (nb.w == par ? 3 : -1)));
+    if (is < 0 || ip < 0 || is == ip) return CELL_OVERFLOW;
+    // the only vertex that can be new: the one opposite the face shared with the parent
+    {
+      int u = tb_sel4(v.x, v.y, v.z, v.w, ip);
+      int before = nn;
+      int r = hash_find_or_insert(ws, true, u, &nn, nbr_cap);
+      if (r < 0) return CELL_OVERFLOW;
+      if (r > 0) ws.nt_idx(before) = (unsigned char)head;
+    }
+    // the two other neighbours, in slot order
+    unsigned m = 0xFu & ~(1u << is) & ~(1u << ip);
+    const int s1 = tb_ffs(m) - 1;
+    m &= m - 1u;
+    const int s2 = tb_ffs(m) - 1;
+    const int n1 = tb_sel4(nb.x, nb.y, nb.z, nb.w, s1), n2 = tb_sel4(nb.x, nb.y, nb.z, nb.w, s2);
+    if (n1 < 0 || n2 < 0) return CELL_INCOMPLETE;
+    {
+      int before_s = ns;
+      int r = hash_find_or_insert(ws, false, n1, &ns, star_cap);
+      if (r < 0) return CELL_OVERFLOW;
+      if (r > 0) ws.parent_idx(before_s) = (unsigned char)head;
+      before_s = ns;
+      r = hash_find_or_insert(ws, false, n2, &ns, star_cap);
+      if (r < 0) return CELL_OVERFLOW;
+      if (r > 0) ws.parent_idx(before_s) = (unsigned char)head;
+    }
+  }
+  *n_star = ns;
+  *n_nbr = nn;
+  return CELL_OK;
+}
+
 #define TB_MAX_LINK 4096
 
 // Walks the tets around Delaunay edge (site, u) starting at ut, in the reference's order
@@ -250,18 +417,15 @@ TB_HD int walk_edge_link(int site, int u, int ut, const int4 *tets, const float4
 struct FaceAccum
 {
   float nrm[3], v0[3], prev[3];
-  float *cmin, *cmax;
-  bool *first_of_cell;
+  float *cmin, *cmax;   // running bbox of the cell (+inf / -inf to start), or null when the caller has it already
   TB_HD void operator()(int k, const float4 &c)
   {
     float cur[3] = {c.x, c.y, c.z};
-    if (*first_of_cell) {
-      for (int d = 0; d < 3; d++) { cmin[d] = cur[d]; cmax[d] = cur[d]; }
-      *first_of_cell = false;
-    } else {
+    // `if (vv < cell_min) cell_min = vv` (src/dense.cpp:701-714) == fminf for non-NaN vertices
+    if (cmin) {
       for (int d = 0; d < 3; d++) {
-        if (cur[d] < cmin[d]) cmin[d] = cur[d];
-        if (cur[d] > cmax[d]) cmax[d] = cur[d];
+        cmin[d] = fminf(cmin[d], cur[d]);
+        cmax[d] = fmaxf(cmax[d], cur[d]);
       }
     }
     if (k == 0) {
@@ -356,6 +520,79 @@ TB_HD int scan_cell(int nx, int ny, int nz, Inside &inside, Line &line)
         int yj;
         for (yj = first_y; yj > 0; yj--)
           if (!inside(first_x, yj, zi + 1)) break;
+        y_start = yj;
+      }
+      if (z_step_done) break;
+    }
+  }
+  return tot;
+}
+
+// The same state machine for index boxes at most 32 points wide, on whole scan lines:
+// `row(j,k)` returns the inside-bits of line (j,k) (bit i = PtInCell of point (i,j,k)); the two
+// x-walks of the reference become find-first-set / count-leading-zeros on masked copies of the row.
+template <class Row, class Line>
+TB_HD int scan_cell_bits(int nx, int ny, int nz, Row &row, Line &line)
+{
+  int tot = 0;
+  int x_left = nx / 2, x_right = nx / 2, y_start = 0, first_x = 0;
+  const uint32_t full = nx >= 32 ? 0xffffffffu : ((1u << nx) - 1u);
+  for (int zi = 0; zi < nz; zi++) {
+    bool border_found = false, z_step_done = false;
+    for (int yi = y_start; yi < ny; yi++) {
+      const uint32_t b = row(yi, zi) & full;
+      const bool x_in = (b >> x_left) & 1u;          // the reference's single test at x_left (src/dense.cpp:1530-1542)
+      int min_xi = nx - 1, max_xi = 0;
+      const uint32_t below_left = (1u << x_left) - 1u;        // bits < x_left
+      const uint32_t upto_right = (2u << x_right) - 1u;       // bits <= x_right
+      if (x_in) {
+        // left walk: inside from x_left downwards until the first outside point (src/dense.cpp:1547-1582)
+        const uint32_t zb = ~b & below_left;
+        int lo_rec = 0;
+        const int old_left = x_left;
+        if (zb) { int stop = 31 - tb_clz(zb); lo_rec = stop + 1; x_left = stop; }
+        if (lo_rec < min_xi) min_xi = lo_rec;
+        if (old_left > max_xi) max_xi = old_left;
+        // right walk: inside from x_right upwards until the first outside point (src/dense.cpp:1585-1620)
+        const uint32_t zr = ~b & full & ~(upto_right >> 1);   // outside points at or above x_right
+        int hi_rec = nx - 1;
+        const int old_right = x_right;
+        if (zr) { int stop = tb_ffs(zr) - 1; hi_rec = stop - 1; x_right = stop; }
+        if (hi_rec >= old_right) {
+          if (old_right < min_xi) min_xi = old_right;
+          if (hi_rec > max_xi) max_xi = hi_rec;
+        }
+      } else {
+        // left walk: outside at x_left, step up to the first inside point
+        const uint32_t ob = b & ~below_left;
+        if (ob) {
+          int xi = tb_ffs(ob) - 1;
+          if (xi < min_xi) min_xi = xi;
+          if (xi > max_xi) max_xi = xi;
+          x_left = xi;
+        }
+        // right walk: step down from x_right to the first inside point
+        const uint32_t orr = b & upto_right;
+        if (orr) {
+          int xi = 31 - tb_clz(orr);
+          if (xi < min_xi) min_xi = xi;
+          if (xi > max_xi) max_xi = xi;
+          x_right = xi;
+        }
+      }
+      bool found = min_xi <= max_xi;
+      if (found) {
+        tot += max_xi - min_xi + 1;
+        if (yi == y_start) first_x = (min_xi + max_xi) / 2;
+        line(yi, zi, min_xi, max_xi);
+      }
+      int first_y = y_start;
+      if (found && !border_found) { first_y = yi; border_found = true; }
+      if (!found && border_found) z_step_done = true;
+      if ((yi == ny - 1 || z_step_done) && zi + 1 < nz) {
+        int yj;
+        for (yj = first_y; yj > 0; yj--)
+          if (!((row(yj, zi + 1) >> first_x) & 1u)) break;
         y_start = yj;
       }
       if (z_step_done) break;

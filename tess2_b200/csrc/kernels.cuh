@@ -3,8 +3,10 @@
 //
 //   k_vert_to_tet      fill_vert_to_tet            (src/tess.cpp:767-787)
 //   k_circumcenters    fill_circumcenters          (src/volume.cpp:6-11, src/tet.cpp:37-66)
-//   k_cell_topo        complete + CellBounds + the data-bounds filter and index box of CellGridPts
-//                      (src/tet.cpp:228-270,337-409; src/dense.cpp:657-736,1381-1410)
+//   k_cell_bfs         complete + neighbor_edges + the cell bbox, data-bounds filter and index box of
+//                      CellBounds / CellGridPts (src/tet.cpp:228-270,337-378; src/dense.cpp:700-714,1381-1410)
+//   k_cell_faces       fill_edge_link + circumcenters + NewellNormal of CellBounds, one thread per face
+//                      (src/tet.cpp:389-409; src/dense.cpp:682-735,1131-1162)
 //   k_cell_scan        PtInCell over the cell's index box + CellInteriorGridPts + CIC fallback
 //                      (src/dense.cpp:1172-1203,1475-1701,1437-1455) -> span records
 //   k_cell_scan_big    same for cells with a large index box / many faces
@@ -52,12 +54,14 @@ struct Counters
   unsigned long long n_spans;                  // span records requested (may exceed capacity)
 };
 
+struct FaceRef;
 struct TopoOut
 {
   CellHdr *small, *big;
   unsigned long long *big_bit_off;
   uint2 *overflow;         // (block index, block-local cell) whose star did not fit the fast workspace
   float *plane_pool;
+  struct FaceRef *faces;   // face list, parallel to the plane pool
   Counters *cnt;
   uint32_t cap_small, cap_big, cap_overflow;
 };
@@ -149,15 +153,31 @@ __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ 
 }
 
 // ---- K3a part 1: topology + faces, one thread per cell --------------------------------------------
+// Shared-memory workspace of the fast topology kernels: word w of a thread lives at
+// base[w * STRIDE] (stride = threads per CTA, so a warp touching the same word index hits 32
+// distinct banks).  Layout in words: star[52] | nu[36] | nt_idx bytes[9] | parent_idx bytes[13] |
+// vis_hash bytes[16] | nbr_hash bytes[16]  = 142 words = 568 B per thread (3 CTAs of 128 per SM).
 template <int STRIDE>
-struct StridedWS
+struct FastWS
 {
   int *base;
-  int star_cap;
-  int nbr_cap;
+  static constexpr int NU = 52, NTI = 88, PAR = 97, VH = 110, NH = 126, WORDS = 142;
   __device__ __forceinline__ int &star(int i) { return base[(size_t)i * STRIDE]; }
-  __device__ __forceinline__ int &nu(int i) { return base[(size_t)(star_cap + i) * STRIDE]; }
-  __device__ __forceinline__ int &nt(int i) { return base[(size_t)(star_cap + nbr_cap + i) * STRIDE]; }
+  __device__ __forceinline__ int &nu(int i) { return base[(size_t)(NU + i) * STRIDE]; }
+  __device__ __forceinline__ unsigned char &byte(int word0, int i)
+  {
+    return reinterpret_cast<unsigned char *>(&base[(size_t)(word0 + (i >> 2)) * STRIDE])[i & 3];
+  }
+  __device__ __forceinline__ unsigned char &nt_idx(int i) { return byte(NTI, i); }
+  __device__ __forceinline__ unsigned char &parent_idx(int i) { return byte(PAR, i); }
+  __device__ __forceinline__ unsigned char &vis_hash(unsigned h) { return byte(VH, (int)h); }
+  __device__ __forceinline__ unsigned char &nbr_hash(unsigned h) { return byte(NH, (int)h); }
+  __device__ __forceinline__ int nt(int i) { return star((int)nt_idx(i)); }
+  __device__ __forceinline__ void hash_clear()
+  {
+#pragma unroll
+    for (int w = VH; w < WORDS; w++) base[(size_t)w * STRIDE] = -1;
+  }
 };
 struct DynStridedWS
 {
@@ -170,41 +190,31 @@ struct DynStridedWS
 };
 
 constexpr int TOPO_THREADS = 128;
-constexpr int TOPO_STAR_CAP = 56;
+constexpr int TOPO_STAR_CAP = 52;
 constexpr int TOPO_NBR_CAP = 36;
-constexpr size_t TOPO_SMEM = (size_t)(TOPO_STAR_CAP + 2 * TOPO_NBR_CAP) * TOPO_THREADS * sizeof(int);
+constexpr size_t TOPO_SMEM = (size_t)FastWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
 constexpr int BIG_STAR_CAP = 4096;
 constexpr int BIG_NBR_CAP = 1024;
 
 constexpr int SCAN_FACE_CAP = 32;     // faces per cell held in shared memory by k_cell_scan
 constexpr int SCAN_PTS_CAP = 2048;    // index-box points per cell handled by k_cell_scan
 
-// The part after the star walk, common to the fast and the large-workspace kernels.  All lanes of
-// the warp call it (inactive lanes with status != CELL_OK).
-template <class WS>
-__device__ __forceinline__ void topo_finish(int status, int cell, int n_nbr, WS &ws, const DevBlock &blk, int blk_id,
-                                            const GridGeom &g, const TopoOut &out)
+// One Voronoi face handed from the BFS kernels to k_cell_faces (16 bytes); slot f of the face list
+// is also slot f of the plane pool
+struct __align__(16) FaceRef
 {
-  // plane space: pairs of faces, so every cell's planes start 16-byte aligned for the bulk copy
-  uint32_t want = status == CELL_OK ? (uint32_t)((n_nbr + 1) >> 1) : 0u;
-  uint32_t poff = warp_alloc<unsigned int>(&out.cnt->plane_cursor, want);
-  float cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
-  if (status == CELL_OK) {
-    float site[3] = {blk.particles[3 * (size_t)cell], blk.particles[3 * (size_t)cell + 1], blk.particles[3 * (size_t)cell + 2]};
-    bool first = true;
-    float2 *dst = reinterpret_cast<float2 *>(out.plane_pool + (size_t)poff * 12);
-    for (int k = 0; k < n_nbr; k++) {
-      FaceAccum fa;
-      fa.cmin = cmin; fa.cmax = cmax; fa.first_of_cell = &first;
-      int n = walk_edge_link(cell, ws.nu(k), ws.nt(k), blk.tets, blk.cc, fa);
-      if (n < 0) { status = CELL_BAD_MESH; break; }
-      newell_term(fa.nrm, fa.prev, fa.v0);
-      newell_finish(fa.nrm, fa.v0, site);
-      dst[3 * k + 0] = make_float2(fa.nrm[0], fa.nrm[1]);
-      dst[3 * k + 1] = make_float2(fa.nrm[2], fa.v0[0]);
-      dst[3 * k + 2] = make_float2(fa.v0[1], fa.v0[2]);
-    }
-  }
+  int site;   // block-local id of the cell's site
+  int u;      // Delaunay neighbour (the face is dual to edge (site, u)); -1 = padding slot
+  int ut;     // first star tet in BFS order that holds u: the circulation starts there
+  int blk;    // block index
+};
+
+// After the star walk: data-bounds filter, index box, classification, header + face list.  All lanes
+// of the warp call it (lanes without an accepted cell pass status != CELL_OK).
+template <class WS>
+__device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &ws, const float *cmin, const float *cmax,
+                                           const DevBlock &blk, int blk_id, const GridGeom &g, const TopoOut &out)
+{
   int lo[3] = {0, 0, 0}, n3[3] = {0, 0, 0};
   if (status == CELL_OK) {
     // src/dense.cpp:1385-1392
@@ -223,9 +233,25 @@ __device__ __forceinline__ void topo_finish(int status, int cell, int n_nbr, WS 
       status = CELL_BAD_MESH;
     npts = (long long)n3[0] * n3[1] * n3[2];
   }
-  bool ok = status == CELL_OK;
-  bool small = ok && n_nbr <= SCAN_FACE_CAP && npts <= SCAN_PTS_CAP;
-  bool big = ok && !small;
+  const bool ok = status == CELL_OK;
+  // plane / face-list space in pairs of faces (48-byte units: every cell's planes start 16-byte aligned)
+  const uint32_t want = ok ? (uint32_t)((n_nbr + 1) >> 1) : 0u;
+  const uint32_t poff = warp_alloc<unsigned int>(&out.cnt->plane_cursor, want);
+  if (ok) {
+    FaceRef *fr = out.faces + (size_t)poff * 2;
+    for (int k = 0; k < n_nbr; k++) {
+      FaceRef r;
+      r.site = cell; r.u = ws.nu(k); r.ut = ws.nt(k); r.blk = blk_id;
+      fr[k] = r;
+    }
+    if (n_nbr & 1) {
+      FaceRef r;
+      r.site = cell; r.u = -1; r.ut = 0; r.blk = blk_id;
+      fr[n_nbr] = r;
+    }
+  }
+  const bool small = ok && n_nbr <= SCAN_FACE_CAP && npts <= SCAN_PTS_CAP;
+  const bool big = ok && !small;
   CellHdr h;
   h.cell = blk.cell_base + (uint32_t)cell;
   h.blk_nf = ((uint32_t)blk_id << 16) | (uint32_t)n_nbr;
@@ -248,40 +274,119 @@ __device__ __forceinline__ void topo_finish(int status, int cell, int n_nbr, WS 
   warp_count(&out.cnt->n_bad, status == CELL_BAD_MESH);
 }
 
-__global__ void __launch_bounds__(TOPO_THREADS) k_cell_topo(DevBlock blk, int blk_id, const __grid_constant__ GridGeom g, TopoOut out)
+// K3a part 1a: star BFS + cell bbox + filter + header + face list, one thread per cell
+__global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(DevBlock blk, int blk_id, const __grid_constant__ GridGeom g, TopoOut out)
 {
   extern __shared__ int ws_s[];
   int cell = blockIdx.x * TOPO_THREADS + threadIdx.x;
-  StridedWS<TOPO_THREADS> ws{ws_s + threadIdx.x, TOPO_STAR_CAP, TOPO_NBR_CAP};
+  FastWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
   int status = -1, n_star = 0, n_nbr = 0;
+  float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
   if (cell < blk.num_orig) {
     int t0 = blk.v2t[cell];
-    status = t0 < 0 ? CELL_NO_TET : star_and_neighbors(cell, t0, blk.tets, ws, TOPO_STAR_CAP, TOPO_NBR_CAP, &n_star, &n_nbr);
+    status = t0 < 0 ? CELL_NO_TET
+                    : star_bfs_uniform(cell, t0, blk.tets, blk.cc, ws, TOPO_STAR_CAP, TOPO_NBR_CAP, &n_star, &n_nbr, cmin, cmax);
   }
   __syncwarp();
   bool ovf = status == CELL_OVERFLOW;
   uint32_t o_slot = warp_append<unsigned int>(&out.cnt->n_overflow, ovf);
   if (ovf && o_slot < out.cap_overflow) out.overflow[o_slot] = make_uint2((unsigned)blk_id, (unsigned)cell);
-  topo_finish(ovf ? -1 : status, cell, n_nbr, ws, blk, blk_id, g, out);
+  bfs_finish(ovf ? -1 : status, cell, n_nbr, ws, cmin, cmax, blk, blk_id, g, out);
 }
 
-// large-workspace retry for the (rare) cells whose star exceeds the shared-memory workspace
-__global__ void __launch_bounds__(128) k_cell_topo_big(const DevBlock *__restrict__ blocks, const __grid_constant__ GridGeom g, TopoOut out,
-                                                        const uint2 *__restrict__ cells, int n_cells, int *ws_g)
+// The general star walk for the (rare) cells whose star exceeds the shared-memory workspace or is
+// not a manifold: one WARP per cell, lists in global memory, the two "already seen?" searches done
+// by all lanes at once.  Same order and results as star_and_neighbors (cell_core.cuh).
+struct GlobalListWS
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  DynStridedWS ws{ws_g + (i < n_cells ? i : 0), (size_t)n_cells, BIG_STAR_CAP, BIG_NBR_CAP};
-  int status = -1, n_star = 0, n_nbr = 0, cell = 0, blk_id = 0;
-  if (i < n_cells) {
-    blk_id = (int)cells[i].x;
-    cell = (int)cells[i].y;
-    const DevBlock &b = blocks[blk_id];
-    status = star_and_neighbors(cell, b.v2t[cell], b.tets, ws, BIG_STAR_CAP, BIG_NBR_CAP, &n_star, &n_nbr);
-    if (status == CELL_OVERFLOW) status = CELL_BAD_MESH; // documented limit: > 4096 tets around one site
+  int *star_, *nu_, *nt_;
+  __device__ __forceinline__ int nu(int i) const { return nu_[i]; }
+  __device__ __forceinline__ int nt(int i) const { return nt_[i]; }
+};
+
+__device__ __forceinline__ bool warp_contains(const int *list, int n, int key)
+{
+  bool f = false;
+  for (int j = (int)lane_id(); j < n; j += 32) f |= list[j] == key;
+  return __any_sync(0xffffffffu, f);
+}
+
+__global__ void __launch_bounds__(128) k_cell_bfs_big(const DevBlock *__restrict__ blocks, const __grid_constant__ GridGeom g, TopoOut out,
+                                                       const uint2 *__restrict__ cells, int n_cells, int *ws_g)
+{
+  const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = (int)lane_id();
+  if (wi >= n_cells) return;                      // whole warp
+  const int blk_id = (int)cells[wi].x, cell = (int)cells[wi].y;
+  const DevBlock blk = blocks[blk_id];
+  int *base = ws_g + (size_t)wi * (BIG_STAR_CAP + 2 * BIG_NBR_CAP);
+  GlobalListWS ws{base, base + BIG_STAR_CAP, base + BIG_STAR_CAP + BIG_NBR_CAP};
+  float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int status = CELL_OK, ns = 1, nn = 0;
+  if (lane == 0) ws.star_[0] = blk.v2t[cell];
+  __syncwarp();
+  for (int head = 0; head < ns && status == CELL_OK; head++) {
+    const int t = ws.star_[head];
+    const int4 v = blk.tets[2 * (size_t)t], nb = blk.tets[2 * (size_t)t + 1];
+    const float4 c = blk.cc[t];
+    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
+    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+    const int vv[4] = {v.x, v.y, v.z, v.w}, bb[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (status != CELL_OK) break;
+      const int u = vv[i];
+      if (u == cell) continue;
+      if (!warp_contains(ws.nu_, nn, u)) {
+        if (nn >= BIG_NBR_CAP) { status = CELL_BAD_MESH; break; }   // documented limit: > 1024 faces on one cell
+        if (lane == 0) { ws.nu_[nn] = u; ws.nt_[nn] = t; }
+        nn++;
+        __syncwarp();
+      }
+      const int next = bb[i];
+      if (next < 0) { status = CELL_INCOMPLETE; break; }
+      if (!warp_contains(ws.star_, ns, next)) {
+        if (ns >= BIG_STAR_CAP) { status = CELL_BAD_MESH; break; }  // documented limit: > 4096 tets around one site
+        if (lane == 0) ws.star_[ns] = next;
+        ns++;
+        __syncwarp();
+      }
+    }
   }
   __syncwarp();
-  DevBlock blk = blocks[blk_id];
-  topo_finish(status, cell, n_nbr, ws, blk, blk_id, g, out);
+  // lane 0 carries the cell through the common tail; the other lanes pass "no cell"
+  bfs_finish(lane == 0 ? status : -1, cell, nn, ws, cmin, cmax, blk, blk_id, g, out);
+}
+
+// K3a part 1b: one thread per Voronoi face: walk the tets around the Delaunay edge in the
+// reference's order, Newell normal, orientation, plane = (normal, first vertex) -> plane pool.
+// Tiny per-thread state and no shared memory: full occupancy hides the dependent gathers.
+__global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ faces, const Counters *cnt_in, const DevBlock *__restrict__ blocks,
+                                                     float *__restrict__ plane_pool, Counters *cnt)
+{
+  const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nfaces = (size_t)cnt_in->plane_cursor * 2;
+  if (f >= nfaces) return;
+  const FaceRef r = faces[f];
+  if (r.u < 0) return;
+  const DevBlock &b = blocks[r.blk];
+  const float site[3] = {b.particles[3 * (size_t)r.site], b.particles[3 * (size_t)r.site + 1], b.particles[3 * (size_t)r.site + 2]};
+  FaceAccum fa;
+  fa.cmin = nullptr; fa.cmax = nullptr;
+  const int n = walk_edge_link(r.site, r.u, r.ut, b.tets, b.cc, fa);
+  float2 *dst = reinterpret_cast<float2 *>(plane_pool + f * 6);
+  if (n < 0) {
+    // the link did not close (malformed mesh): a NaN plane is never significant in PtInCell
+    const float q = __int_as_float(0x7fc00000);
+    dst[0] = make_float2(q, q); dst[1] = make_float2(q, q); dst[2] = make_float2(q, q);
+    atomicAdd(&cnt->n_bad, 1ull);
+    return;
+  }
+  newell_term(fa.nrm, fa.prev, fa.v0);
+  newell_finish(fa.nrm, fa.v0, site);
+  dst[0] = make_float2(fa.nrm[0], fa.nrm[1]);
+  dst[1] = make_float2(fa.nrm[2], fa.v0[0]);
+  dst[2] = make_float2(fa.v0[1], fa.v0[2]);
 }
 
 // ---- span emission shared by the scan kernels and k_cic --------------------------------------------
@@ -363,13 +468,22 @@ __device__ __forceinline__ void emit_cic(const ScanCtx &sc, int e, uint32_t cell
                   float_path_local, vals[n], emit);
 }
 
-// ---- K3a part 2: inside bits + scan-line walk, 64 cells per CTA -----------------------------------
-constexpr int SCAN_CELLS = 64;
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_SLOT_FLOATS = 196;                 // 32 faces * 6 floats + 4 pad (784 B, 16-B multiple, bank shift 4)
-constexpr int SCAN_BIT_WORDS = 2048;                  // 65536 inside bits per round
-constexpr size_t SCAN_SMEM = SCAN_CELLS * SCAN_SLOT_FLOATS * 4 + SCAN_BIT_WORDS * 4 + SCAN_CELLS * sizeof(CellHdr) +
-                             (SCAN_CELLS + 2) * 4 + 32;
+// ---- K3a part 2: inside bits + scan-line walk -----------------------------------------------------
+// Every warp is autonomous (no CTA barrier): it takes 32 consecutive cell headers, one per lane, and
+// works through them in sub-batches whose planes (TMA bulk copies into the warp's shared-memory
+// slice, completion on the warp's own mbarrier) and inside-bits fit the slice:
+//   phase 2  warp per cell: the lanes test 32 points of the cell's index box per step against the
+//            cell's planes (shared-memory broadcast reads, face loop trip count warp-uniform);
+//            one ballot = one word of inside-bits
+//   phase 3  lane per cell: the reference's scan-line state machine on the bits (pass 1 counts,
+//            pass 2 emits span records at a warp-aggregated offset)
+constexpr int SCAN_WARPS = 4;
+constexpr int SCAN_THREADS = SCAN_WARPS * 32;
+constexpr int SCAN_PLANE_FLOATS = 2048;               // 8 KB of planes per warp (341 faces)
+constexpr int SCAN_BIT_WORDS = 256;                   // 8192 inside bits per warp (+ 1 pad word for the funnel shift)
+constexpr int SCAN_LINE_CAP = 24;                     // non-empty scan lines per cell kept from pass 1 (else the walk is redone)
+constexpr int SCAN_WARP_BYTES = SCAN_PLANE_FLOATS * 4 + (SCAN_BIT_WORDS + 4) * 4 + SCAN_LINE_CAP * 32 * 4 + 16;
+constexpr size_t SCAN_SMEM = (size_t)SCAN_WARPS * SCAN_WARP_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -414,24 +528,49 @@ struct BitsInside
     return (bits[b >> 5] >> (b & 31u)) & 1u;
   }
 };
-struct NullLine
+
+// inside-bits of one scan line (nx <= 32) out of the packed bit array
+struct RowBits
 {
-  __device__ __forceinline__ void operator()(int, int, int, int) {}
+  const uint32_t *bits;
+  uint32_t off;
+  int nx, ny;
+  __device__ __forceinline__ uint32_t operator()(int j, int k) const
+  {
+    uint32_t b = off + (uint32_t)((k * ny + j) * nx);
+    return __funnelshift_r(bits[b >> 5], bits[(b >> 5) + 1], b & 31u);
+  }
+};
+// keeps the non-empty lines of pass 1: yi | zi << 11 | min_xi << 22 | max_xi << 27, lane-strided
+struct LineKeeper
+{
+  uint32_t *buf;
+  int n;
+  __device__ __forceinline__ void operator()(int yi, int zi, int min_xi, int max_xi)
+  {
+    if (n < SCAN_LINE_CAP) buf[n * 32] = (uint32_t)yi | ((uint32_t)zi << 11) | ((uint32_t)min_xi << 22) | ((uint32_t)max_xi << 27);
+    n++;
+  }
 };
 
-__device__ __forceinline__ bool pt_in_cell_smem(const float *pl, int nf, const float *pt, float eps)
+// l / n and l % n for 0 <= l < 2^22, 1 <= n < 2^15 through one float multiply and a fix-up
+__device__ __forceinline__ void divmod_small(int l, int n, float inv_n, int &q, int &r)
 {
-  bool pos = false, neg = false;
-  for (int k = 0; k < nf; k++) {
-    const float2 *p = reinterpret_cast<const float2 *>(pl + 6 * k);
-    float2 a = p[0], b = p[1], c = p[2];
-    float n[3] = {a.x, a.y, b.x}, f[3] = {b.y, c.x, c.y};
-    int s = plane_side(n, f, pt, eps);
-    pos |= s > 0;
-    neg |= s < 0;
-    if (pos && neg) return false;
+  q = (int)((float)l * inv_n);
+  r = l - q * n;
+  if (r < 0) { q--; r += n; }
+  if (r >= n) { q++; r -= n; }
+}
+
+template <class T>
+__device__ __forceinline__ T warp_incl_scan(T v)
+{
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = __shfl_up_sync(0xffffffffu, v, d);
+    if ((int)lane_id() >= d) v += o;
   }
-  return true;
+  return v;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__restrict__ hdrs, const Counters *cnt_in, uint32_t cap_small,
@@ -439,110 +578,131 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
                                                              ScanCtx sc, const __grid_constant__ GridGeom g, SpanOut out)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *planes_s = reinterpret_cast<float *>(smem_raw);
-  uint32_t *bits_s = reinterpret_cast<uint32_t *>(planes_s + SCAN_CELLS * SCAN_SLOT_FLOATS);
-  CellHdr *hdr_s = reinterpret_cast<CellHdr *>(bits_s + SCAN_BIT_WORDS);
-  int *pfx_s = reinterpret_cast<int *>(hdr_s + SCAN_CELLS);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(pfx_s + SCAN_CELLS + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *mine = smem_raw + (size_t)warp * SCAN_WARP_BYTES;
+  float *planes_w = reinterpret_cast<float *>(mine);
+  uint32_t *bits_w = reinterpret_cast<uint32_t *>(planes_w + SCAN_PLANE_FLOATS);
+  uint32_t *lines_w = bits_w + SCAN_BIT_WORDS + 4;     // [SCAN_LINE_CAP][32 lanes]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(lines_w + SCAN_LINE_CAP * 32);
 
-  uint32_t n_hdrs = cnt_in->n_small < cap_small ? cnt_in->n_small : cap_small;
-  uint32_t first = blockIdx.x * SCAN_CELLS;
-  if (first >= n_hdrs) return;
-  int ncell = (int)(n_hdrs - first < (uint32_t)SCAN_CELLS ? n_hdrs - first : SCAN_CELLS);
-  const int tid = threadIdx.x;
+  const uint32_t n_hdrs = cnt_in->n_small < cap_small ? cnt_in->n_small : cap_small;
+  const uint32_t first = (blockIdx.x * SCAN_WARPS + warp) * 32u;
+  if (first >= n_hdrs) return;                       // whole warp leaves together
+  const int ncell = (int)(n_hdrs - first < 32u ? n_hdrs - first : 32u);
 
-  if (tid == 0) {
-    mbar_init(bar, SCAN_CELLS);
+  if (lane == 0) {
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  // stage headers and planes: thread c < 64 owns cell c
-  if (tid < SCAN_CELLS) {
-    uint32_t bytes = 0;
-    int npts = 0;
-    if (tid < ncell) {
-      CellHdr h = hdrs[first + tid];
-      hdr_s[tid] = h;
-      int nf = (int)(h.blk_nf & 0xffffu);
-      bytes = (uint32_t)((nf + 1) >> 1) * 48u;
-      npts = (int)h.n3[0] * (int)h.n3[1] * (int)h.n3[2];
-      mbar_arrive_expect_tx(bar, bytes);
-      if (bytes) bulk_g2s(planes_s + tid * SCAN_SLOT_FLOATS, plane_pool + (size_t)h.plane_off * 12, bytes, bar);
-    } else {
-      mbar_arrive_expect_tx(bar, 0);
-    }
-    // inclusive prefix of npts over the 64 cells (two warps)
-    int incl = npts;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int o = __shfl_up_sync(0xffffffffu, incl, d);
-      if ((int)lane_id() >= d) incl += o;
-    }
-    pfx_s[tid + 1] = incl;
-  }
-  if (tid == 0) pfx_s[0] = 0;
-  __syncthreads();
-  if (tid >= 32 && tid < SCAN_CELLS) pfx_s[tid + 1] += pfx_s[32];
-  __syncthreads();
-  mbar_wait(bar, 0);
+  __syncwarp();
 
-  // rounds of consecutive cells whose inside bits fit the bit buffer
+  // lane c owns cell c of the batch
+  CellHdr h;
+  h.cell = 0; h.blk_nf = 0; h.lo[0] = h.lo[1] = h.lo[2] = 0; h.n3[0] = h.n3[1] = h.n3[2] = 1; h.pad = 0; h.plane_off = 0;
+  if (lane < ncell) h = hdrs[first + lane];
+  const int nf = (int)(h.blk_nf & 0xffffu);
+  const int e = (int)(h.blk_nf >> 16);
+  const int npts = lane < ncell ? (int)h.n3[0] * (int)h.n3[1] * (int)h.n3[2] : 0;
+  const int pairs = lane < ncell ? (nf + 1) >> 1 : 0;                 // 48-byte units of planes
+  const int pts32 = (npts + 31) & ~31;
+
+  uint32_t parity = 0;
   int c0 = 0;
   while (c0 < ncell) {
-    int c1 = c0;
-    int base_pts = pfx_s[c0];
-    while (c1 < ncell && pfx_s[c1 + 1] - base_pts <= SCAN_BIT_WORDS * 32) c1++;
-    int total = pfx_s[c1] - base_pts;
-    int total32 = (total + 31) & ~31;
+    // sub-batch [c0, c1): the longest run whose planes and bits fit the warp's slice
+    int incl_f = warp_incl_scan(lane >= c0 ? pairs : 0);
+    int incl_p = warp_incl_scan(lane >= c0 ? pts32 : 0);
+    bool fits = lane >= c0 && lane < ncell && incl_f * 12 <= SCAN_PLANE_FLOATS && incl_p <= SCAN_BIT_WORDS * 32;
+    unsigned fm = __ballot_sync(0xffffffffu, fits);
+    // (fm >> c0) is a run of ones starting at bit 0 (the prefix sums are monotone): c1 = c0 + its length
+    const unsigned run = fm >> c0;
+    int c1 = c0 + (run == 0xffffffffu ? 32 : __ffs(~run) - 1);
+    if (c1 > ncell) c1 = ncell;
+    const bool in_sub = lane >= c0 && lane < c1;
+    const int f_off = incl_f - pairs;                                  // pairs before this cell in the slice
+    const int p_off = incl_p - pts32;                                  // bits before this cell in the slice
+    const uint32_t total_bytes = (uint32_t)__shfl_sync(0xffffffffu, incl_f, c1 - 1) * 48u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of the slice vs. the new bulk writes
+    if (lane == 0) mbar_arrive_expect_tx(bar, total_bytes);
+    __syncwarp();
+    if (in_sub && pairs) bulk_g2s(planes_w + (size_t)f_off * 12, plane_pool + (size_t)h.plane_off * 12, (uint32_t)pairs * 48u, bar);
+    mbar_wait(bar, parity);
+    parity ^= 1u;
 
-    // phase 2: PtInCell for every point of every index box, one point per lane
-    for (int s = tid; s < total32; s += SCAN_THREADS) {
-      bool in = false;
-      if (s < total) {
-        int lo_c = c0, hi_c = c1; // find cell: pfx[c] - base <= s < pfx[c+1] - base
-        while (hi_c - lo_c > 1) {
-          int mid = (lo_c + hi_c) >> 1;
-          if (pfx_s[mid] - base_pts <= s) lo_c = mid; else hi_c = mid;
+    // phase 2: warp per cell
+    for (int c = c0; c < c1; c++) {
+      const int nx = __shfl_sync(0xffffffffu, (int)h.n3[0], c), ny = __shfl_sync(0xffffffffu, (int)h.n3[1], c);
+      const int np = __shfl_sync(0xffffffffu, npts, c), cnf = __shfl_sync(0xffffffffu, nf, c);
+      const int lx = __shfl_sync(0xffffffffu, h.lo[0], c), ly = __shfl_sync(0xffffffffu, h.lo[1], c), lz = __shfl_sync(0xffffffffu, h.lo[2], c);
+      const float *pl = planes_w + (size_t)__shfl_sync(0xffffffffu, f_off, c) * 12;
+      const int wbase = __shfl_sync(0xffffffffu, p_off, c) >> 5;
+      // probe position: cell_min_grid_pos + i * step with cell_min_grid_pos = idx2phys(lo)  (src/dense.cpp:1404,1530-1532)
+      const float bx = idx2phys1(lx, g.step[0], g.gmin[0]), by = idx2phys1(ly, g.step[1], g.gmin[1]), bz = idx2phys1(lz, g.step[2], g.gmin[2]);
+      const float inv_nx = 1.0f / (float)nx, inv_ny = 1.0f / (float)ny;
+      for (int l0 = 0; l0 < np; l0 += 32) {
+        const int l = l0 + lane;
+        const bool valid = l < np;
+        int i, r, j, k;
+        divmod_small(valid ? l : 0, nx, inv_nx, r, i);
+        divmod_small(r, ny, inv_ny, k, j);
+        const float pt[3] = {fadd(bx, fmul((float)i, g.step[0])), fadd(by, fmul((float)j, g.step[1])), fadd(bz, fmul((float)k, g.step[2]))};
+        // PtInCell (src/dense.cpp:1172-1203): false iff some face has dist > eps and some face has
+        // dist < -eps.  Tracked as running max / min of dist (NaN never counts, as in the reference).
+        float dmax = -INFINITY, dmin = INFINITY;
+        const float neg_eps = -g.eps;
+#pragma unroll 4
+        for (int f = 0; f < cnf; f++) {
+          const float2 *p = reinterpret_cast<const float2 *>(pl + 6 * f);
+          const float2 a = p[0], b = p[1], cc2 = p[2];
+          const float dist = fadd(fadd(fmul(a.x, fsub(pt[0], b.y)), fmul(a.y, fsub(pt[1], cc2.x))), fmul(b.x, fsub(pt[2], cc2.y)));
+          dmax = fmaxf(dmax, dist);
+          dmin = fminf(dmin, dist);
+          if ((f & 3) == 3 && __all_sync(0xffffffffu, !valid || (dmax > g.eps && dmin < neg_eps))) break;
         }
-        const CellHdr &h = hdr_s[lo_c];
-        int l = s - (pfx_s[lo_c] - base_pts);
-        int nx = h.n3[0], ny = h.n3[1];
-        int i = l % nx;
-        int r = l / nx;
-        int j = r % ny;
-        int k = r / ny;
-        float pt[3];
-        // probe position: cell_min_grid_pos + i * step, cell_min_grid_pos = idx2phys(lo) (src/dense.cpp:1404,1530-1532)
-        pt[0] = fadd(idx2phys1(h.lo[0], g.step[0], g.gmin[0]), fmul((float)i, g.step[0]));
-        pt[1] = fadd(idx2phys1(h.lo[1], g.step[1], g.gmin[1]), fmul((float)j, g.step[1]));
-        pt[2] = fadd(idx2phys1(h.lo[2], g.step[2], g.gmin[2]), fmul((float)k, g.step[2]));
-        in = pt_in_cell_smem(planes_s + lo_c * SCAN_SLOT_FLOATS, (int)(h.blk_nf & 0xffffu), pt, g.eps);
+        const unsigned w = __ballot_sync(0xffffffffu, valid && !(dmax > g.eps && dmin < neg_eps));
+        if (lane == 0) bits_w[wbase + (l0 >> 5)] = w;
       }
-      unsigned w = __ballot_sync(0xffffffffu, in);
-      if (lane_id() == 0) bits_s[s >> 5] = w;
     }
-    __syncthreads();
+    __syncwarp();
 
-    // phase 3: the scan-line walk on the bits, one thread per cell; pass 1 counts, pass 2 emits
-    if (tid < 64) {
-      int c = c0 + tid;
-      bool act = c < c1;
-      int tot = 0, nrec = 0, e = 0;
-      bool local_box = false;
+    // phase 3: lane per cell.  Index boxes at most 32 wide (all but exotic cells) take the
+    // bit-parallel walk and keep their non-empty lines, so the walk runs once.
+    {
+      int tot = 0, nrec = 0, nlines = 0;
+      bool local_box = false, bitpath = false;
       float site[3] = {0, 0, 0};
-      CellHdr h;
-      BitsInside inside{bits_s, 0, 1, 1};
-      if (act) {
-        h = hdr_s[c];
-        e = (int)(h.blk_nf >> 16);
-        int lo[3] = {h.lo[0], h.lo[1], h.lo[2]}, n3[3] = {h.n3[0], h.n3[1], h.n3[2]};
+      const int nx = (int)h.n3[0], ny = (int)h.n3[1], nz = (int)h.n3[2];
+      BitsInside inside{bits_w, (uint32_t)p_off, nx, ny};
+      RowBits row{bits_w, (uint32_t)p_off, nx, ny};
+      if (in_sub) {
+        int lo[3] = {h.lo[0], h.lo[1], h.lo[2]}, n3[3] = {nx, ny, nz};
         local_box = box_is_local(sc.boxes[e], lo, n3, sc.project);
-        inside.off = (uint32_t)(pfx_s[c] - base_pts);
-        inside.nx = n3[0]; inside.ny = n3[1];
-        CountEmit ce{0};
-        LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
-        tot = scan_cell(n3[0], n3[1], n3[2], inside, le);
-        nrec = ce.n;
+        bitpath = nx <= 32 && ny < 2048 && nz < 2048;
+        if (bitpath) {
+          LineKeeper lk{lines_w + lane, 0};
+          tot = scan_cell_bits(nx, ny, nz, row, lk);
+          nlines = lk.n;
+          if (nlines <= SCAN_LINE_CAP && local_box) nrec = nlines;
+          else if (nlines <= SCAN_LINE_CAP) {
+            CountEmit ce{0};
+            LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
+            for (int q = 0; q < nlines; q++) {
+              uint32_t pk = lines_w[q * 32 + lane];
+              le((int)(pk & 2047u), (int)((pk >> 11) & 2047u), (int)((pk >> 22) & 31u), (int)(pk >> 27));
+            }
+            nrec = ce.n;
+          } else {
+            CountEmit ce{0};
+            LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
+            scan_cell_bits(nx, ny, nz, row, le);
+            nrec = ce.n;
+          }
+        } else {
+          CountEmit ce{0};
+          LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
+          tot = scan_cell(nx, ny, nz, inside, le);
+          nrec = ce.n;
+        }
         if (tot == 0) {
           const DevBlock &b = blocks[e];
           uint32_t lc = h.cell - b.cell_base;
@@ -554,20 +714,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
       }
       __syncwarp();
       unsigned long long base = warp_alloc<unsigned long long>(&out.cnt->n_spans, (unsigned long long)nrec);
-      warp_count(&out.cnt->n_deposit, act);
-      warp_count(&out.cnt->n_cic_fallback, act && tot == 0);
-      if (act) {
+      warp_count(&out.cnt->n_deposit, in_sub);
+      warp_count(&out.cnt->n_cic_fallback, in_sub && tot == 0);
+      if (in_sub) {
         StoreEmit se{out.keys, out.data, base, out.capacity};
         if (tot > 0) {
           float m = fdiv(g.mass, (float)tot); // src/dense.cpp:1692
           LineEmitter<StoreEmit> le{sc, e, h.cell, h.lo, local_box, m, se, 0};
-          scan_cell((int)h.n3[0], (int)h.n3[1], (int)h.n3[2], inside, le);
+          if (bitpath && nlines <= SCAN_LINE_CAP) {
+            for (int q = 0; q < nlines; q++) {
+              uint32_t pk = lines_w[q * 32 + lane];
+              le((int)(pk & 2047u), (int)((pk >> 11) & 2047u), (int)((pk >> 22) & 31u), (int)(pk >> 27));
+            }
+          } else if (bitpath) {
+            scan_cell_bits(nx, ny, nz, row, le);
+          } else {
+            scan_cell(nx, ny, nz, inside, le);
+          }
         } else {
           emit_cic(sc, e, h.cell, site, g, 0, se);
         }
       }
+      __syncwarp();
     }
-    __syncthreads();
     c0 = c1;
   }
 }
@@ -781,11 +950,11 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_volumes(DevBlock blk, int
 {
   extern __shared__ int ws_s[];
   int site = blockIdx.x * TOPO_THREADS + threadIdx.x;
-  StridedWS<TOPO_THREADS> ws{ws_s + threadIdx.x, TOPO_STAR_CAP, TOPO_NBR_CAP};
+  FastWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
   int status = -1, n_star = 0, n_nbr = 0;
   if (site < num_sites) {
     int t0 = blk.v2t[site];
-    status = t0 < 0 ? CELL_NO_TET : star_and_neighbors(site, t0, blk.tets, ws, TOPO_STAR_CAP, TOPO_NBR_CAP, &n_star, &n_nbr);
+    status = t0 < 0 ? CELL_NO_TET : star_and_neighbors_hashed(site, t0, blk.tets, ws, TOPO_STAR_CAP, TOPO_NBR_CAP, &n_star, &n_nbr);
   }
   __syncwarp();
   bool ovf = status == CELL_OVERFLOW;

@@ -48,6 +48,66 @@ struct HostWS
   int &nt(int i) { return t[i]; }
 };
 
+// the fast kernels' workspace (hash tables, caps 56 / 36) with the linear-search workspace as the
+// overflow path -- the same two-level scheme as k_cell_topo / k_cell_topo_big
+struct HashWS
+{
+  int s[52], u[36];
+  unsigned char nti[36], par[52], vh[64], nh[64];
+  unsigned char &parent_idx(int i) { return par[i]; }
+  int &star(int i) { return s[i]; }
+  int &nu(int i) { return u[i]; }
+  unsigned char &nt_idx(int i) { return nti[i]; }
+  unsigned char &vis_hash(unsigned h) { return vh[h]; }
+  unsigned char &nbr_hash(unsigned h) { return nh[h]; }
+  int nt(int i) { return s[nti[i]]; }
+  void hash_clear() { memset(vh, 0xFF, 64); memset(nh, 0xFF, 64); }
+};
+
+struct Topo
+{
+  HostWS big;
+  HashWS fast;
+  bool use_fast = true;
+  int nn = 0;
+  float cmin[3], cmax[3];   // bbox from the star's circumcenters (k_cell_bfs), when cc is given
+  int run(int site, int t0, const int4 *tets, const float4 *cc = nullptr)
+  {
+    int ns;
+    use_fast = true;
+    int st;
+    for (int d = 0; d < 3; d++) { cmin[d] = INFINITY; cmax[d] = -INFINITY; }
+    if (cc) {
+      st = star_bfs_uniform(site, t0, tets, cc, fast, 52, 36, &ns, &nn, cmin, cmax);
+      // the parent-trick BFS must agree with the plain hashed one
+      HashWS chk;
+      int ns2, nn2;
+      int st2 = star_and_neighbors_hashed(site, t0, tets, chk, 52, 36, &ns2, &nn2);
+      if (st2 != st || (st == CELL_OK && (ns2 != ns || nn2 != nn))) { fprintf(stderr, "emul: BFS variants disagree\n"); abort(); }
+      if (st == CELL_OK)
+        for (int k = 0; k < nn; k++)
+          if (chk.nu(k) != fast.nu(k) || chk.nt(k) != fast.nt(k)) { fprintf(stderr, "emul: BFS variants disagree on faces\n"); abort(); }
+    } else {
+      st = star_and_neighbors_hashed(site, t0, tets, fast, 52, 36, &ns, &nn);
+    }
+    if (st == CELL_OVERFLOW) {
+      use_fast = false;
+      st = star_and_neighbors(site, t0, tets, big, 4096, 1024, &ns, &nn);
+      if (cc && st == CELL_OK) {
+        for (int d = 0; d < 3; d++) { cmin[d] = INFINITY; cmax[d] = -INFINITY; }
+        for (int k = 0; k < ns; k++) {
+          float4 c = cc[big.star(k)];
+          float v[3] = {c.x, c.y, c.z};
+          for (int d = 0; d < 3; d++) { cmin[d] = fminf(cmin[d], v[d]); cmax[d] = fmaxf(cmax[d], v[d]); }
+        }
+      }
+    }
+    return st;
+  }
+  int nu(int k) { return use_fast ? fast.nu(k) : big.nu(k); }
+  int nt(int k) { return use_fast ? fast.nt(k) : big.nt(k); }
+};
+
 struct Rec { uint64_t key, data; };
 struct VecEmit
 {
@@ -60,6 +120,18 @@ struct BitsIn
   const std::vector<unsigned char> *bits;
   int nx, ny;
   bool operator()(int i, int j, int k) const { return (*bits)[((size_t)k * ny + j) * nx + i] != 0; }
+};
+
+struct RowIn
+{
+  const std::vector<unsigned char> *bits;
+  int nx, ny;
+  uint32_t operator()(int j, int k) const
+  {
+    uint32_t r = 0;
+    for (int i = 0; i < nx; i++) r |= (uint32_t)((*bits)[((size_t)k * ny + j) * nx + i] != 0) << i;
+    return r;
+  }
 };
 
 struct LineEmit
@@ -112,11 +184,10 @@ static std::vector<float4> make_cc(int num_tets, const int *tets, const float *p
 extern "C" void emu_complete(int num_verts, int num_tets, const int *tets, const int *v2t, int *out)
 {
   (void)num_tets;
-  HostWS ws;
+  Topo tp;
   for (int v = 0; v < num_verts; v++) {
     if (v2t[v] < 0) { out[v] = -1; continue; }
-    int ns, nn;
-    int st = star_and_neighbors(v, v2t[v], (const int4 *)tets, ws, 4096, 1024, &ns, &nn);
+    int st = tp.run(v, v2t[v], (const int4 *)tets);
     out[v] = st == CELL_OK ? 1 : 0;
   }
 }
@@ -124,18 +195,17 @@ extern "C" void emu_complete(int num_verts, int num_tets, const int *tets, const
 extern "C" void emu_volumes(int num_verts, int num_tets, const int *tets, const float *particles, const int *v2t, float *out)
 {
   std::vector<float4> cc = make_cc(num_tets, tets, particles);
-  HostWS ws;
+  Topo tp;
   for (int v = 0; v < num_verts; v++) {
     if (v2t[v] < 0) { out[v] = -2.0f; continue; }
-    int ns, nn;
-    int st = star_and_neighbors(v, v2t[v], (const int4 *)tets, ws, 4096, 1024, &ns, &nn);
+    int st = tp.run(v, v2t[v], (const int4 *)tets);
     if (st != CELL_OK) { out[v] = -1.0f; continue; }
     float vol = 0.0f;
-    for (int k = 0; k < nn; k++) {
+    for (int k = 0; k < tp.nn; k++) {
       AreaAccum aa;
       aa.area = 0.0f;
-      int u = ws.nu(k);
-      walk_edge_link(v, u, ws.nt(k), (const int4 *)tets, cc.data(), aa);
+      int u = tp.nu(k);
+      walk_edge_link(v, u, tp.nt(k), (const int4 *)tets, cc.data(), aa);
       float n = 0.0f;
       for (int d = 0; d < 3; d++) {
         float df = fsub(particles[3 * u + d], particles[3 * v + d]);
@@ -199,7 +269,7 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
 
   std::vector<Rec> recs;
   VecEmit emit{&recs};
-  HostWS ws;
+  Topo tp;
   for (int bi = 0; bi < nblocks; bi++) {
     emu_block_t &b = blocks[bi];
     if (only_gid >= 0 && b.gid != only_gid) continue;
@@ -226,24 +296,25 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
     std::vector<float4> cc = make_cc(b.num_tets, b.tets, b.particles);
     for (int cell = 0; cell < b.num_orig_particles; cell++) {
       if (v2t[cell] < 0) continue;
-      int ns, nn;
-      int st = star_and_neighbors(cell, v2t[cell], (const int4 *)b.tets, ws, 4096, 1024, &ns, &nn);
+      int st = tp.run(cell, v2t[cell], (const int4 *)b.tets, cc.data());
       if (st != CELL_OK) continue;
-      float cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
-      bool first = true;
+      const int nn = tp.nn;
+      float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
       const float *site = &b.particles[3 * cell];
       std::vector<float> planes(6 * nn);
       bool bad = false;
       for (int k = 0; k < nn; k++) {
         FaceAccum fa;
-        fa.cmin = cmin; fa.cmax = cmax; fa.first_of_cell = &first;
-        int n = walk_edge_link(cell, ws.nu(k), ws.nt(k), (const int4 *)b.tets, cc.data(), fa);
+        fa.cmin = cmin; fa.cmax = cmax;
+        int n = walk_edge_link(cell, tp.nu(k), tp.nt(k), (const int4 *)b.tets, cc.data(), fa);
         if (n < 0) { bad = true; break; }
         newell_term(fa.nrm, fa.prev, fa.v0);
         newell_finish(fa.nrm, fa.v0, site);
         for (int d = 0; d < 3; d++) { planes[6 * k + d] = fa.nrm[d]; planes[6 * k + 3 + d] = fa.v0[d]; }
       }
       if (bad) continue;
+      for (int d = 0; d < 3; d++)
+        if (cmin[d] != tp.cmin[d] || cmax[d] != tp.cmax[d]) { fprintf(stderr, "emul: star bbox != face bbox\n"); abort(); }
       bool outside = false;
       for (int d = 0; d < 3; d++)
         if (cmin[d] < fsub(g.dmin[d], g.dext_eps[d]) || cmax[d] > fadd(g.dmax[d], g.dext_eps[d])) outside = true;
@@ -269,11 +340,14 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
             bits[((size_t)k * n3[1] + j) * n3[0] + i] = !(pos && neg);
           }
       BitsIn inside{&bits, n3[0], n3[1]};
+      RowIn row{&bits, n3[0], n3[1]};
+      const bool bitpath = n3[0] <= 32;   // the kernels' bit-parallel walk (scan_cell_bits), else the generic one
       LineEmit cnt{&boxes, kl, g.project, bi, cell_base[bi] + (uint32_t)cell, lo, 0.0f, nullptr, 0};
-      int tot = scan_cell(n3[0], n3[1], n3[2], inside, cnt);
+      int tot = bitpath ? scan_cell_bits(n3[0], n3[1], n3[2], row, cnt) : scan_cell(n3[0], n3[1], n3[2], inside, cnt);
       if (tot > 0) {
         LineEmit le{&boxes, kl, g.project, bi, cell_base[bi] + (uint32_t)cell, lo, fdiv(g.mass, (float)tot), &emit, 0};
-        scan_cell(n3[0], n3[1], n3[2], inside, le);
+        if (bitpath) scan_cell_bits(n3[0], n3[1], n3[2], row, le);
+        else scan_cell(n3[0], n3[1], n3[2], inside, le);
       } else {
         int i0[3];
         float vals[8];
