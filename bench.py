@@ -221,7 +221,7 @@ def run_ours(args, rank, world, local_rank):
     blocks, layout, owner, dmin, dmax, gsize = build_workload(n, rank)
     keep = []
     for b in blocks:                      # pinned host buffers: the e2e leg copies from these
-        for k in ("particles", "tets"):
+        for k in ("particles", "tets", "vert_to_tet"):
             t, b[k] = pinned_copy(b[k])
             keep.append(t)
     ctx = tess2_b200.Context(local_rank)
@@ -273,7 +273,7 @@ def run_ours(args, rank, world, local_rank):
         t = torch.empty(npts, dtype=torch.float32).pin_memory()
         out_t.append(t)
         out_blocks.append(t.numpy())
-    h2d = sum(b["particles"].nbytes + b["tets"].nbytes for b in blocks)
+    h2d = sum(b["particles"].nbytes + b["tets"].nbytes + b["vert_to_tet"].nbytes for b in blocks)
     d2h = sum(o.nbytes for o in out_blocks)
 
     def e2e_step():
@@ -328,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
         cores = os.cpu_count() or 1
         procs = min(len(blocks), cores)
         max_cells = int(os.environ.get("TESSB200_CPU_SAMPLE_CELLS", str(max(1024, (H ** 3) // 4))))
-        plain = [dict(b, particles=np.array(b["particles"]), tets=np.array(b["tets"])) for b in blocks]
+        plain = [dict(b, particles=np.array(b["particles"]), tets=np.array(b["tets"]), vert_to_tet=np.array(b["vert_to_tet"])) for b in blocks]
         wall_s, slowest, cells, kind = cpu_dense_sample(plain, gsize, None, max_cells, procs)
         cpu_value = G_total * (cells / (cells_local)) / wall_s
         cpu = {"value": cpu_value, "unit": UNIT, "cores": procs, "kind": kind,

@@ -129,7 +129,7 @@ struct BlockRes
   int num_orig = 0, num_particles = 0, num_tets = 0;
   float bmin[3], bmax[3];
   bool have_v2t = false;
-  Buf particles, tets, v2t, cc;
+  Buf particles, tets, v2t, cc, order, mkeys, mkeys2, order2;
   // geometry of the last run
   int mn[3], num[3];
   long long npts = 0, nrows = 0, row_base = 0, out_off = 0;
@@ -200,6 +200,7 @@ static void free_blocks(tessb200_ctx *c)
 {
   for (BlockRes *b : c->blocks) {
     b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
+    b->order.release(); b->mkeys.release(); b->mkeys2.release(); b->order2.release();
     delete b;
   }
   c->blocks.clear();
@@ -364,6 +365,7 @@ extern "C" int tessb200_dense_upload(tessb200_ctx *c, int nblocks, const tessb20
   while ((int)c->blocks.size() > nblocks) {
     BlockRes *b = c->blocks.back();
     b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
+    b->order.release(); b->mkeys.release(); b->mkeys2.release(); b->order2.release();
     delete b;
     c->blocks.pop_back();
   }
@@ -404,6 +406,9 @@ static DevBlock dev_block(const BlockRes *b)
   d.cc = (const float4 *)b->cc.p;
   d.num_orig = b->num_orig; d.num_particles = b->num_particles; d.num_tets = b->num_tets;
   d.cell_base = b->cell_base;
+  d.order = (const uint32_t *)b->order.p;
+  d.cta_start = 0;
+  d.pad_ = 0;
   return d;
 }
 
@@ -422,6 +427,25 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b)
     COUNT_LAUNCH(c, 1);
   }
   CU(cudaGetLastError());
+  return 0;
+}
+
+// processing order of a block's cells: Morton order of the sites (results do not depend on it)
+static int prep_block_order(tessb200_ctx *c, BlockRes *b)
+{
+  const int n = b->num_orig;
+  if (n == 0) return 0;
+  TRY(b->order.ensure(4 * (size_t)n)); TRY(b->order2.ensure(4 * (size_t)n));
+  TRY(b->mkeys.ensure(4 * (size_t)n)); TRY(b->mkeys2.ensure(4 * (size_t)n));
+  float3 bmin = make_float3(b->bmin[0], b->bmin[1], b->bmin[2]);
+  float3 inv = make_float3(1.0f / fmaxf(b->bmax[0] - b->bmin[0], 1e-30f), 1.0f / fmaxf(b->bmax[1] - b->bmin[1], 1e-30f),
+                           1.0f / fmaxf(b->bmax[2] - b->bmin[2], 1e-30f));
+  k_morton_keys<<<cdiv(n, 256), 256, 0, c->stream>>>((const float *)b->particles.p, n, bmin, inv, b->mkeys.as<uint32_t>(), b->order2.as<uint32_t>());
+  COUNT_LAUNCH(c, 1);
+  size_t tmp = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, b->mkeys.as<uint32_t>(), b->mkeys2.as<uint32_t>(), b->order2.as<uint32_t>(), b->order.as<uint32_t>(), n, 0, 30, c->stream));
+  TRY(c->cub_tmp.ensure(tmp));
+  CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, b->mkeys.as<uint32_t>(), b->mkeys2.as<uint32_t>(), b->order2.as<uint32_t>(), b->order.as<uint32_t>(), n, 0, 30, c->stream));
   return 0;
 }
 
@@ -454,8 +478,15 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   // device descriptors
   std::vector<DevBlock> hblocks(nall);
   memset(hblocks.data(), 0, sizeof(DevBlock) * nall);
+  uint32_t bfs_ctas = 0;
   for (int i = 0; i < nall; i++)
-    if (G.local_of[i] >= 0) hblocks[i] = dev_block(c->blocks[G.local_of[i]]);
+    if (G.local_of[i] >= 0) {
+      BlockRes *b = c->blocks[G.local_of[i]];
+      if (p->alg == TESSB200_DENSE_TESS && b->num_orig) { TRY(b->order.ensure(4 * (size_t)b->num_orig)); }
+      hblocks[i] = dev_block(b);
+      hblocks[i].cta_start = bfs_ctas;
+      bfs_ctas += cdiv(b->num_orig, TOPO_THREADS);
+    }
   TRY(c->d_blocks.ensure(sizeof(DevBlock) * nall));
   TRY(c->d_boxes.ensure(sizeof(BlockBox) * nall));
   TRY(c->d_rblocks.ensure(sizeof(RowBlock) * std::max<size_t>(1, G.rblocks.size())));
@@ -482,7 +513,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   CU(cudaEventRecord(c->ev[3], s));
   if (p->alg == TESSB200_DENSE_TESS) {
     // K0/K1
-    for (BlockRes *b : c->blocks) TRY(prep_block_geometry(c, b));
+    for (BlockRes *b : c->blocks) { TRY(prep_block_geometry(c, b)); TRY(prep_block_order(c, b)); }
     CU(cudaEventRecord(c->ev[4], s));
     // K3a part 1
     TRY(c->plane_pool.ensure(48 * ((size_t)2 * tets + (size_t)cells + 64)));   // sum of faces <= 4 T
@@ -497,11 +528,8 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     to.big_bit_off = c->big_bitoff.as<unsigned long long>();
     to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.faces = c->face_list.as<FaceRef>(); to.cnt = cnt;
     to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
-    for (int i = 0; i < nall; i++) {
-      if (G.local_of[i] < 0) continue;
-      const DevBlock &db = hblocks[i];
-      if (db.num_orig == 0) continue;
-      k_cell_bfs<<<cdiv(db.num_orig, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, s>>>(db, i, G.g, to);
+    if (bfs_ctas) {
+      k_cell_bfs<<<bfs_ctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), nall, G.g, to);
       COUNT_LAUNCH(c, 1);
     }
     CU(cudaGetLastError());
@@ -737,7 +765,7 @@ extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nbl
 struct TmpBlock
 {
   BlockRes b;
-  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); }
+  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.order.release(); b.mkeys.release(); b.mkeys2.release(); b.order2.release(); }
 };
 
 static int upload_tmp(tessb200_ctx *c, TmpBlock &t, int num_particles, const float *particles, int num_tets, const int *tets, const int *v2t)

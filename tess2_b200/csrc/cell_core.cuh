@@ -336,11 +336,29 @@ TB_HD int star_bfs_uniform(int site, int t0, const int4 *tets, const float4 *cc,
       if (r2 > 0) ws.parent_idx(before_s) = 0;
     }
   }
+  // software pipelining: the record of the next tet in the queue is requested before the table
+  // operations of the current one, so its latency overlaps them
+  int4 v_n = {0, 0, 0, 0}, nb_n = {0, 0, 0, 0};
+  float4 c_n = {0, 0, 0, 0};
+  bool have_n = false;
+  if (ns > 1) {
+    int t1 = ws.star(1);
+    v_n = tets[2 * (size_t)t1]; nb_n = tets[2 * (size_t)t1 + 1]; c_n = cc[t1];
+    have_n = true;
+  }
   for (int head = 1; head < ns; head++) {
-    int t = ws.star(head);
-    int4 v = tets[2 * (size_t)t];
-    int4 nb = tets[2 * (size_t)t + 1];
-    float4 c = cc[t];
+    int4 v, nb;
+    float4 c;
+    if (have_n) { v = v_n; nb = nb_n; c = c_n; }
+    else {
+      int t = ws.star(head);
+      v = tets[2 * (size_t)t]; nb = tets[2 * (size_t)t + 1]; c = cc[t];
+    }
+    have_n = head + 1 < ns;
+    if (have_n) {
+      int t1 = ws.star(head + 1);
+      v_n = tets[2 * (size_t)t1]; nb_n = tets[2 * (size_t)t1 + 1]; c_n = cc[t1];
+    }
     cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
     cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
     const int par = ws.star((int)ws.parent_idx(head));

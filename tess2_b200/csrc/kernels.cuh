@@ -32,6 +32,9 @@ struct DevBlock
   const float4 *cc;        // circumcenter per tet (w unused)
   int num_orig, num_particles, num_tets;
   uint32_t cell_base;      // global number of this block's cell 0 (blocks in ascending gid order)
+  const uint32_t *order;   // cells of the block in Morton order of their sites (processing order only)
+  uint32_t cta_start;      // first CTA of this block in the all-blocks BFS launch
+  uint32_t pad_;
 };
 
 // One accepted cell handed from k_cell_topo to the scan kernels (32 bytes)
@@ -274,15 +277,45 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
   warp_count(&out.cnt->n_bad, status == CELL_BAD_MESH);
 }
 
-// K3a part 1a: star BFS + cell bbox + filter + header + face list, one thread per cell
-__global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(DevBlock blk, int blk_id, const __grid_constant__ GridGeom g, TopoOut out)
+// Morton key of a site inside its block's bounds, 10 bits per axis (processing order only: cells
+// that are close in space share star tets, so consecutive threads reuse L1 / L2 lines)
+__device__ __forceinline__ uint32_t spread10(uint32_t x)
+{
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000ffu;
+  x = (x | (x << 8)) & 0x0300f00fu;
+  x = (x | (x << 4)) & 0x030c30c3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+__global__ void k_morton_keys(const float *__restrict__ particles, int n, float3 bmin, float3 inv_ext, uint32_t *__restrict__ keys,
+                              uint32_t *__restrict__ ids)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = (particles[3 * (size_t)i] - bmin.x) * inv_ext.x, y = (particles[3 * (size_t)i + 1] - bmin.y) * inv_ext.y,
+        z = (particles[3 * (size_t)i + 2] - bmin.z) * inv_ext.z;
+  uint32_t xi = (uint32_t)fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f), yi = (uint32_t)fminf(fmaxf(y * 1024.0f, 0.0f), 1023.0f),
+           zi = (uint32_t)fminf(fmaxf(z * 1024.0f, 0.0f), 1023.0f);
+  keys[i] = spread10(xi) | (spread10(yi) << 1) | (spread10(zi) << 2);
+  ids[i] = (uint32_t)i;
+}
+
+// K3a part 1a: star BFS + cell bbox + filter + header + face list, one thread per cell, every block
+// of this GPU in one launch (CTAs [cta_start_b, cta_start_{b+1}) work on block b)
+__global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__restrict__ blocks, int nblocks, const __grid_constant__ GridGeom g, TopoOut out)
 {
   extern __shared__ int ws_s[];
-  int cell = blockIdx.x * TOPO_THREADS + threadIdx.x;
+  int blk_id = 0;
+  for (int b = 1; b < nblocks; b++)
+    if (blocks[b].num_orig > 0 && blocks[b].tets != nullptr && blockIdx.x >= blocks[b].cta_start) blk_id = b;
+  const DevBlock blk = blocks[blk_id];
+  const int slot = (int)(blockIdx.x - blk.cta_start) * TOPO_THREADS + (int)threadIdx.x;
   FastWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
-  int status = -1, n_star = 0, n_nbr = 0;
+  int status = -1, n_star = 0, n_nbr = 0, cell = 0;
   float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (cell < blk.num_orig) {
+  if (slot < blk.num_orig && blk.tets != nullptr) {
+    cell = (int)blk.order[slot];
     int t0 = blk.v2t[cell];
     status = t0 < 0 ? CELL_NO_TET
                     : star_bfs_uniform(cell, t0, blk.tets, blk.cc, ws, TOPO_STAR_CAP, TOPO_NBR_CAP, &n_star, &n_nbr, cmin, cmax);
@@ -896,16 +929,22 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__rest
   unsigned long long s0 = row_start[r], s1 = row_start[r + 1];
   for (unsigned long long sb = s0; sb < s1; sb += 32) {
     unsigned long long mine = sb + lane < s1 ? data[sb + lane] : 0ull;
+    // the quotient mass / div of the reference's accumulate step is computed once per record by
+    // the lane that loaded it (off the serial chain), then broadcast
+    const float my_m = u2f((uint32_t)(mine >> 32));
+    const int my_fp = (int)((mine >> 31) & 1u);
+    const double my_q = my_fp ? (double)fdiv(my_m, div) : (double)my_m / (double)div;
     int cnt = (int)(s1 - sb < 32 ? s1 - sb : 32);
     for (int j = 0; j < cnt; j++) {
-      unsigned long long d = __shfl_sync(0xffffffffu, mine, j);
-      int x0 = (int)(d & 0xffffu);
-      int len = (int)((d >> 16) & 0x7fffu);
-      int fp = (int)((d >> 31) & 1u);
-      float m = u2f((uint32_t)(d >> 32));
+      const unsigned lo32 = __shfl_sync(0xffffffffu, (unsigned)mine, j);
+      const double q = __shfl_sync(0xffffffffu, my_q, j);
+      const int x0 = (int)(lo32 & 0xffffu);
+      const int len = (int)((lo32 >> 16) & 0x7fffu);
+      const int fp = (int)(lo32 >> 31);
       for (int x = lane; x < len; x += 32) {
         int xx = x0 + x;
-        if (xx < nx) buf[xx] = accumulate(buf[xx], m, div, fp);
+        // double path: (float)((double)cur + q)  (src/dense.cpp:290,193); float path: cur + (m / div)  (:539)
+        if (xx < nx) buf[xx] = fp ? fadd(buf[xx], (float)q) : (float)((double)buf[xx] + q);
       }
       __syncwarp();
     }

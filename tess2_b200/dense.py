@@ -101,7 +101,8 @@ class Context:
             arr[i].tets = _ip(te)
             v2t = b.get("vert_to_tet")
             if v2t is not None:
-                v2t = np.ascontiguousarray(v2t, dtype=np.int32)
+                if not (isinstance(v2t, np.ndarray) and v2t.dtype == np.int32 and v2t.flags.c_contiguous):
+                    v2t = np.ascontiguousarray(v2t, dtype=np.int32)
                 keep.append(v2t)
                 arr[i].vert_to_tet = _ip(v2t)
             for d in range(3):

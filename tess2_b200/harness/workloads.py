@@ -24,6 +24,7 @@ def _save(path, blocks):
         out[f"{i}_tets"] = b["tets"]
         out[f"{i}_num_orig"] = np.array(b["num_orig"])
         out[f"{i}_bounds"] = np.stack([b["bounds_min"], b["bounds_max"]]).astype(np.float32)
+        out[f"{i}_v2t"] = b["vert_to_tet"]
     tmp = path + f".tmp{os.getpid()}.npz"
     np.savez(tmp, **out)
     os.replace(tmp, path)
@@ -34,7 +35,8 @@ def _load(path):
     blocks = []
     for i in range(int(z["n"])):
         blocks.append(dict(gid=int(z[f"{i}_gid"]), particles=z[f"{i}_particles"], tets=z[f"{i}_tets"],
-                           num_orig=int(z[f"{i}_num_orig"]), bounds_min=z[f"{i}_bounds"][0], bounds_max=z[f"{i}_bounds"][1]))
+                           num_orig=int(z[f"{i}_num_orig"]), bounds_min=z[f"{i}_bounds"][0], bounds_max=z[f"{i}_bounds"][1],
+                           vert_to_tet=z[f"{i}_v2t"]))
     return blocks
 
 
@@ -61,7 +63,7 @@ def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log
                 layout.append((len(layout), mn, mx))
     if gids is None:
         gids = list(range(len(layout)))
-    key = f"uniform_regular:{n_side}:{blocks_xyz}:{sorted(gids)}:v3"
+    key = f"uniform_regular:{n_side}:{blocks_xyz}:{sorted(gids)}:v4"
     path = _cache_path(key)
     if cache and os.path.exists(path):
         if log:
@@ -83,6 +85,8 @@ def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log
     # tessellate only the wanted gids
     delaunay._G.update(points=allp, owner=owner, bounds=bounds, dmin=dom_min, dmax=dom_max, margin0=None, max_growth=1.0)
     blocks = delaunay.tessellate_gids(gids, workers)
+    for b in blocks:   # dblock_t::vert_to_tet is part of what tess hands to dense (src/tess.cpp:767-787)
+        b["vert_to_tet"] = delaunay.fill_vert_to_tet(len(b["particles"]), b["tets"])
     if log:
         log(f"tessellated {len(gids)} blocks ({sum(b['num_orig'] for b in blocks)} particles, "
             f"{sum(len(b['tets']) for b in blocks)} tets) in {time.time() - t0:.1f} s")
