@@ -53,9 +53,9 @@ class Checker:
     def __init__(self, kind, path=None, prefix=None):
         self.kind = kind
         if path is None:
-            assert kind in ("reference", "port")
-            name = "libtess_ref.so" if kind == "reference" else "libtess_oracle.so"
-            prefix = "ref_" if kind == "reference" else "orc_"
+            assert kind in ("reference", "port", "dropin")
+            name = {"reference": "libtess_ref.so", "port": "libtess_oracle.so", "dropin": "libtess_dropin.so"}[kind]
+            prefix = {"reference": "ref_", "port": "orc_", "dropin": "drp_"}[kind]
             path = os.path.join(HERE, "_ref", name)
         self.prefix = prefix
         if not os.path.exists(path):

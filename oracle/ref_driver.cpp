@@ -20,6 +20,20 @@
 #include "tess/dense.hpp"
 #include "tess/volume.h"
 
+// -DTESSB200_DROPIN builds the SAME driver with one line changed: the call to the reference's dense()
+// becomes tessb200::dense() from include/tess_b200_diy.hpp (same signature + a GPU context).  That
+// library (oracle/_ref/libtess_dropin.so, entry point drp_dense) is the drop-in test: identical
+// DBlock objects in an identical diy::Master, only the dense stage swapped (tests/test_dropin.py).
+#ifdef TESSB200_DROPIN
+#include "tess_b200_diy.hpp"
+#define ref_dense drp_dense
+#define ref_fill_vert_to_tet drp_fill_vert_to_tet
+#define ref_circumcenters drp_circumcenters
+#define ref_complete drp_complete
+#define ref_volumes drp_volumes
+#define ref_cell_points drp_cell_points
+#endif
+
 extern "C" {
 
 struct ref_block_t
@@ -161,9 +175,22 @@ int ref_dense(ref_params_t *p, int nblocks, ref_block_t *blocks, int only_gid, c
   }
 
   double t0 = MPI_Wtime();
+#ifdef TESSB200_DROPIN
+  static tessb200_ctx *ctx = 0;
+  try {
+    if (!ctx) tessb200::check(tessb200_create(&ctx, 0));
+    tessb200::dense((alg)p->alg, p->num_given_bounds, p->given_mins, p->given_maxs, p->project != 0, p->proj_plane,
+                    p->mass, p->data_mins, p->data_maxs, p->grid_phys_mins, p->grid_phys_maxs, p->grid_step_size,
+                    p->eps, p->glo_num_idx, master, ctx);
+  } catch (const tessb200::Error &e) {
+    fprintf(stderr, "drp_dense: %s\n", e.what());
+    return e.code;
+  }
+#else
   dense((alg)p->alg, p->num_given_bounds, p->given_mins, p->given_maxs, p->project != 0, p->proj_plane,
         p->mass, p->data_mins, p->data_maxs, p->grid_phys_mins, p->grid_phys_maxs, p->grid_step_size,
         p->eps, p->glo_num_idx, master);
+#endif
   p->seconds = MPI_Wtime() - t0;
 
   int rc = 0;

@@ -129,7 +129,7 @@ struct BlockRes
   int num_orig = 0, num_particles = 0, num_tets = 0;
   float bmin[3], bmax[3];
   bool have_v2t = false;
-  Buf particles, tets, v2t, cc, order, mkeys, mkeys2, order2;
+  Buf particles, tets, v2t, cc;
   // geometry of the last run
   int mn[3], num[3];
   long long npts = 0, nrows = 0, row_base = 0, out_off = 0;
@@ -154,7 +154,7 @@ struct tessb200_ctx
   ncclComm_t comm = nullptr;
 #endif
   Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
-  Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data;
+  Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2];
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
@@ -200,7 +200,6 @@ static void free_blocks(tessb200_ctx *c)
 {
   for (BlockRes *b : c->blocks) {
     b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
-    b->order.release(); b->mkeys.release(); b->mkeys2.release(); b->order2.release();
     delete b;
   }
   c->blocks.clear();
@@ -214,7 +213,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   free_blocks(c);
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
-                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data};
+                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1]};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -365,7 +364,6 @@ extern "C" int tessb200_dense_upload(tessb200_ctx *c, int nblocks, const tessb20
   while ((int)c->blocks.size() > nblocks) {
     BlockRes *b = c->blocks.back();
     b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
-    b->order.release(); b->mkeys.release(); b->mkeys2.release(); b->order2.release();
     delete b;
     c->blocks.pop_back();
   }
@@ -406,7 +404,7 @@ static DevBlock dev_block(const BlockRes *b)
   d.cc = (const float4 *)b->cc.p;
   d.num_orig = b->num_orig; d.num_particles = b->num_particles; d.num_tets = b->num_tets;
   d.cell_base = b->cell_base;
-  d.order = (const uint32_t *)b->order.p;
+  d.order = nullptr;
   d.cta_start = 0;
   d.pad_ = 0;
   return d;
@@ -430,22 +428,37 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b)
   return 0;
 }
 
-// processing order of a block's cells: Morton order of the sites (results do not depend on it)
-static int prep_block_order(tessb200_ctx *c, BlockRes *b)
+// processing order of the cells: Morton order of the sites inside each block (results do not depend
+// on it).  One radix sort for all blocks: key = block tag | Morton bits.
+static int prep_cell_order(tessb200_ctx *c, long long cells)
 {
-  const int n = b->num_orig;
-  if (n == 0) return 0;
-  TRY(b->order.ensure(4 * (size_t)n)); TRY(b->order2.ensure(4 * (size_t)n));
-  TRY(b->mkeys.ensure(4 * (size_t)n)); TRY(b->mkeys2.ensure(4 * (size_t)n));
-  float3 bmin = make_float3(b->bmin[0], b->bmin[1], b->bmin[2]);
-  float3 inv = make_float3(1.0f / fmaxf(b->bmax[0] - b->bmin[0], 1e-30f), 1.0f / fmaxf(b->bmax[1] - b->bmin[1], 1e-30f),
-                           1.0f / fmaxf(b->bmax[2] - b->bmin[2], 1e-30f));
-  k_morton_keys<<<cdiv(n, 256), 256, 0, c->stream>>>((const float *)b->particles.p, n, bmin, inv, b->mkeys.as<uint32_t>(), b->order2.as<uint32_t>());
-  COUNT_LAUNCH(c, 1);
+  if (cells == 0) return 0;
+  const int nloc = (int)c->blocks.size();
+  const int blk_bits = ceil_log2((unsigned long long)nloc);
+  int morton_bits = 32 - blk_bits;
+  if (morton_bits > 30) morton_bits = 30;
+  morton_bits -= morton_bits % 3;
+  for (int i = 0; i < 2; i++) { TRY(c->mkeys[i].ensure(4 * (size_t)cells)); TRY(c->order[i].ensure(4 * (size_t)cells)); }
+  long long off = 0;
+  for (int k = 0; k < nloc; k++) {
+    BlockRes *b = c->blocks[k];
+    const int n = b->num_orig;
+    if (n) {
+      float3 bmin = make_float3(b->bmin[0], b->bmin[1], b->bmin[2]);
+      float3 inv = make_float3(1.0f / fmaxf(b->bmax[0] - b->bmin[0], 1e-30f), 1.0f / fmaxf(b->bmax[1] - b->bmin[1], 1e-30f),
+                               1.0f / fmaxf(b->bmax[2] - b->bmin[2], 1e-30f));
+      k_morton_keys<<<cdiv(n, 256), 256, 0, c->stream>>>((const float *)b->particles.p, n, bmin, inv, (uint32_t)k << morton_bits, 30 - morton_bits,
+                                                       c->mkeys[0].as<uint32_t>() + off, c->order[0].as<uint32_t>() + off);
+      COUNT_LAUNCH(c, 1);
+    }
+    off += n;
+  }
   size_t tmp = 0;
-  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, b->mkeys.as<uint32_t>(), b->mkeys2.as<uint32_t>(), b->order2.as<uint32_t>(), b->order.as<uint32_t>(), n, 0, 30, c->stream));
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->mkeys[0].as<uint32_t>(), c->mkeys[1].as<uint32_t>(), c->order[0].as<uint32_t>(),
+                                     c->order[1].as<uint32_t>(), (int)cells, 0, morton_bits + blk_bits, c->stream));
   TRY(c->cub_tmp.ensure(tmp));
-  CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, b->mkeys.as<uint32_t>(), b->mkeys2.as<uint32_t>(), b->order2.as<uint32_t>(), b->order.as<uint32_t>(), n, 0, 30, c->stream));
+  CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->mkeys[0].as<uint32_t>(), c->mkeys[1].as<uint32_t>(), c->order[0].as<uint32_t>(),
+                                     c->order[1].as<uint32_t>(), (int)cells, 0, morton_bits + blk_bits, c->stream));
   return 0;
 }
 
@@ -479,11 +492,15 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   std::vector<DevBlock> hblocks(nall);
   memset(hblocks.data(), 0, sizeof(DevBlock) * nall);
   uint32_t bfs_ctas = 0;
+  long long order_off = 0;
+  if (p->alg == TESSB200_DENSE_TESS)
+    for (int i = 0; i < 2; i++) { TRY(c->mkeys[i].ensure(4 * (size_t)std::max<long long>(1, cells))); TRY(c->order[i].ensure(4 * (size_t)std::max<long long>(1, cells))); }
   for (int i = 0; i < nall; i++)
     if (G.local_of[i] >= 0) {
       BlockRes *b = c->blocks[G.local_of[i]];
-      if (p->alg == TESSB200_DENSE_TESS && b->num_orig) { TRY(b->order.ensure(4 * (size_t)b->num_orig)); }
       hblocks[i] = dev_block(b);
+      hblocks[i].order = c->order[1].as<uint32_t>() + order_off;   // sorted ids land in order[1] (blocks in local order)
+      order_off += b->num_orig;
       hblocks[i].cta_start = bfs_ctas;
       bfs_ctas += cdiv(b->num_orig, TOPO_THREADS);
     }
@@ -513,7 +530,8 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   CU(cudaEventRecord(c->ev[3], s));
   if (p->alg == TESSB200_DENSE_TESS) {
     // K0/K1
-    for (BlockRes *b : c->blocks) { TRY(prep_block_geometry(c, b)); TRY(prep_block_order(c, b)); }
+    for (BlockRes *b : c->blocks) TRY(prep_block_geometry(c, b));
+    TRY(prep_cell_order(c, cells));
     CU(cudaEventRecord(c->ev[4], s));
     // K3a part 1
     TRY(c->plane_pool.ensure(48 * ((size_t)2 * tets + (size_t)cells + 64)));   // sum of faces <= 4 T
@@ -765,7 +783,7 @@ extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nbl
 struct TmpBlock
 {
   BlockRes b;
-  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.order.release(); b.mkeys.release(); b.mkeys2.release(); b.order2.release(); }
+  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); }
 };
 
 static int upload_tmp(tessb200_ctx *c, TmpBlock &t, int num_particles, const float *particles, int num_tets, const int *tets, const int *v2t)

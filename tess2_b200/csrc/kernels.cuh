@@ -288,8 +288,8 @@ __device__ __forceinline__ uint32_t spread10(uint32_t x)
   x = (x | (x << 2)) & 0x09249249u;
   return x;
 }
-__global__ void k_morton_keys(const float *__restrict__ particles, int n, float3 bmin, float3 inv_ext, uint32_t *__restrict__ keys,
-                              uint32_t *__restrict__ ids)
+__global__ void k_morton_keys(const float *__restrict__ particles, int n, float3 bmin, float3 inv_ext, uint32_t blk_tag, int drop_bits,
+                              uint32_t *__restrict__ keys, uint32_t *__restrict__ ids)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -297,7 +297,8 @@ __global__ void k_morton_keys(const float *__restrict__ particles, int n, float3
         z = (particles[3 * (size_t)i + 2] - bmin.z) * inv_ext.z;
   uint32_t xi = (uint32_t)fminf(fmaxf(x * 1024.0f, 0.0f), 1023.0f), yi = (uint32_t)fminf(fmaxf(y * 1024.0f, 0.0f), 1023.0f),
            zi = (uint32_t)fminf(fmaxf(z * 1024.0f, 0.0f), 1023.0f);
-  keys[i] = spread10(xi) | (spread10(yi) << 1) | (spread10(zi) << 2);
+  // block tag above the Morton bits: ONE sort orders the cells of every block, block by block
+  keys[i] = blk_tag | ((spread10(xi) | (spread10(yi) << 1) | (spread10(zi) << 2)) >> drop_bits);
   ids[i] = (uint32_t)i;
 }
 
