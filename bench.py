@@ -207,6 +207,10 @@ def pinned_copy(a):
 
 
 def run_ours(args, rank, world, local_rank):
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner)
+    # is diverted to stderr for the duration of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import tess2_b200
@@ -308,6 +312,8 @@ def run_ours(args, rank, world, local_rank):
     }
     stage_ms = {"k_circumcenters": stage["ms_circumcenters"], "k_cell_topo": stage["ms_cells"], "k_cell_scan": stage["ms_scan"],
                 "sort (cub radix, 64-bit key + 64-bit payload)": stage["ms_sort"], "k_rows": stage["ms_deposit"]}
+    stage_ms["nccl span exchange"] = stage["ms_exchange"]
+    alg_bytes["nccl span exchange"] = 0
     stage_ms = {k: v / args.steps for k, v in stage_ms.items()}
     dom = max((k for k in stage_ms if k.startswith("k_")), key=lambda k: stage_ms[k])
     traffic = None
@@ -354,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
                       "deposit_cells": int(st.num_deposit_cells), "cic_fallback_cells": int(st.num_cic_fallback), "slow_cells": int(st.num_slow_cells),
                       "tot_mass": float(st.tot_mass)},
         }
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -154,7 +154,7 @@ struct tessb200_ctx
   ncclComm_t comm = nullptr;
 #endif
   Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
-  Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2];
+  Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2], x_small;
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
@@ -213,7 +213,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   free_blocks(c);
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
-                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1]};
+                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -980,30 +980,67 @@ extern "C" int tessb200_comm_init(tessb200_ctx *c, int nranks, int rank, const v
   return 0;
 }
 
-// Replaces master.exchange() (src/dense.cpp:98): span records whose row belongs to another rank's
-// blocks are partitioned by destination (a stable radix pass on the destination rank), the
-// nranks x nranks count matrix is all-gathered, and the payload moves with grouped
-// ncclSend/ncclRecv over NVLink.  Only boundary cells produce such records.
-__global__ void k_dest_rank(const uint64_t *__restrict__ keys, unsigned long long n, KeyLayout kl, const long long *__restrict__ rank_row_end,
-                            int nranks, uint32_t *__restrict__ dest, unsigned long long *__restrict__ counts)
+// Replaces master.exchange() (src/dense.cpp:98).  Only span records whose row belongs to another
+// rank's blocks move (boundary cells: O(surface)): they are counted per destination, the
+// nranks x nranks count matrix is all-gathered (one host sync), the records are compacted into
+// per-destination segments of a send buffer -- their slots in the local list are overwritten with a
+// sentinel key that sorts behind every row -- and the payload crosses NVLink with grouped
+// ncclSend / ncclRecv straight into the tail of the local list.
+__device__ __forceinline__ int dest_rank_of(uint64_t key, const KeyLayout &kl, const long long *__restrict__ rank_row_end, int nranks)
+{
+  long long row = (long long)key_row(kl, key);
+  int r = 0;
+  while (r < nranks - 1 && row >= rank_row_end[r]) r++;
+  return r;
+}
+__global__ void k_count_remote(const uint64_t *__restrict__ keys, unsigned long long n, KeyLayout kl, const long long *__restrict__ rank_row_end,
+                               int nranks, int me, unsigned long long *__restrict__ counts)
 {
   unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  long long row = (long long)key_row(kl, keys[i]);
-  int r = 0;
-  while (r < nranks - 1 && row >= rank_row_end[r]) r++;
-  dest[i] = (uint32_t)r;
-  atomicAdd(&counts[r], 1ull);
+  int r = dest_rank_of(keys[i], kl, rank_row_end, nranks);
+  if (r != me) atomicAdd(&counts[r], 1ull);
+}
+__global__ void k_scatter_remote(uint64_t *__restrict__ keys, const uint64_t *__restrict__ data, unsigned long long n, KeyLayout kl,
+                                 const long long *__restrict__ rank_row_end, int nranks, int me, unsigned long long *__restrict__ cursor,
+                                 uint64_t *__restrict__ send_k, uint64_t *__restrict__ send_d, uint64_t sentinel)
+{
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = keys[i];
+  int r = dest_rank_of(k, kl, rank_row_end, nranks);
+  if (r == me) return;
+  unsigned long long pos = atomicAdd(&cursor[r], 1ull);
+  send_k[pos] = k;
+  send_d[pos] = data[i];
+  keys[i] = sentinel;
+}
+
+// grow a device buffer, keeping its first keep_bytes
+static int grow_keep(Buf &b, size_t bytes, size_t keep_bytes, cudaStream_t s)
+{
+  if (bytes <= b.cap) return 0;
+  Buf nb;
+  TRY(nb.ensure(bytes));
+  if (keep_bytes && b.p) {
+    cudaError_t e = cudaMemcpyAsync(nb.p, b.p, keep_bytes, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { nb.release(); return fail(TESSB200_ECUDA, "grow_keep: %s", cudaGetErrorString(e)); }
+  }
+  b.release();
+  b = nb;
+  return 0;
 }
 
 static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned long long *n_spans)
 {
   cudaStream_t s = c->stream;
-  const int R = c->nranks;
+  const int R = c->nranks, me = c->rank;
   // row range end of every rank (blocks of a rank are contiguous in gid order)
   std::vector<long long> row_end(R, 0);
   {
     const std::vector<LayoutBlock> &L = c->layout;
+    if (L.empty()) return fail(TESSB200_ESTATE, "multi-GPU run without tessb200_dense_set_layout");
     for (size_t i = 0; i < L.size(); i++) {
       long long nrows = G.g.project ? G.boxes[i].b_num[1] : (long long)G.boxes[i].b_num[1] * G.boxes[i].b_num[2];
       long long end = G.boxes[i].row_base + nrows;
@@ -1012,73 +1049,58 @@ static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned 
     }
     for (int r = 1; r < R; r++) row_end[r] = std::max(row_end[r], row_end[r - 1]);
   }
-  unsigned long long n = *n_spans;
-  Buf d_row_end, d_dest, d_dest2, d_counts, d_all;
-  auto cleanup = [&]() { d_row_end.release(); d_dest.release(); d_dest2.release(); d_counts.release(); d_all.release(); };
-  int rc = 0;
-  if ((rc = d_row_end.ensure(8 * R)) || (rc = d_dest.ensure(4 * (size_t)std::max<unsigned long long>(1, n))) ||
-      (rc = d_dest2.ensure(4 * (size_t)std::max<unsigned long long>(1, n))) || (rc = d_counts.ensure(8 * R)) || (rc = d_all.ensure(8 * (size_t)R * R))) {
-    cleanup();
-    return rc;
-  }
-  cudaMemcpyAsync(d_row_end.p, row_end.data(), 8 * R, cudaMemcpyHostToDevice, s);
-  cudaMemsetAsync(d_counts.p, 0, 8 * R, s);
-  if (n) k_dest_rank<<<cdiv((long long)n, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n, G.kl, d_row_end.as<long long>(), R, d_dest.as<uint32_t>(),
-                                                            d_counts.as<unsigned long long>());
-  // group records by destination: two stable sorts with the same small key keep keys/data paired
+  const unsigned long long n = *n_spans;
+  TRY(c->x_small.ensure(8 * (size_t)(R + R + (size_t)R * R)));      // row_end | counts / cursor | all-gathered matrix
+  long long *d_row_end = c->x_small.as<long long>();
+  unsigned long long *d_counts = c->x_small.as<unsigned long long>() + R;
+  unsigned long long *d_all = d_counts + R;
+  CU(cudaMemcpyAsync(d_row_end, row_end.data(), 8 * (size_t)R, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(d_counts, 0, 8 * (size_t)R, s));
   if (n) {
-    size_t tb1 = 0, tb2 = 0;
-    int bits = std::max(1, ceil_log2((unsigned long long)R));
-    cub::DeviceRadixSort::SortPairs(nullptr, tb1, d_dest.as<uint32_t>(), d_dest2.as<uint32_t>(), c->keys[cur].as<uint64_t>(), c->keys[cur ^ 1].as<uint64_t>(), (int)n, 0, bits, s);
-    tb2 = tb1;
-    if ((rc = c->cub_tmp.ensure(tb1))) { cleanup(); return rc; }
-    cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb1, d_dest.as<uint32_t>(), d_dest2.as<uint32_t>(), c->keys[cur].as<uint64_t>(), c->keys[cur ^ 1].as<uint64_t>(), (int)n, 0, bits, s);
-    cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb2, d_dest.as<uint32_t>(), d_dest2.as<uint32_t>(), c->data[cur].as<uint64_t>(), c->data[cur ^ 1].as<uint64_t>(), (int)n, 0, bits, s);
+    k_count_remote<<<cdiv((long long)n, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n, G.kl, d_row_end, R, me, d_counts);
+    COUNT_LAUNCH(c, 1);
   }
-  ncclResult_t nr = ncclw::g.AllGather(d_counts.p, d_all.p, (size_t)R, ncclUint64, c->comm, s);
-  if (nr != ncclSuccess) { cleanup(); return fail(TESSB200_ENCCL, "ncclAllGather: %s", ncclw::g.GetErrorString(nr)); }
+  NC(ncclw::g.AllGather(d_counts, d_all, (size_t)R, ncclUint64, c->comm, s));
   std::vector<unsigned long long> all((size_t)R * R);
-  cudaMemcpyAsync(all.data(), d_all.p, 8 * (size_t)R * R, cudaMemcpyDeviceToHost, s);
-  cudaError_t e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) { cleanup(); return fail(TESSB200_ECUDA, "exchange: %s", cudaGetErrorString(e)); }
+  CU(cudaMemcpyAsync(all.data(), d_all, 8 * (size_t)R * R, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   // all[src * R + dst]
-  unsigned long long recv_total = 0;
-  for (int src = 0; src < R; src++) recv_total += all[(size_t)src * R + c->rank];
-  // receive into the "current" buffers (the partitioned copies live in cur ^ 1)
-  for (int i = 0; i < 2; i++) {
-    // keep the partitioned source intact: only grow the destination side
+  std::vector<unsigned long long> soff(R + 1, 0), roff(R + 1, 0);
+  for (int r = 0; r < R; r++) {
+    soff[r + 1] = soff[r] + all[(size_t)me * R + r];
+    roff[r + 1] = roff[r] + all[(size_t)r * R + me];
   }
-  if ((rc = c->recv_keys.ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total))) ||
-      (rc = c->recv_data.ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total)))) { cleanup(); return rc; }
-  const uint64_t *sk = c->keys[cur ^ 1].as<uint64_t>(), *sd = c->data[cur ^ 1].as<uint64_t>();
-  uint64_t *rk = c->recv_keys.as<uint64_t>(), *rd = c->recv_data.as<uint64_t>();
-  ncclw::g.GroupStart();
-  unsigned long long soff = 0, roff = 0;
+  const unsigned long long send_total = soff[R], recv_total = roff[R];
+  TRY(c->recv_keys.ensure(8 * (size_t)std::max<unsigned long long>(1, send_total)));   // used as the send buffers
+  TRY(c->recv_data.ensure(8 * (size_t)std::max<unsigned long long>(1, send_total)));
+  for (int i = 0; i < 2; i++) {
+    TRY(grow_keep(c->keys[i], 8 * (size_t)(n + recv_total), i == cur ? 8 * (size_t)n : 0, s));
+    TRY(grow_keep(c->data[i], 8 * (size_t)(n + recv_total), i == cur ? 8 * (size_t)n : 0, s));
+  }
+  uint64_t *sk = c->recv_keys.as<uint64_t>(), *sd = c->recv_data.as<uint64_t>();
+  uint64_t *lk = c->keys[cur].as<uint64_t>(), *ld = c->data[cur].as<uint64_t>();
+  if (send_total) {
+    CU(cudaMemcpyAsync(d_counts, soff.data(), 8 * (size_t)R, cudaMemcpyHostToDevice, s));   // cursors start at the segment offsets
+    const uint64_t sentinel = G.key_bits >= 64 ? ~0ull : ((1ull << G.key_bits) - 1ull);
+    k_scatter_remote<<<cdiv((long long)n, 256), 256, 0, s>>>(lk, ld, n, G.kl, d_row_end, R, me, d_counts, sk, sd, sentinel);
+    COUNT_LAUNCH(c, 1);
+  }
+  NC(ncclw::g.GroupStart());
   for (int peer = 0; peer < R; peer++) {
-    unsigned long long ns = all[(size_t)c->rank * R + peer], nrcv = all[(size_t)peer * R + c->rank];
-    if (peer == c->rank) {
-      cudaMemcpyAsync(rk + roff, sk + soff, 8 * (size_t)ns, cudaMemcpyDeviceToDevice, s);
-      cudaMemcpyAsync(rd + roff, sd + soff, 8 * (size_t)ns, cudaMemcpyDeviceToDevice, s);
-    } else {
-      if (ns) { ncclw::g.Send(sk + soff, (size_t)ns, ncclUint64, peer, c->comm, s); ncclw::g.Send(sd + soff, (size_t)ns, ncclUint64, peer, c->comm, s); }
-      if (nrcv) { ncclw::g.Recv(rk + roff, (size_t)nrcv, ncclUint64, peer, c->comm, s); ncclw::g.Recv(rd + roff, (size_t)nrcv, ncclUint64, peer, c->comm, s); }
+    if (peer == me) continue;
+    const unsigned long long ns = all[(size_t)me * R + peer], nr = all[(size_t)peer * R + me];
+    if (ns) {
+      NC(ncclw::g.Send(sk + soff[peer], (size_t)ns, ncclUint64, peer, c->comm, s));
+      NC(ncclw::g.Send(sd + soff[peer], (size_t)ns, ncclUint64, peer, c->comm, s));
     }
-    soff += ns;
-    roff += nrcv;
+    if (nr) {
+      NC(ncclw::g.Recv(lk + n + roff[peer], (size_t)nr, ncclUint64, peer, c->comm, s));
+      NC(ncclw::g.Recv(ld + n + roff[peer], (size_t)nr, ncclUint64, peer, c->comm, s));
+    }
   }
-  nr = ncclw::g.GroupEnd();
-  if (nr != ncclSuccess) { cleanup(); return fail(TESSB200_ENCCL, "ncclGroupEnd: %s", ncclw::g.GetErrorString(nr)); }
-  // the received records become the current span list
-  for (int i = 0; i < 2; i++) {
-    if ((rc = c->keys[i].ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total))) ||
-        (rc = c->data[i].ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total)))) { cleanup(); return rc; }
-  }
-  cudaMemcpyAsync(c->keys[cur].p, rk, 8 * (size_t)recv_total, cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(c->data[cur].p, rd, 8 * (size_t)recv_total, cudaMemcpyDeviceToDevice, s);
-  e = cudaStreamSynchronize(s);
-  cleanup();
-  if (e != cudaSuccess) return fail(TESSB200_ECUDA, "exchange: %s", cudaGetErrorString(e));
-  *n_spans = recv_total;
+  NC(ncclw::g.GroupEnd());
+  CU(cudaGetLastError());
+  *n_spans = n + recv_total;
   return 0;
 }
 #endif
