@@ -147,6 +147,9 @@ struct tessb200_ctx
 {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t blk_ev[64];
+  std::vector<cudaEvent_t> h2d_ev;
   std::vector<BlockRes *> blocks;   // uploaded blocks of this rank, ascending gid
   std::vector<LayoutBlock> layout;  // every block of the decomposition (multi-GPU), ascending gid
   int nranks = 1, rank = 0;
@@ -185,6 +188,8 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   tessb200_ctx *c = new tessb200_ctx;
   c->device = device;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto &ev : c->blk_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CU(cudaMallocHost(&c->h_cnt, sizeof(Counters)));
   CU(cudaMallocHost(&c->h_sum, sizeof(double) * 1024));
   CU(cudaMallocHost(&c->h_max, sizeof(float) * 1024));
@@ -220,6 +225,9 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
 #endif
   cudaFreeHost(c->h_cnt); cudaFreeHost(c->h_sum); cudaFreeHost(c->h_max);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
+  for (auto &ev : c->blk_ev) cudaEventDestroy(ev);
+  for (auto &ev : c->h2d_ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -253,12 +261,22 @@ static int check_params(const tessb200_dense_params *p)
 }
 
 // fills params outputs and every block's grid geometry; `all` = every block of the decomposition
-static int make_geometry(tessb200_ctx *c, tessb200_dense_params *p, Geometry *G)
+static int make_geometry(tessb200_ctx *c, tessb200_dense_params *p, Geometry *G, const tessb200_block *hb = nullptr, int nhb = 0)
 {
   TRY(check_params(p));
   std::vector<LayoutBlock> all;
   if (!c->layout.empty()) all = c->layout;
-  else
+  else if (hb) {
+    // geometry only, straight from the caller's blocks (nothing needs to be uploaded)
+    for (int i = 0; i < nhb; i++) {
+      LayoutBlock l;
+      l.gid = hb[i].gid;
+      memcpy(l.bmin, hb[i].bounds_min, 12); memcpy(l.bmax, hb[i].bounds_max, 12);
+      l.owner = -1;
+      all.push_back(l);
+    }
+    std::sort(all.begin(), all.end(), [](const LayoutBlock &x, const LayoutBlock &y) { return x.gid < y.gid; });
+  } else
     for (BlockRes *b : c->blocks) {
       LayoutBlock l;
       l.gid = b->gid;
@@ -305,6 +323,7 @@ static int make_geometry(tessb200_ctx *c, tessb200_dense_params *p, Geometry *G)
       int li = -1;
       for (size_t k = 0; k < c->blocks.size(); k++)
         if (c->blocks[k]->gid == all[i].gid) li = (int)k;
+      if (li < 0 && hb) { row_base += nrows; continue; }
       if (li < 0) return fail(TESSB200_ESTATE, "block gid %d is owned by this rank but was not uploaded", all[i].gid);
       if (!seen_local) G->row0 = (unsigned long long)row_base;
       seen_local = true;
@@ -348,13 +367,21 @@ static int make_geometry(tessb200_ctx *c, tessb200_dense_params *p, Geometry *G)
 }
 
 // ---- upload ----------------------------------------------------------------------------------------
-extern "C" int tessb200_dense_upload(tessb200_ctx *c, int nblocks, const tessb200_block *blocks)
+static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *blocks, bool async)
 {
   if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
   if (nblocks < 1 || !blocks) return fail(TESSB200_EINVAL, "need at least one block");
   if (nblocks > 65535) return fail(TESSB200_ELIMIT, "more than 65535 blocks");
   CU(cudaSetDevice(c->device));
-  CU(cudaEventRecord(c->ev[0], c->stream));
+  // async: copies go to the copy stream with one event per block (the one-call path overlaps them
+  // with the cell kernels); otherwise they are complete when the call returns
+  cudaStream_t cs = async ? c->copy_stream : c->stream;
+  CU(cudaEventRecord(c->ev[0], cs));
+  while ((int)c->h2d_ev.size() < nblocks) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->h2d_ev.push_back(e);
+  }
   // reuse device buffers of a previous upload where possible
   std::vector<int> order(nblocks);
   for (int i = 0; i < nblocks; i++) order[i] = i;
@@ -383,16 +410,22 @@ extern "C" int tessb200_dense_upload(tessb200_ctx *c, int nblocks, const tessb20
     TRY(b->tets.ensure(32 * (size_t)std::max(1, hb.num_tets)));
     TRY(b->v2t.ensure(sizeof(int) * (size_t)std::max(1, hb.num_particles)));
     TRY(b->cc.ensure(16 * (size_t)std::max(1, hb.num_tets)));
-    if (hb.num_particles) CU(cudaMemcpyAsync(b->particles.p, hb.particles, sizeof(float) * 3 * (size_t)hb.num_particles, cudaMemcpyHostToDevice, c->stream));
-    if (hb.num_tets) CU(cudaMemcpyAsync(b->tets.p, hb.tets, 32 * (size_t)hb.num_tets, cudaMemcpyHostToDevice, c->stream));
+    if (hb.num_particles) CU(cudaMemcpyAsync(b->particles.p, hb.particles, sizeof(float) * 3 * (size_t)hb.num_particles, cudaMemcpyHostToDevice, cs));
+    if (hb.num_tets) CU(cudaMemcpyAsync(b->tets.p, hb.tets, 32 * (size_t)hb.num_tets, cudaMemcpyHostToDevice, cs));
     b->have_v2t = hb.vert_to_tet != nullptr;
     if (b->have_v2t && hb.num_particles)
-      CU(cudaMemcpyAsync(b->v2t.p, hb.vert_to_tet, sizeof(int) * (size_t)hb.num_particles, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(b->v2t.p, hb.vert_to_tet, sizeof(int) * (size_t)hb.num_particles, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(c->h2d_ev[k], cs));
   }
-  CU(cudaEventRecord(c->ev[1], c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventRecord(c->ev[1], cs));
+  if (!async) CU(cudaStreamSynchronize(cs));
   c->ran = false;
   return 0;
+}
+
+extern "C" int tessb200_dense_upload(tessb200_ctx *c, int nblocks, const tessb200_block *blocks)
+{
+  return upload_impl(c, nblocks, blocks, false);
 }
 
 static DevBlock dev_block(const BlockRes *b)
@@ -428,37 +461,38 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b)
   return 0;
 }
 
-// processing order of the cells: Morton order of the sites inside each block (results do not depend
-// on it).  One radix sort for all blocks: key = block tag | Morton bits.
-static int prep_cell_order(tessb200_ctx *c, long long cells)
+// processing order of the cells of local blocks [k0, k1): Morton order of the sites inside each block
+// (results do not depend on it).  One radix sort per group: key = block tag | Morton bits.  The
+// sorted ids of block k land in order[1] at the block's offset in the rank-wide cell numbering.
+static int prep_cell_order(tessb200_ctx *c, int k0, int k1, long long cell_off)
 {
+  long long cells = 0;
+  for (int k = k0; k < k1; k++) cells += c->blocks[k]->num_orig;
   if (cells == 0) return 0;
-  const int nloc = (int)c->blocks.size();
-  const int blk_bits = ceil_log2((unsigned long long)nloc);
+  const int blk_bits = ceil_log2((unsigned long long)(k1 - k0));
   int morton_bits = 32 - blk_bits;
   if (morton_bits > 30) morton_bits = 30;
   morton_bits -= morton_bits % 3;
-  for (int i = 0; i < 2; i++) { TRY(c->mkeys[i].ensure(4 * (size_t)cells)); TRY(c->order[i].ensure(4 * (size_t)cells)); }
-  long long off = 0;
-  for (int k = 0; k < nloc; k++) {
+  long long off = cell_off;
+  for (int k = k0; k < k1; k++) {
     BlockRes *b = c->blocks[k];
     const int n = b->num_orig;
     if (n) {
       float3 bmin = make_float3(b->bmin[0], b->bmin[1], b->bmin[2]);
       float3 inv = make_float3(1.0f / fmaxf(b->bmax[0] - b->bmin[0], 1e-30f), 1.0f / fmaxf(b->bmax[1] - b->bmin[1], 1e-30f),
                                1.0f / fmaxf(b->bmax[2] - b->bmin[2], 1e-30f));
-      k_morton_keys<<<cdiv(n, 256), 256, 0, c->stream>>>((const float *)b->particles.p, n, bmin, inv, (uint32_t)k << morton_bits, 30 - morton_bits,
+      k_morton_keys<<<cdiv(n, 256), 256, 0, c->stream>>>((const float *)b->particles.p, n, bmin, inv, (uint32_t)(k - k0) << morton_bits, 30 - morton_bits,
                                                        c->mkeys[0].as<uint32_t>() + off, c->order[0].as<uint32_t>() + off);
       COUNT_LAUNCH(c, 1);
     }
     off += n;
   }
   size_t tmp = 0;
-  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->mkeys[0].as<uint32_t>(), c->mkeys[1].as<uint32_t>(), c->order[0].as<uint32_t>(),
-                                     c->order[1].as<uint32_t>(), (int)cells, 0, morton_bits + blk_bits, c->stream));
+  uint32_t *k_in = c->mkeys[0].as<uint32_t>() + cell_off, *k_out = c->mkeys[1].as<uint32_t>() + cell_off;
+  uint32_t *v_in = c->order[0].as<uint32_t>() + cell_off, *v_out = c->order[1].as<uint32_t>() + cell_off;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (int)cells, 0, morton_bits + blk_bits, c->stream));
   TRY(c->cub_tmp.ensure(tmp));
-  CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->mkeys[0].as<uint32_t>(), c->mkeys[1].as<uint32_t>(), c->order[0].as<uint32_t>(),
-                                     c->order[1].as<uint32_t>(), (int)cells, 0, morton_bits + blk_bits, c->stream));
+  CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (int)cells, 0, morton_bits + blk_bits, c->stream));
   return 0;
 }
 
@@ -474,36 +508,89 @@ static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned 
 #endif
 
 // ---- run ---------------------------------------------------------------------------------------------
-extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_stats *st)
+// The stage runs group by group over the local blocks (cell kernels), then once over all span
+// records (exchange, sort, deposit).  Resident inputs: one group = all blocks.  One-call path
+// (tessb200_dense): one group per block, each waiting for that block's host-to-device copy, so the
+// cell kernels of block k overlap the copy of block k+1; the deposit then runs block by block with
+// the device-to-host copy of block k overlapping the deposit of block k+1.
+struct PipeIO
 {
-  if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
+  bool pipelined = false;
+  std::vector<cudaEvent_t> *h2d_done = nullptr;   // per local block (ctx->blocks order)
+  int nblocks_out = 0;
+  tessb200_block *out_blocks = nullptr;           // caller's blocks: density pointers for the streamed download
+  float *global_grid = nullptr;
+};
+
+static int copy_block_out(tessb200_ctx *c, const tessb200_dense_params &p, BlockRes *b, tessb200_block *ob, float *global_grid, cudaStream_t s)
+{
+  if (ob) {
+    memcpy(ob->block_min_idx, b->mn, 12); memcpy(ob->block_num_idx, b->num, 12);
+    ob->num_grid_pts = b->npts;
+    if (ob->density) {
+      if (ob->density_capacity < b->npts)
+        return fail(TESSB200_ECAPACITY, "block gid %d: density_capacity %lld < %lld grid points", b->gid, (long long)ob->density_capacity, b->npts);
+      if (b->npts) CU(cudaMemcpyAsync(ob->density, c->out.as<float>() + b->out_off, sizeof(float) * (size_t)b->npts, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  if (global_grid && b->npts) {
+    if (p.project) return fail(TESSB200_EINVAL, "global_grid is only assembled for 3-D runs; use tessb200_write_grid for projections");
+    const size_t gx = p.glo_num_idx[0], gy = p.glo_num_idx[1];
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.srcPtr = make_cudaPitchedPtr(c->out.as<float>() + b->out_off, sizeof(float) * (size_t)b->num[0], (size_t)b->num[0], (size_t)b->num[1]);
+    cp.dstPtr = make_cudaPitchedPtr(global_grid, sizeof(float) * gx, gx, gy);
+    cp.dstPos = make_cudaPos(sizeof(float) * (size_t)b->mn[0], (size_t)b->mn[1], (size_t)b->mn[2]);
+    cp.extent = make_cudaExtent(sizeof(float) * (size_t)b->num[0], (size_t)b->num[1], (size_t)b->num[2]);
+    cp.kind = cudaMemcpyDeviceToHost;
+    CU(cudaMemcpy3DAsync(&cp, s));
+  }
+  return 0;
+}
+
+static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_stats *st, const PipeIO &io)
+{
   if (c->blocks.empty()) return fail(TESSB200_ESTATE, "tessb200_dense_run before tessb200_dense_upload");
   CU(cudaSetDevice(c->device));
   Geometry G;
   TRY(make_geometry(c, p, &G));
   cudaStream_t s = c->stream;
-  c->launches = 0;
+  const int nloc = (int)c->blocks.size();
   const int nall = (int)G.boxes.size();
   long long cells = 0, tets = 0;
   for (BlockRes *b : c->blocks) { cells += b->num_orig; tets += b->num_tets; }
+  c->launches = 0;
+  const bool tess = p->alg == TESSB200_DENSE_TESS;
 
   CU(cudaEventRecord(c->ev[2], s));
+  // groups of local blocks (indices into c->blocks)
+  std::vector<std::pair<int, int> > groups;
+  if (io.pipelined) for (int k = 0; k < nloc; k++) groups.push_back(std::make_pair(k, k + 1));
+  else groups.push_back(std::make_pair(0, nloc));
+  int first_local_all = -1;
+  for (int i = 0; i < nall; i++) if (G.local_of[i] == 0) first_local_all = i;   // local blocks are contiguous in `all`
+  if (first_local_all < 0) return fail(TESSB200_ESTATE, "no local block in the layout");
+
   // device descriptors
+  if (tess)
+    for (int i = 0; i < 2; i++) { TRY(c->mkeys[i].ensure(4 * (size_t)std::max<long long>(1, cells))); TRY(c->order[i].ensure(4 * (size_t)std::max<long long>(1, cells))); }
   std::vector<DevBlock> hblocks(nall);
   memset(hblocks.data(), 0, sizeof(DevBlock) * nall);
-  uint32_t bfs_ctas = 0;
-  long long order_off = 0;
-  if (p->alg == TESSB200_DENSE_TESS)
-    for (int i = 0; i < 2; i++) { TRY(c->mkeys[i].ensure(4 * (size_t)std::max<long long>(1, cells))); TRY(c->order[i].ensure(4 * (size_t)std::max<long long>(1, cells))); }
-  for (int i = 0; i < nall; i++)
-    if (G.local_of[i] >= 0) {
-      BlockRes *b = c->blocks[G.local_of[i]];
-      hblocks[i] = dev_block(b);
-      hblocks[i].order = c->order[1].as<uint32_t>() + order_off;   // sorted ids land in order[1] (blocks in local order)
-      order_off += b->num_orig;
-      hblocks[i].cta_start = bfs_ctas;
-      bfs_ctas += cdiv(b->num_orig, TOPO_THREADS);
+  {
+    long long order_off = 0;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+      uint32_t ctas = 0;
+      for (int k = groups[gi].first; k < groups[gi].second; k++) {
+        BlockRes *b = c->blocks[k];
+        DevBlock &d = hblocks[first_local_all + k];
+        d = dev_block(b);
+        d.order = c->order[1].as<uint32_t>() + order_off;
+        order_off += b->num_orig;
+        d.cta_start = ctas;
+        ctas += cdiv(b->num_orig, TOPO_THREADS);
+      }
     }
+  }
   TRY(c->d_blocks.ensure(sizeof(DevBlock) * nall));
   TRY(c->d_boxes.ensure(sizeof(BlockBox) * nall));
   TRY(c->d_rblocks.ensure(sizeof(RowBlock) * std::max<size_t>(1, G.rblocks.size())));
@@ -516,9 +603,9 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   ScanCtx sc;
   sc.boxes = c->d_boxes.as<BlockBox>(); sc.nblocks = nall; sc.kl = G.kl; sc.project = G.g.project;
 
-  unsigned long long n_spans = 0;
   unsigned long long span_cap = 0;
-  auto ensure_spans = [&](unsigned long long cap) -> int {
+  auto ensure_spans = [&](unsigned long long cap, unsigned long long keep) -> int {
+    (void)keep;
     for (int i = 0; i < 2; i++) {
       TRY(c->keys[i].ensure(8 * (size_t)cap));
       TRY(c->data[i].ensure(8 * (size_t)cap));
@@ -527,91 +614,131 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     return 0;
   };
 
-  CU(cudaEventRecord(c->ev[3], s));
-  if (p->alg == TESSB200_DENSE_TESS) {
-    // K0/K1
-    for (BlockRes *b : c->blocks) TRY(prep_block_geometry(c, b));
-    TRY(prep_cell_order(c, cells));
-    CU(cudaEventRecord(c->ev[4], s));
-    // K3a part 1
-    TRY(c->plane_pool.ensure(48 * ((size_t)2 * tets + (size_t)cells + 64)));   // sum of faces <= 4 T (DESIGN.md)
+  // scratch that does not depend on the group
+  long long n_slow = 0;
+  TopoOut to;
+  memset(&to, 0, sizeof(to));
+  uint32_t cap_ovf = 0;
+  if (tess) {
+    TRY(c->plane_pool.ensure(48 * ((size_t)2 * tets + (size_t)cells + 64)));   // sum of faces <= 4 T (DESIGN.md 3)
     TRY(c->face_list.ensure(32 * ((size_t)2 * tets + (size_t)cells + 64)));
     TRY(c->hdr_small.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
     TRY(c->hdr_big.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
     TRY(c->big_bitoff.ensure(8 * (size_t)std::max<long long>(1, cells)));
-    const uint32_t cap_ovf = (uint32_t)std::max<long long>(1024, cells / 64);
+    cap_ovf = (uint32_t)std::max<long long>(1024, cells / 64);
     TRY(c->overflow.ensure(sizeof(uint2) * (size_t)cap_ovf));
-    TopoOut to;
     to.small = c->hdr_small.as<CellHdr>(); to.big = c->hdr_big.as<CellHdr>();
     to.big_bit_off = c->big_bitoff.as<unsigned long long>();
     to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.faces = c->face_list.as<FaceRef>(); to.cnt = cnt;
     to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
-    if (bfs_ctas) {
-      k_cell_bfs<<<bfs_ctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), nall, G.g, to);
+    TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells), 0));
+  } else {
+    TRY(ensure_spans(std::max<unsigned long long>(1ull << 16, 8ull * (unsigned long long)cells + 1024), 0));
+  }
+
+  CU(cudaEventRecord(c->ev[3], s));
+  float ms_cc = 0, ms_cells = 0, ms_scan = 0;
+  unsigned done_small = 0, done_big = 0, done_ovf = 0, done_pairs = 0;
+  unsigned long long done_bits = 0;
+  long long cell_off = 0;
+  for (size_t gi = 0; gi < groups.size(); gi++) {
+    const int k0 = groups[gi].first, k1 = groups[gi].second;
+    long long gcells = 0;
+    uint32_t gctas = 0;
+    for (int k = k0; k < k1; k++) {
+      if (io.pipelined && io.h2d_done) CU(cudaStreamWaitEvent(s, (*io.h2d_done)[k], 0));
+      gcells += c->blocks[k]->num_orig;
+      gctas += cdiv(c->blocks[k]->num_orig, TOPO_THREADS);
+    }
+    const bool timed = groups.size() == 1;
+    if (!tess) {
+      if (timed) { CU(cudaEventRecord(c->ev[4], s)); CU(cudaEventRecord(c->ev[5], s)); }
+      SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
+      for (int k = k0; k < k1; k++) {
+        const DevBlock &db = hblocks[first_local_all + k];
+        if (db.num_orig == 0) continue;
+        k_cic<<<cdiv(db.num_orig, 256), 256, 0, s>>>(db, first_local_all + k, sc, G.g, so);
+        COUNT_LAUNCH(c, 1);
+      }
+      CU(cudaGetLastError());
+      cell_off += gcells;
+      continue;
+    }
+    // K0 / K1 / processing order
+    for (int k = k0; k < k1; k++) TRY(prep_block_geometry(c, c->blocks[k]));
+    TRY(prep_cell_order(c, k0, k1, cell_off));
+    cell_off += gcells;
+    if (timed) CU(cudaEventRecord(c->ev[4], s));
+    // K3a part 1: BFS (+ general BFS for overflowing stars) and faces
+    if (gctas) {
+      k_cell_bfs<<<gctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to);
       COUNT_LAUNCH(c, 1);
     }
     CU(cudaGetLastError());
     TRY(read_counters(c));
     if (c->h_cnt->n_overflow > cap_ovf) return fail(TESSB200_ELIMIT, "%u cells exceed the fast star workspace (capacity %u)", c->h_cnt->n_overflow, cap_ovf);
-    long long n_slow = c->h_cnt->n_overflow;
-    if (c->h_cnt->n_overflow) {
-      int n = (int)c->h_cnt->n_overflow;
+    if (c->h_cnt->n_overflow > done_ovf) {
+      const int n = (int)(c->h_cnt->n_overflow - done_ovf);
       TRY(c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)n));
-      k_cell_bfs_big<<<cdiv((long long)n * 32, 128), 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>(), n, c->ws_big.as<int>());
+      k_cell_bfs_big<<<cdiv((long long)n * 32, 128), 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>() + done_ovf, n, c->ws_big.as<int>());
       COUNT_LAUNCH(c, 1);
       CU(cudaGetLastError());
+      n_slow += n;
+      done_ovf = c->h_cnt->n_overflow;
       TRY(read_counters(c));
     }
-    if (c->h_cnt->plane_cursor) {
-      k_cell_faces<<<cdiv((long long)c->h_cnt->plane_cursor * 2, 256), 256, 0, s>>>(c->face_list.as<FaceRef>(), cnt, c->d_blocks.as<DevBlock>(),
-                                                                                 c->plane_pool.as<float>(), cnt);
+    if (c->h_cnt->plane_cursor > done_pairs) {
+      const size_t f0 = (size_t)done_pairs * 2, f1 = (size_t)c->h_cnt->plane_cursor * 2;
+      k_cell_faces<<<cdiv((long long)(f1 - f0), 256), 256, 0, s>>>(c->face_list.as<FaceRef>(), f0, f1, c->d_blocks.as<DevBlock>(), c->plane_pool.as<float>(), cnt);
       COUNT_LAUNCH(c, 1);
       CU(cudaGetLastError());
+      done_pairs = c->h_cnt->plane_cursor;
     }
-    CU(cudaEventRecord(c->ev[5], s));
-    const unsigned n_small = c->h_cnt->n_small, n_big = c->h_cnt->n_big;
-    n_slow += n_big;
-    if (n_big) TRY(c->bits_big.ensure((size_t)(c->h_cnt->big_bits / 8) + 64));
-    TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells)));
-    for (int attempt = 0; attempt < 2; attempt++) {
-      SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
-      COUNT_LAUNCH(c, (n_small ? 1 : 0) + (n_big ? 1 : 0));
-      if (n_small)
-        k_cell_scan<<<cdiv(n_small, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), cnt, to.cap_small, c->plane_pool.as<float>(),
-                                                                              c->d_blocks.as<DevBlock>(), sc, G.g, so);
-      if (n_big)
-        k_cell_scan_big<<<n_big, 128, 0, s>>>(c->hdr_big.as<CellHdr>(), c->big_bitoff.as<unsigned long long>(), (int)n_big, c->plane_pool.as<float>(),
-                                              c->bits_big.as<uint32_t>(), c->d_blocks.as<DevBlock>(), sc, G.g, so);
-      CU(cudaGetLastError());
-      TRY(read_counters(c));
-      n_spans = c->h_cnt->n_spans;
-      if (n_spans <= span_cap) break;
-      if (attempt == 1) return fail(TESSB200_ECAPACITY, "span buffer overflow after regrow");
-      // regrow and redo the scan (counters of the scan stage reset)
-      TRY(ensure_spans(n_spans + n_spans / 16 + 1024));
-      Counters z = *c->h_cnt;
-      z.n_spans = 0; z.n_deposit = 0; z.n_cic_fallback = 0;
-      CU(cudaMemcpyAsync(c->d_cnt.p, &z, sizeof(Counters), cudaMemcpyHostToDevice, s));
-      CU(cudaStreamSynchronize(s));
-    }
-    if (st) st->num_slow_cells = n_slow;
-  } else {
-    CU(cudaEventRecord(c->ev[4], s));
-    CU(cudaEventRecord(c->ev[5], s));
-    TRY(ensure_spans(std::max<unsigned long long>(1ull << 16, 8ull * (unsigned long long)cells + 1024)));
+    if (timed) CU(cudaEventRecord(c->ev[5], s));
+    // K3a part 2: scan
+    const unsigned n_small = std::min(c->h_cnt->n_small, to.cap_small), n_big = std::min(c->h_cnt->n_big, to.cap_big);
+    if (n_big > done_big) TRY(c->bits_big.ensure((size_t)((c->h_cnt->big_bits - done_bits) / 8) + 64));
     SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
-    for (int i = 0; i < nall; i++) {
-      if (G.local_of[i] < 0) continue;
-      const DevBlock &db = hblocks[i];
-      if (db.num_orig == 0) continue;
-      k_cic<<<cdiv(db.num_orig, 256), 256, 0, s>>>(db, i, sc, G.g, so);
+    if (n_small > done_small) {
+      const unsigned n = n_small - done_small;
+      k_cell_scan<<<cdiv(n, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>() + done_small, n, c->plane_pool.as<float>(),
+                                                                         c->d_blocks.as<DevBlock>(), sc, G.g, so);
       COUNT_LAUNCH(c, 1);
     }
+    if (n_big > done_big) {
+      const unsigned n = n_big - done_big;
+      k_cell_scan_big<<<n, 128, 0, s>>>(c->hdr_big.as<CellHdr>() + done_big, c->big_bitoff.as<unsigned long long>() + done_big, (int)n,
+                                        c->plane_pool.as<float>(), c->bits_big.as<uint32_t>(), done_bits, c->d_blocks.as<DevBlock>(), sc, G.g, so);
+      COUNT_LAUNCH(c, 1);
+      n_slow += n;
+    }
+    CU(cudaGetLastError());
+    done_small = n_small; done_big = n_big; done_bits = c->h_cnt->big_bits;
+  }
+  // span count (and the rare regrow: the span buffer was too small -> redo the scans of every group)
+  TRY(read_counters(c));
+  unsigned long long n_spans = c->h_cnt->n_spans;
+  if (n_spans > span_cap) {
+    if (!tess) return fail(TESSB200_ECAPACITY, "span buffer overflow in CIC");
+    TRY(ensure_spans(n_spans + n_spans / 16 + 1024, 0));
+    Counters z = *c->h_cnt;
+    z.n_spans = 0; z.n_deposit = 0; z.n_cic_fallback = 0;
+    CU(cudaMemcpyAsync(c->d_cnt.p, &z, sizeof(Counters), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
+    if (done_small)
+      k_cell_scan<<<cdiv(done_small, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), done_small, c->plane_pool.as<float>(),
+                                                                                  c->d_blocks.as<DevBlock>(), sc, G.g, so);
+    if (done_big) {
+      TRY(c->bits_big.ensure((size_t)(c->h_cnt->big_bits / 8) + 64));
+      k_cell_scan_big<<<done_big, 128, 0, s>>>(c->hdr_big.as<CellHdr>(), c->big_bitoff.as<unsigned long long>(), (int)done_big, c->plane_pool.as<float>(),
+                                               c->bits_big.as<uint32_t>(), 0ull, c->d_blocks.as<DevBlock>(), sc, G.g, so);
+    }
+    COUNT_LAUNCH(c, 2);
     CU(cudaGetLastError());
     TRY(read_counters(c));
     n_spans = c->h_cnt->n_spans;
-    if (n_spans > span_cap) return fail(TESSB200_ECAPACITY, "span buffer overflow in CIC");
-    if (st) st->num_slow_cells = 0;
+    if (n_spans > span_cap) return fail(TESSB200_ECAPACITY, "span buffer overflow after regrow");
   }
   CU(cudaEventRecord(c->ev[6], s));
 
@@ -635,18 +762,37 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   }
   CU(cudaEventRecord(c->ev[8], s));
 
-  // deposit
+  // deposit: every grid point written exactly once
   TRY(c->row_start.ensure(8 * (size_t)(G.nrows + 2)));
   TRY(c->out.ensure(sizeof(float) * (size_t)std::max<long long>(4, G.out_floats)));
-  COUNT_LAUNCH(c, 2);
   k_row_starts<<<cdiv((long long)n_spans + 1, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows,
                                                                  c->row_start.as<unsigned long long>());
+  COUNT_LAUNCH(c, 1);
   {
     size_t smem = sizeof(float) * (size_t)ROWS_WARPS * (size_t)G.nx_max;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_rows<<<cdiv((long long)G.nrows, ROWS_WARPS), ROWS_WARPS * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0,
-                                                                               G.nrows, c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div,
-                                                                               G.nx_max, c->out.as<float>());
+    if (!io.pipelined) {
+      k_rows<<<cdiv((long long)G.nrows, ROWS_WARPS), ROWS_WARPS * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0, 0ull,
+                                                                                 G.nrows, c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div,
+                                                                                 G.nx_max, c->out.as<float>());
+      COUNT_LAUNCH(c, 1);
+    } else {
+      // block by block: the device-to-host copy of block k (copy stream) overlaps the deposit of block k+1
+      for (int k = 0; k < nloc; k++) {
+        BlockRes *b = c->blocks[k];
+        if (b->nrows) {
+          k_rows<<<cdiv(b->nrows, ROWS_WARPS), ROWS_WARPS * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0,
+                                                                            (unsigned long long)(b->row_base - (long long)G.row0), (unsigned long long)b->nrows,
+                                                                            c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div, G.nx_max, c->out.as<float>());
+          COUNT_LAUNCH(c, 1);
+        }
+        CU(cudaEventRecord(c->blk_ev[k % 64], s));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->blk_ev[k % 64], 0));
+        tessb200_block *ob = nullptr;
+        for (int j = 0; j < io.nblocks_out; j++) if (io.out_blocks[j].gid == b->gid) ob = &io.out_blocks[j];
+        TRY(copy_block_out(c, *p, b, ob, io.global_grid, c->copy_stream));
+      }
+    }
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[9], s));
@@ -670,6 +816,7 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   }
   CU(cudaEventRecord(c->ev[10], s));
   CU(cudaStreamSynchronize(s));
+  if (io.pipelined) CU(cudaStreamSynchronize(c->copy_stream));
 
   c->ran = true;
   c->last_params = *p;
@@ -681,16 +828,19 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
     st->num_outside = (int64_t)(c->h_cnt->n_outside + c->h_cnt->n_bad);
     st->num_deposit_cells = (int64_t)c->h_cnt->n_deposit;
     st->num_cic_fallback = (int64_t)c->h_cnt->n_cic_fallback;
+    st->num_slow_cells = n_slow;
     st->num_spans = (int64_t)n_spans;
     st->num_tets = tets;
     st->num_kernel_launches = c->launches;
     st->num_grid_pts = 0;
     for (BlockRes *b : c->blocks) st->num_grid_pts += b->npts;
     auto ms = [&](int a, int b) { float m = 0; cudaEventElapsedTime(&m, c->ev[a], c->ev[b]); return m; };
-    st->ms_upload = ms(0, 1);
-    st->ms_circumcenters = ms(3, 4);
-    st->ms_cells = ms(4, 5);
-    st->ms_scan = ms(5, 6);
+    (void)ms_cc; (void)ms_cells; (void)ms_scan;
+    const bool one = groups.size() == 1;
+    st->ms_upload = 0;
+    st->ms_circumcenters = one ? ms(3, 4) : 0;
+    st->ms_cells = one ? ms(4, 5) : 0;
+    st->ms_scan = one ? ms(5, 6) : ms(3, 6);      // pipelined: all cell stages together (they overlap the copies)
     st->ms_exchange = ms(6, 7);
     st->ms_sort = ms(7, 8);
     st->ms_deposit = ms(8, 9);
@@ -700,17 +850,34 @@ extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tes
   return 0;
 }
 
-extern "C" int tessb200_dense_geometry(tessb200_ctx *c, tessb200_dense_params *p, int nblocks, tessb200_block *blocks)
+extern "C" int tessb200_dense_run(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_stats *st)
 {
   if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
+  PipeIO io;
+  return run_impl(c, p, st, io);
+}
+
+extern "C" int tessb200_dense_geometry(tessb200_ctx *c, tessb200_dense_params *p, int nblocks, tessb200_block *blocks)
+{
+  if (!c || !blocks || nblocks < 1) return fail(TESSB200_EINVAL, "NULL argument");
   Geometry G;
-  TRY(make_geometry(c, p, &G));
+  TRY(make_geometry(c, p, &G, blocks, nblocks));
+  // G.boxes follows the layout (ascending gid); match the caller's blocks by gid
+  std::vector<std::pair<int, int> > gids;   // (gid, index in G.boxes)
+  if (!c->layout.empty()) for (size_t i = 0; i < c->layout.size(); i++) gids.push_back(std::make_pair(c->layout[i].gid, (int)i));
+  else {
+    std::vector<int> g(nblocks);
+    for (int i = 0; i < nblocks; i++) g[i] = blocks[i].gid;
+    std::sort(g.begin(), g.end());
+    for (int i = 0; i < nblocks; i++) gids.push_back(std::make_pair(g[i], i));
+  }
   for (int i = 0; i < nblocks; i++) {
-    BlockRes *b = nullptr;
-    for (BlockRes *x : c->blocks) if (x->gid == blocks[i].gid) b = x;
-    if (!b) return fail(TESSB200_EINVAL, "block gid %d was not uploaded", blocks[i].gid);
-    memcpy(blocks[i].block_min_idx, b->mn, 12); memcpy(blocks[i].block_num_idx, b->num, 12);
-    blocks[i].num_grid_pts = b->npts;
+    int bi = -1;
+    for (size_t k = 0; k < gids.size(); k++) if (gids[k].first == blocks[i].gid) bi = gids[k].second;
+    if (bi < 0 || bi >= (int)G.boxes.size()) return fail(TESSB200_EINVAL, "block gid %d is not part of the layout", blocks[i].gid);
+    const BlockBox &bx = G.boxes[bi];
+    memcpy(blocks[i].block_min_idx, bx.b_lo, 12); memcpy(blocks[i].block_num_idx, bx.b_num, 12);
+    blocks[i].num_grid_pts = (p->project ? (int64_t)bx.b_num[1] : (int64_t)bx.b_num[1] * bx.b_num[2]) * bx.b_num[0];
   }
   return 0;
 }
@@ -737,46 +904,33 @@ extern "C" int tessb200_dense_download(tessb200_ctx *c, int nblocks, tessb200_bl
     BlockRes *b = nullptr;
     for (BlockRes *x : c->blocks) if (x->gid == blocks[i].gid) b = x;
     if (!b) return fail(TESSB200_EINVAL, "block gid %d was not uploaded", blocks[i].gid);
-    memcpy(blocks[i].block_min_idx, b->mn, 12); memcpy(blocks[i].block_num_idx, b->num, 12);
-    blocks[i].num_grid_pts = b->npts;
-    if (blocks[i].density) {
-      if (blocks[i].density_capacity < b->npts)
-        return fail(TESSB200_ECAPACITY, "block gid %d: density_capacity %lld < %lld grid points", b->gid, (long long)blocks[i].density_capacity, b->npts);
-      CU(cudaMemcpyAsync(blocks[i].density, c->out.as<float>() + b->out_off, sizeof(float) * (size_t)b->npts, cudaMemcpyDeviceToHost, c->stream));
-    }
+    TRY(copy_block_out(c, p, b, &blocks[i], nullptr, c->stream));
   }
-  if (global_grid) {
-    if (p.project) return fail(TESSB200_EINVAL, "global_grid is only assembled for 3-D runs; use tessb200_write_grid for projections");
-    const size_t gx = p.glo_num_idx[0], gy = p.glo_num_idx[1];
-    for (BlockRes *b : c->blocks) {
-      if (!b->npts) continue;
-      cudaMemcpy3DParms cp;
-      memset(&cp, 0, sizeof(cp));
-      cp.srcPtr = make_cudaPitchedPtr(c->out.as<float>() + b->out_off, sizeof(float) * (size_t)b->num[0], (size_t)b->num[0], (size_t)b->num[1]);
-      cp.dstPtr = make_cudaPitchedPtr(global_grid, sizeof(float) * gx, gx, gy);
-      cp.dstPos = make_cudaPos(sizeof(float) * (size_t)b->mn[0], (size_t)b->mn[1], (size_t)b->mn[2]);
-      cp.extent = make_cudaExtent(sizeof(float) * (size_t)b->num[0], (size_t)b->num[1], (size_t)b->num[2]);
-      cp.kind = cudaMemcpyDeviceToHost;
-      CU(cudaMemcpy3DAsync(&cp, c->stream));
-    }
-  }
+  if (global_grid)
+    for (BlockRes *b : c->blocks) TRY(copy_block_out(c, p, b, nullptr, global_grid, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
+// One call, host buffers in and out.  The block copies, the cell kernels and the result copies are
+// pipelined (see run_impl); with pageable host memory the copies serialise but the result is the same.
 extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nblocks, tessb200_block *blocks, float *global_grid,
                               tessb200_dense_stats *st)
 {
-  TRY(tessb200_dense_upload(c, nblocks, blocks));
-  TRY(tessb200_dense_run(c, p, st));
-  CU(cudaEventRecord(c->ev[0], c->stream));
-  TRY(tessb200_dense_download(c, nblocks, blocks, global_grid));
-  if (st) {
-    CU(cudaEventRecord(c->ev[1], c->stream));
-    CU(cudaEventSynchronize(c->ev[1]));
-    cudaEventElapsedTime(&st->ms_download, c->ev[0], c->ev[1]);
-  }
-  return 0;
+  if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
+  int rc = upload_impl(c, nblocks, blocks, true);
+  if (rc) { cudaStreamSynchronize(c->copy_stream); return rc; }
+  PipeIO io;
+  io.pipelined = true;
+  io.h2d_done = &c->h2d_ev;
+  io.nblocks_out = nblocks;
+  io.out_blocks = blocks;
+  io.global_grid = global_grid;
+  rc = run_impl(c, p, st, io);
+  // the inputs are borrowed only for the duration of the call: never return with copies in flight
+  cudaStreamSynchronize(c->copy_stream);
+  cudaStreamSynchronize(c->stream);
+  return rc;
 }
 
 // ---- per-tet / per-site entry points ----------------------------------------------------------------

@@ -303,12 +303,13 @@ __global__ void k_morton_keys(const float *__restrict__ particles, int n, float3
 }
 
 // K3a part 1a: star BFS + cell bbox + filter + header + face list, one thread per cell, every block
-// of this GPU in one launch (CTAs [cta_start_b, cta_start_{b+1}) work on block b)
-__global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__restrict__ blocks, int nblocks, const __grid_constant__ GridGeom g, TopoOut out)
+// of a group (all blocks of this GPU when the inputs are resident; one block at a time when the run is
+// pipelined against the host-to-device copies) in one launch: CTAs [cta_start_b, cta_start_{b+1}) work on block b
+__global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__restrict__ blocks, int blk_begin, int blk_end, const __grid_constant__ GridGeom g, TopoOut out)
 {
   extern __shared__ int ws_s[];
-  int blk_id = 0;
-  for (int b = 1; b < nblocks; b++)
+  int blk_id = blk_begin;
+  for (int b = blk_begin + 1; b < blk_end; b++)
     if (blocks[b].num_orig > 0 && blocks[b].tets != nullptr && blockIdx.x >= blocks[b].cta_start) blk_id = b;
   const DevBlock blk = blocks[blk_id];
   const int slot = (int)(blockIdx.x - blk.cta_start) * TOPO_THREADS + (int)threadIdx.x;
@@ -395,12 +396,11 @@ __global__ void __launch_bounds__(128) k_cell_bfs_big(const DevBlock *__restrict
 // K3a part 1b: one thread per Voronoi face: walk the tets around the Delaunay edge in the
 // reference's order, Newell normal, orientation, plane = (normal, first vertex) -> plane pool.
 // Tiny per-thread state and no shared memory: full occupancy hides the dependent gathers.
-__global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ faces, const Counters *cnt_in, const DevBlock *__restrict__ blocks,
+__global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ faces, size_t f_begin, size_t f_end, const DevBlock *__restrict__ blocks,
                                                      float *__restrict__ plane_pool, Counters *cnt)
 {
-  const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nfaces = (size_t)cnt_in->plane_cursor * 2;
-  if (f >= nfaces) return;
+  const size_t f = f_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= f_end) return;
   const FaceRef r = faces[f];
   if (r.u < 0) return;
   const DevBlock &b = blocks[r.blk];
@@ -607,7 +607,7 @@ __device__ __forceinline__ T warp_incl_scan(T v)
   return v;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__restrict__ hdrs, const Counters *cnt_in, uint32_t cap_small,
+__global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__restrict__ hdrs, uint32_t n_hdrs,
                                                              const float *__restrict__ plane_pool, const DevBlock *__restrict__ blocks,
                                                              ScanCtx sc, const __grid_constant__ GridGeom g, SpanOut out)
 {
@@ -619,7 +619,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
   uint32_t *lines_w = bits_w + SCAN_BIT_WORDS + 4;     // [SCAN_LINE_CAP][32 lanes]
   uint64_t *bar = reinterpret_cast<uint64_t *>(lines_w + SCAN_LINE_CAP * 32);
 
-  const uint32_t n_hdrs = cnt_in->n_small < cap_small ? cnt_in->n_small : cap_small;
   const uint32_t first = (blockIdx.x * SCAN_WARPS + warp) * 32u;
   if (first >= n_hdrs) return;                       // whole warp leaves together
   const int ncell = (int)(n_hdrs - first < 32u ? n_hdrs - first : 32u);
@@ -789,7 +788,7 @@ struct GlobalPlanesInsideBits
 };
 
 __global__ void __launch_bounds__(128) k_cell_scan_big(const CellHdr *__restrict__ hdrs, const unsigned long long *__restrict__ bit_off,
-                                                        int n_cells, const float *__restrict__ plane_pool, uint32_t *bits_g,
+                                                        int n_cells, const float *__restrict__ plane_pool, uint32_t *bits_g, unsigned long long bit_base,
                                                         const DevBlock *__restrict__ blocks, ScanCtx sc,
                                                         const __grid_constant__ GridGeom g, SpanOut out)
 {
@@ -798,7 +797,7 @@ __global__ void __launch_bounds__(128) k_cell_scan_big(const CellHdr *__restrict
   CellHdr h = hdrs[ci];
   int nf = (int)(h.blk_nf & 0xffffu);
   const float *pl = plane_pool + (size_t)h.plane_off * 12;
-  uint32_t *bits = bits_g + (bit_off[ci] >> 5);
+  uint32_t *bits = bits_g + ((bit_off[ci] - bit_base) >> 5);
   int nx = h.n3[0], ny = h.n3[1], nz = h.n3[2];
   long long total = (long long)nx * ny * nz;
   long long total32 = (total + 31) & ~31LL;
@@ -908,13 +907,15 @@ struct RowBlock
 constexpr int ROWS_WARPS = 4;
 
 __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__restrict__ data, const unsigned long long *__restrict__ row_start,
-                                                          unsigned long long row0, unsigned long long nrows, const RowBlock *__restrict__ rblocks,
+                                                          unsigned long long row0, unsigned long long r_begin, unsigned long long nrows, const RowBlock *__restrict__ rblocks,
                                                           int n_rblocks, float div, int nx_max, float *__restrict__ out)
 {
+  // rows [r_begin, r_begin + nrows) of this GPU's row range (row ids row0 + r)
   extern __shared__ float rowbuf_all[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long r = (unsigned long long)blockIdx.x * ROWS_WARPS + warp;
   if (r >= nrows) return;
+  r += r_begin;
   float *buf = rowbuf_all + (size_t)warp * nx_max;
   long long row = (long long)(row0 + r);
   // owning block: last rblock with row_base <= row

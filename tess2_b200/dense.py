@@ -176,11 +176,31 @@ class Context:
 
     # ---- one-call interface == the reference's dense() ---------------------------------------
     def dense(self, alg_type, num_given_bounds, given_mins, given_maxs, project, proj_plane, mass, eps, glo_num_idx,
-              blocks, want_grid=True):
+              blocks, want_grid=True, out_blocks=None, want_stats=True):
+        """tessb200_dense(): host buffers in, host buffers out, copies pipelined with the kernels."""
         params = self.make_params(alg_type, num_given_bounds, given_mins, given_maxs, project, proj_plane, mass, eps, glo_num_idx)
-        self.upload(blocks)
-        st = self.run(params)
-        res = self.download(params, want_grid=want_grid)
+        return self.dense_params(params, blocks, want_grid=want_grid, out_blocks=out_blocks, want_stats=want_stats)
+
+    def dense_params(self, params, blocks, want_grid=True, out_blocks=None, want_stats=True):
+        arr, keep = self._marshal(blocks, False, None, False)
+        self._arr, self._keep, self._nb, self._blocks = arr, keep, len(blocks), blocks
+        geo = self.geometry(params)                 # host-only: BlockGridParams of every block
+        dens = []
+        for i, (mn, num, npts) in enumerate(geo):
+            d = out_blocks[i] if out_blocks is not None else np.empty(npts, dtype=np.float32)
+            dens.append(d)
+            arr[i].density = _fp(d)
+            arr[i].density_capacity = d.size
+        grid = None
+        if want_grid and not params.project:
+            gs = [params.glo_num_idx[d] for d in range(3)]
+            grid = np.zeros((gs[2], gs[1], gs[0]), dtype=np.float32)
+        st = _l.DenseStats()
+        _l.check(self.lib.tessb200_dense(self.handle, C.byref(params), len(blocks), arr, _fp(grid) if grid is not None else None,
+                                         C.byref(st) if want_stats else None))
+        res = DenseResult()
+        res.project = bool(params.project)
+        self._fill_result(res, params, geo, dens, grid)
         res.stats = st
         return res
 

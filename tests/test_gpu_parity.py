@@ -177,6 +177,23 @@ def test_edge_cases(ctx):
         ctx.dense(0, 0, None, None, True, (1.0, 0.0, 0.0), 1.0, 1e-4, (32, 32, 32), blocks)
 
 
+def test_three_step_interface_equals_one_call(ctx, port):
+    # upload -> run -> download (inputs resident, one group of all blocks) vs tessb200_dense()
+    # (per-block groups pipelined against the copies): same bytes, and both equal the oracle
+    blocks = dataset("clump8")
+    for alg in (0, 1):
+        params = ctx.make_params(alg, 0, None, None, False, (0.0, 0.0, 1.0), 1.0, 1e-4, (48, 48, 48))
+        ctx.upload(blocks)
+        st = ctx.run(params)
+        res3 = ctx.download(params)
+        res1 = run_gpu(ctx, blocks, (48, 48, 48), alg=alg)
+        assert_same_bits(res3.grid, res1.grid, "three-step vs one-call")
+        for d3, d1 in zip(res3.block_density, res1.block_density):
+            assert_same_bits(d3, d1, "three-step vs one-call block")
+        assert st.num_deposit_cells == res1.stats.num_deposit_cells and st.num_spans == res1.stats.num_spans
+        compare_dense(res3, port.dense(blocks, (48, 48, 48), alg=alg), f"three-step alg{alg}")
+
+
 def test_repeatability(ctx):
     # two runs on the same inputs give the same bytes (no atomics on values, ordered accumulation)
     blocks = dataset("clump8")
