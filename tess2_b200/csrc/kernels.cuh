@@ -503,20 +503,21 @@ __device__ __forceinline__ void emit_cic(const ScanCtx &sc, int e, uint32_t cell
 }
 
 // ---- K3a part 2: inside bits + scan-line walk -----------------------------------------------------
-// Every warp is autonomous (no CTA barrier): it takes 32 consecutive cell headers, one per lane, and
-// works through them in sub-batches whose planes (TMA bulk copies into the warp's shared-memory
-// slice, completion on the warp's own mbarrier) and inside-bits fit the slice:
-//   phase 2  warp per cell: the lanes test 32 points of the cell's index box per step against the
-//            cell's planes (shared-memory broadcast reads, face loop trip count warp-uniform);
-//            one ballot = one word of inside-bits
-//   phase 3  lane per cell: the reference's scan-line state machine on the bits (pass 1 counts,
-//            pass 2 emits span records at a warp-aggregated offset)
-constexpr int SCAN_WARPS = 4;
+// Every warp is autonomous (no CTA barrier): it takes 32 consecutive cell headers, one per lane.
+//   phase 2  warp per cell, cell after cell: the lanes test 32 points of the cell's index box per step
+//            against the cell's planes.  The planes of cell c+1 are in flight (TMA 1-D bulk copy
+//            into the other slot of a two-slot ring in the warp's shared-memory slice, completion on
+//            that slot's mbarrier) while cell c is tested; reads are shared-memory broadcasts and the
+//            face loop trip count is warp-uniform.  One ballot = one word of inside-bits.
+//   phase 3  lane per cell: the reference's scan-line state machine on the bits; the non-empty lines
+//            are kept so the walk runs once; span records go out at a warp-aggregated offset.
+// A batch whose inside-bits exceed the slice is processed in sub-batches.
+constexpr int SCAN_WARPS = 8;
 constexpr int SCAN_THREADS = SCAN_WARPS * 32;
-constexpr int SCAN_PLANE_FLOATS = 2048;               // 8 KB of planes per warp (341 faces)
-constexpr int SCAN_BIT_WORDS = 256;                   // 8192 inside bits per warp (+ 1 pad word for the funnel shift)
+constexpr int SCAN_SLOT_FLOATS = SCAN_FACE_CAP * 6;   // one cell's planes: 32 faces * 24 B = 768 B
+constexpr int SCAN_BIT_WORDS = 256;                   // 8192 inside bits per warp (+ pad words for the funnel shift)
 constexpr int SCAN_LINE_CAP = 24;                     // non-empty scan lines per cell kept from pass 1 (else the walk is redone)
-constexpr int SCAN_WARP_BYTES = SCAN_PLANE_FLOATS * 4 + (SCAN_BIT_WORDS + 4) * 4 + SCAN_LINE_CAP * 32 * 4 + 16;
+constexpr int SCAN_WARP_BYTES = 2 * SCAN_SLOT_FLOATS * 4 + (SCAN_BIT_WORDS + 4) * 4 + SCAN_LINE_CAP * 32 * 4 + 16;
 constexpr size_t SCAN_SMEM = (size_t)SCAN_WARPS * SCAN_WARP_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -614,17 +615,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *mine = smem_raw + (size_t)warp * SCAN_WARP_BYTES;
-  float *planes_w = reinterpret_cast<float *>(mine);
-  uint32_t *bits_w = reinterpret_cast<uint32_t *>(planes_w + SCAN_PLANE_FLOATS);
-  uint32_t *lines_w = bits_w + SCAN_BIT_WORDS + 4;     // [SCAN_LINE_CAP][32 lanes]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(lines_w + SCAN_LINE_CAP * 32);
+  float *planes_w = reinterpret_cast<float *>(mine);                       // [2][SCAN_SLOT_FLOATS]
+  uint32_t *bits_w = reinterpret_cast<uint32_t *>(planes_w + 2 * SCAN_SLOT_FLOATS);
+  uint32_t *lines_w = bits_w + SCAN_BIT_WORDS + 4;                          // [SCAN_LINE_CAP][32 lanes]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(lines_w + SCAN_LINE_CAP * 32); // [2]
 
   const uint32_t first = (blockIdx.x * SCAN_WARPS + warp) * 32u;
   if (first >= n_hdrs) return;                       // whole warp leaves together
   const int ncell = (int)(n_hdrs - first < 32u ? n_hdrs - first : 32u);
 
   if (lane == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
@@ -636,39 +638,45 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
   const int nf = (int)(h.blk_nf & 0xffffu);
   const int e = (int)(h.blk_nf >> 16);
   const int npts = lane < ncell ? (int)h.n3[0] * (int)h.n3[1] * (int)h.n3[2] : 0;
-  const int pairs = lane < ncell ? (nf + 1) >> 1 : 0;                 // 48-byte units of planes
+  const uint32_t my_bytes = lane < ncell ? (uint32_t)((nf + 1) >> 1) * 48u : 0u;   // planes come in 48-byte units
   const int pts32 = (npts + 31) & ~31;
 
-  uint32_t parity = 0;
+  // the plane ring: cell c uses slot c & 1; its copy is issued by lane c (which holds the header)
+  uint32_t phase_bits = 0;                           // bit s = parity to wait for on slot s
+  if (lane == 0 && my_bytes) { mbar_arrive_expect_tx(&bar[0], my_bytes); bulk_g2s(planes_w, plane_pool + (size_t)h.plane_off * 12, my_bytes, &bar[0]); }
+
   int c0 = 0;
   while (c0 < ncell) {
-    // sub-batch [c0, c1): the longest run whose planes and bits fit the warp's slice
-    int incl_f = warp_incl_scan(lane >= c0 ? pairs : 0);
-    int incl_p = warp_incl_scan(lane >= c0 ? pts32 : 0);
-    bool fits = lane >= c0 && lane < ncell && incl_f * 12 <= SCAN_PLANE_FLOATS && incl_p <= SCAN_BIT_WORDS * 32;
-    unsigned fm = __ballot_sync(0xffffffffu, fits);
-    // (fm >> c0) is a run of ones starting at bit 0 (the prefix sums are monotone): c1 = c0 + its length
-    const unsigned run = fm >> c0;
+    // sub-batch [c0, c1): the longest run whose inside-bits fit the warp's slice
+    const int incl_p = warp_incl_scan(lane >= c0 ? pts32 : 0);
+    const bool fits = lane >= c0 && lane < ncell && incl_p <= SCAN_BIT_WORDS * 32;
+    const unsigned fm = __ballot_sync(0xffffffffu, fits);
+    const unsigned run = fm >> c0;                   // a run of ones from bit 0 (prefix sums are monotone)
     int c1 = c0 + (run == 0xffffffffu ? 32 : __ffs(~run) - 1);
     if (c1 > ncell) c1 = ncell;
     const bool in_sub = lane >= c0 && lane < c1;
-    const int f_off = incl_f - pairs;                                  // pairs before this cell in the slice
-    const int p_off = incl_p - pts32;                                  // bits before this cell in the slice
-    const uint32_t total_bytes = (uint32_t)__shfl_sync(0xffffffffu, incl_f, c1 - 1) * 48u;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of the slice vs. the new bulk writes
-    if (lane == 0) mbar_arrive_expect_tx(bar, total_bytes);
-    __syncwarp();
-    if (in_sub && pairs) bulk_g2s(planes_w + (size_t)f_off * 12, plane_pool + (size_t)h.plane_off * 12, (uint32_t)pairs * 48u, bar);
-    mbar_wait(bar, parity);
-    parity ^= 1u;
+    const int p_off = incl_p - pts32;                // bits before this cell in the slice
 
     // phase 2: warp per cell
     for (int c = c0; c < c1; c++) {
+      const int slot = c & 1;
+      // prefetch the planes of cell c+1 into the other slot (its previous user, cell c-1, is done)
+      if (c + 1 < ncell) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic reads of that slot vs. the bulk write
+        if (lane == c + 1 && my_bytes) {
+          mbar_arrive_expect_tx(&bar[slot ^ 1], my_bytes);
+          bulk_g2s(planes_w + (slot ^ 1) * SCAN_SLOT_FLOATS, plane_pool + (size_t)h.plane_off * 12, my_bytes, &bar[slot ^ 1]);
+        }
+      }
       const int nx = __shfl_sync(0xffffffffu, (int)h.n3[0], c), ny = __shfl_sync(0xffffffffu, (int)h.n3[1], c);
       const int np = __shfl_sync(0xffffffffu, npts, c), cnf = __shfl_sync(0xffffffffu, nf, c);
       const int lx = __shfl_sync(0xffffffffu, h.lo[0], c), ly = __shfl_sync(0xffffffffu, h.lo[1], c), lz = __shfl_sync(0xffffffffu, h.lo[2], c);
-      const float *pl = planes_w + (size_t)__shfl_sync(0xffffffffu, f_off, c) * 12;
+      const float *pl = planes_w + slot * SCAN_SLOT_FLOATS;
       const int wbase = __shfl_sync(0xffffffffu, p_off, c) >> 5;
+      if (cnf) {
+        mbar_wait(&bar[slot], (phase_bits >> slot) & 1u);
+        phase_bits ^= 1u << slot;
+      }
       // probe position: cell_min_grid_pos + i * step with cell_min_grid_pos = idx2phys(lo)  (src/dense.cpp:1404,1530-1532)
       const float bx = idx2phys1(lx, g.step[0], g.gmin[0]), by = idx2phys1(ly, g.step[1], g.gmin[1]), bz = idx2phys1(lz, g.step[2], g.gmin[2]);
       const float inv_nx = 1.0f / (float)nx, inv_ny = 1.0f / (float)ny;
@@ -695,8 +703,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
         const unsigned w = __ballot_sync(0xffffffffu, valid && !(dmax > g.eps && dmin < neg_eps));
         if (lane == 0) bits_w[wbase + (l0 >> 5)] = w;
       }
+      __syncwarp();
     }
-    __syncwarp();
 
     // phase 3: lane per cell.  Index boxes at most 32 wide (all but exotic cells) take the
     // bit-parallel walk and keep their non-empty lines, so the walk runs once.
