@@ -156,7 +156,7 @@ struct tessb200_ctx
 #ifdef TESSB200_WITH_NCCL
   ncclComm_t comm = nullptr;
 #endif
-  Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
+  Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, pre_hdr, cand, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
   Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2], x_small;
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
@@ -196,7 +196,8 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
   CU(cudaFuncSetAttribute(k_cell_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
   CU(cudaFuncSetAttribute(k_cell_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
-  CU(cudaFuncSetAttribute(k_cell_volumes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_volumes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOL_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_nbrs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NBRS_SMEM));
   *out = c;
   return 0;
 }
@@ -216,7 +217,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_blocks(c);
-  Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
+  Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->pre_hdr, &c->cand, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
                  &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small};
   for (Buf *b : bufs) b->release();
@@ -671,8 +672,13 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     if (timed) CU(cudaEventRecord(c->ev[4], s));
     // K3a part 1: BFS (+ general BFS for overflowing stars) and faces
     if (gctas) {
-      k_cell_bfs<<<gctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to);
-      COUNT_LAUNCH(c, 1);
+      const size_t n_slots = (size_t)gctas * TOPO_THREADS;
+      TRY(c->pre_hdr.ensure(sizeof(CellHdr) * n_slots));
+      TRY(c->cand.ensure(sizeof(int2) * n_slots * TOPO_CAND_CAP));
+      k_cell_bfs<<<gctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to,
+                                                        c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
+      k_cell_nbrs<<<gctas, TOPO_THREADS, NBRS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), to, c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
+      COUNT_LAUNCH(c, 2);
     }
     CU(cudaGetLastError());
     TRY(read_counters(c));
@@ -1007,7 +1013,7 @@ extern "C" int tessb200_cell_volumes(tessb200_ctx *c, int num_sites, int num_par
         (rc = d_ovf.ensure(4 * (size_t)cap)) || (rc = d_n.ensure(4))) { cleanup(); return rc; }
     cudaMemsetAsync(d_n.p, 0, 4, c->stream);
     DevBlock db = dev_block(&t.b);
-    k_cell_volumes<<<cdiv(num_sites, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, c->stream>>>(db, num_sites, mass, d_comp.as<int>(), d_vol.as<float>(), d_den.as<float>(),
+    k_cell_volumes<<<cdiv(num_sites, TOPO_THREADS), TOPO_THREADS, VOL_SMEM, c->stream>>>(db, num_sites, mass, d_comp.as<int>(), d_vol.as<float>(), d_den.as<float>(),
                                                                                   d_ovf.as<uint32_t>(), d_n.as<unsigned int>(), cap);
     unsigned int n_ovf = 0;
     cudaMemcpyAsync(&n_ovf, d_n.p, 4, cudaMemcpyDeviceToHost, c->stream);

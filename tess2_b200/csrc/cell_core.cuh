@@ -396,6 +396,161 @@ TB_HD int star_bfs_uniform(int site, int t0, const int4 *tets, const float4 *cc,
   return CELL_OK;
 }
 
+// The star walk split in two (k_cell_bfs + k_cell_nbrs): the BFS keeps only the visited set and hands
+// every CANDIDATE new neighbour to `sink(k, u, t)` in BFS order -- the root's three vertices, then per
+// popped tet the vertex opposite its parent face (the only one that can be new, see above).  A second
+// pass (nbrs_from_cands) drops the candidates that were seen before; what remains is neighbor_edges'
+// list of (u, first tet holding u).  ws needs star(), parent_idx(), vis_hash(), hash_clear_vis().
+// Bucketized byte tables: a bucket is one 32-bit word holding four list indices (0xFF = empty, filled
+// from byte 0 up; nothing is ever deleted).  One shared-memory load fetches the bucket, the up to
+// four list entries it names are compared without data-dependent branching, and a full bucket
+// spills to the next one.  Compared with one-byte open addressing this keeps the lanes of a warp on
+// the same path (profiles/r01_i: the probe-continuation code ran at 3.6 of 32 lanes).
+//   vis table: VIS_BUCKETS buckets over star();  nbr table: NBR_BUCKETS buckets over nu().
+#define TB_VIS_BUCKETS 16
+#define TB_NBR_BUCKETS 16
+
+template <class WS>
+TB_HD int vis_find_or_insert(WS &ws, int key, int *count, int cap)
+{
+  unsigned h = ((unsigned)key * 0x9E3779B1u) >> 28;      // 16 buckets
+  for (int guard = 0; guard < TB_VIS_BUCKETS; guard++) {
+    const uint32_t w = ws.vis_word(h);
+    const unsigned i0 = w & 0xFFu, i1 = (w >> 8) & 0xFFu, i2 = (w >> 16) & 0xFFu, i3 = w >> 24;
+    // entries are filled from byte 0 up, so an empty byte ends the bucket
+    const bool hit = (i0 != 0xFFu && ws.star((int)i0) == key) || (i1 != 0xFFu && ws.star((int)i1) == key) ||
+                     (i2 != 0xFFu && ws.star((int)i2) == key) || (i3 != 0xFFu && ws.star((int)i3) == key);
+    if (hit) return 0;
+    if (i3 == 0xFFu) {
+      if (*count >= cap) return -1;
+      const int b = i0 == 0xFFu ? 0 : (i1 == 0xFFu ? 1 : (i2 == 0xFFu ? 2 : 3));
+      ws.vis_word(h) = (w & ~(0xFFu << (8 * b))) | ((uint32_t)*count << (8 * b));
+      ws.star(*count) = key;
+      (*count)++;
+      return 1;
+    }
+    h = (h + 1u) & (TB_VIS_BUCKETS - 1u);
+  }
+  return -1;
+}
+
+template <class WS, class Sink>
+TB_HD int star_bfs_cands(int site, int t0, const int4 *tets, const float4 *cc, WS &ws, int star_cap, int *n_star, float *cmin,
+                         float *cmax, Sink &sink)
+{
+  ws.hash_clear_vis();
+  int ns = 0, ncand = 0;
+  vis_find_or_insert(ws, t0, &ns, star_cap);
+  {
+    int4 v = tets[2 * (size_t)t0];
+    int4 nb = tets[2 * (size_t)t0 + 1];
+    float4 c = cc[t0];
+    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
+    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+    int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
+    if (is < 0) return CELL_OVERFLOW;
+    for (int q = 0; q < 3; q++) {
+      int s = q + (q >= is ? 1 : 0);
+      sink(ncand++, tb_sel4(v.x, v.y, v.z, v.w, s), t0);
+      int next = tb_sel4(nb.x, nb.y, nb.z, nb.w, s);
+      if (next < 0) return CELL_INCOMPLETE;
+      int before_s = ns;
+      int r2 = vis_find_or_insert(ws, next, &ns, star_cap);
+      if (r2 < 0) return CELL_OVERFLOW;
+      if (r2 > 0) ws.parent_idx(before_s) = 0;
+    }
+  }
+  int4 v_n = {0, 0, 0, 0}, nb_n = {0, 0, 0, 0};
+  float4 c_n = {0, 0, 0, 0};
+  bool have_n = false;
+  if (ns > 1) {
+    int t1 = ws.star(1);
+    v_n = tets[2 * (size_t)t1]; nb_n = tets[2 * (size_t)t1 + 1]; c_n = cc[t1];
+    have_n = true;
+  }
+  for (int head = 1; head < ns; head++) {
+    const int t = ws.star(head);
+    int4 v, nb;
+    float4 c;
+    if (have_n) { v = v_n; nb = nb_n; c = c_n; }
+    else { v = tets[2 * (size_t)t]; nb = tets[2 * (size_t)t + 1]; c = cc[t]; }
+    have_n = head + 1 < ns;
+    if (have_n) {
+      int t1 = ws.star(head + 1);
+      v_n = tets[2 * (size_t)t1]; nb_n = tets[2 * (size_t)t1 + 1]; c_n = cc[t1];
+    }
+    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
+    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+    const int par = ws.star((int)ws.parent_idx(head));
+    const int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
+    const int ip = nb.x == par ? 0 : (nb.y == par ? 1 : (nb.z == par ? 2 : (nb.w == par ? 3 : -1)));
+    if (is < 0 || ip < 0 || is == ip) return CELL_OVERFLOW;
+    sink(ncand++, tb_sel4(v.x, v.y, v.z, v.w, ip), t);
+    unsigned m = 0xFu & ~(1u << is) & ~(1u << ip);
+    const int s1 = tb_ffs(m) - 1;
+    m &= m - 1u;
+    const int s2 = tb_ffs(m) - 1;
+    const int n1 = tb_sel4(nb.x, nb.y, nb.z, nb.w, s1), n2 = tb_sel4(nb.x, nb.y, nb.z, nb.w, s2);
+    if (n1 < 0 || n2 < 0) return CELL_INCOMPLETE;
+    int before_s = ns;
+    int r = vis_find_or_insert(ws, n1, &ns, star_cap);
+    if (r < 0) return CELL_OVERFLOW;
+    if (r > 0) ws.parent_idx(before_s) = (unsigned char)head;
+    before_s = ns;
+    r = vis_find_or_insert(ws, n2, &ns, star_cap);
+    if (r < 0) return CELL_OVERFLOW;
+    if (r > 0) ws.parent_idx(before_s) = (unsigned char)head;
+  }
+  *n_star = ns;
+  return CELL_OK;
+}
+
+// second pass: candidates (u, t) in BFS order -> distinct neighbours with their first tet.
+// ws needs nu(), nt() (int&), nbr_word(), hash_clear_nbr().  Returns nn, or -1 on overflow.
+// Candidates are fetched four at a time (independent loads in flight) before they are consumed.
+template <class WS>
+TB_HD int nbr_insert(WS &ws, int u, int t, int *nn, int nbr_cap)
+{
+  unsigned h = ((unsigned)u * 0x9E3779B1u) >> 28;        // 16 buckets
+  for (int guard = 0; guard < TB_NBR_BUCKETS; guard++) {
+    const uint32_t w = ws.nbr_word(h);
+    const unsigned i0 = w & 0xFFu, i1 = (w >> 8) & 0xFFu, i2 = (w >> 16) & 0xFFu, i3 = w >> 24;
+    const bool hit = (i0 != 0xFFu && ws.nu((int)i0) == u) || (i1 != 0xFFu && ws.nu((int)i1) == u) ||
+                     (i2 != 0xFFu && ws.nu((int)i2) == u) || (i3 != 0xFFu && ws.nu((int)i3) == u);
+    if (hit) return 0;
+    if (i3 == 0xFFu) {
+      if (*nn >= nbr_cap) return -1;
+      const int b = i0 == 0xFFu ? 0 : (i1 == 0xFFu ? 1 : (i2 == 0xFFu ? 2 : 3));
+      ws.nbr_word(h) = (w & ~(0xFFu << (8 * b))) | ((uint32_t)*nn << (8 * b));
+      ws.nu(*nn) = u;
+      ws.nt(*nn) = t;
+      (*nn)++;
+      return 1;
+    }
+    h = (h + 1u) & (TB_NBR_BUCKETS - 1u);
+  }
+  return -1;
+}
+
+template <class WS, class Source>
+TB_HD int nbrs_from_cands(WS &ws, int n_cand, int nbr_cap, Source &src)
+{
+  ws.hash_clear_nbr();
+  int nn = 0;
+  for (int k = 0; k < n_cand; k += 4) {
+    int u[4], t[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      u[q] = -1; t[q] = 0;
+      if (k + q < n_cand) src(k + q, u[q], t[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (k + q < n_cand && nbr_insert(ws, u[q], t[q], &nn, nbr_cap) < 0) return -1;
+  }
+  return nn;
+}
+
 #define TB_MAX_LINK 4096
 
 // Walks the tets around Delaunay edge (site, u) starting at ut, in the reference's order

@@ -156,30 +156,40 @@ __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ 
 }
 
 // ---- K3a part 1: topology + faces, one thread per cell --------------------------------------------
-// Shared-memory workspace of the fast topology kernels: word w of a thread lives at
+// Shared-memory workspaces of the fast topology kernels: word w of a thread lives at
 // base[w * STRIDE] (stride = threads per CTA, so a warp touching the same word index hits 32
-// distinct banks).  Layout in words: star[52] | nu[36] | nt_idx bytes[9] | parent_idx bytes[13] |
-// vis_hash bytes[16] | nbr_hash bytes[16]  = 142 words = 568 B per thread (3 CTAs of 128 per SM).
+// distinct banks).
+//   StarWS (k_cell_bfs):  star[52] | parent_idx bytes[13 words] | vis buckets[16 words] = 81 words = 324 B
+//   NbrWS  (k_cell_nbrs): nu[36] | nt[36] | nbr buckets[16 words]                      = 88 words = 352 B
 template <int STRIDE>
-struct FastWS
+struct StarWS
 {
   int *base;
-  static constexpr int NU = 52, NTI = 88, PAR = 97, VH = 110, NH = 126, WORDS = 142;
+  static constexpr int PAR = 52, VH = 65, WORDS = 81;
   __device__ __forceinline__ int &star(int i) { return base[(size_t)i * STRIDE]; }
-  __device__ __forceinline__ int &nu(int i) { return base[(size_t)(NU + i) * STRIDE]; }
-  __device__ __forceinline__ unsigned char &byte(int word0, int i)
+  __device__ __forceinline__ unsigned char &parent_idx(int i)
   {
-    return reinterpret_cast<unsigned char *>(&base[(size_t)(word0 + (i >> 2)) * STRIDE])[i & 3];
+    return reinterpret_cast<unsigned char *>(&base[(size_t)(PAR + (i >> 2)) * STRIDE])[i & 3];
   }
-  __device__ __forceinline__ unsigned char &nt_idx(int i) { return byte(NTI, i); }
-  __device__ __forceinline__ unsigned char &parent_idx(int i) { return byte(PAR, i); }
-  __device__ __forceinline__ unsigned char &vis_hash(unsigned h) { return byte(VH, (int)h); }
-  __device__ __forceinline__ unsigned char &nbr_hash(unsigned h) { return byte(NH, (int)h); }
-  __device__ __forceinline__ int nt(int i) { return star((int)nt_idx(i)); }
-  __device__ __forceinline__ void hash_clear()
+  __device__ __forceinline__ uint32_t &vis_word(unsigned h) { return reinterpret_cast<uint32_t *>(base)[(size_t)(VH + (int)h) * STRIDE]; }
+  __device__ __forceinline__ void hash_clear_vis()
   {
 #pragma unroll
     for (int w = VH; w < WORDS; w++) base[(size_t)w * STRIDE] = -1;
+  }
+};
+template <int STRIDE>
+struct NbrWS
+{
+  int *base;
+  static constexpr int NT = 36, NH = 72, WORDS = 88;
+  __device__ __forceinline__ int &nu(int i) { return base[(size_t)i * STRIDE]; }
+  __device__ __forceinline__ int &nt(int i) { return base[(size_t)(NT + i) * STRIDE]; }
+  __device__ __forceinline__ uint32_t &nbr_word(unsigned h) { return reinterpret_cast<uint32_t *>(base)[(size_t)(NH + (int)h) * STRIDE]; }
+  __device__ __forceinline__ void hash_clear_nbr()
+  {
+#pragma unroll
+    for (int w = NH; w < WORDS; w++) base[(size_t)w * STRIDE] = -1;
   }
 };
 struct DynStridedWS
@@ -195,7 +205,9 @@ struct DynStridedWS
 constexpr int TOPO_THREADS = 128;
 constexpr int TOPO_STAR_CAP = 52;
 constexpr int TOPO_NBR_CAP = 36;
-constexpr size_t TOPO_SMEM = (size_t)FastWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
+constexpr size_t TOPO_SMEM = (size_t)StarWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
+constexpr size_t NBRS_SMEM = (size_t)NbrWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
+constexpr int TOPO_CAND_CAP = TOPO_STAR_CAP + 2;   // candidates per cell: 3 at the root + 1 per further star tet
 constexpr int BIG_STAR_CAP = 4096;
 constexpr int BIG_NBR_CAP = 1024;
 
@@ -302,31 +314,137 @@ __global__ void k_morton_keys(const float *__restrict__ particles, int n, float3
   ids[i] = (uint32_t)i;
 }
 
-// K3a part 1a: star BFS + cell bbox + filter + header + face list, one thread per cell, every block
+// K3a part 1a: star BFS + cell bbox + data-bounds filter + index box, one thread per cell, every block
 // of a group (all blocks of this GPU when the inputs are resident; one block at a time when the run is
-// pipelined against the host-to-device copies) in one launch: CTAs [cta_start_b, cta_start_{b+1}) work on block b
-__global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__restrict__ blocks, int blk_begin, int blk_end, const __grid_constant__ GridGeom g, TopoOut out)
+// pipelined against the host-to-device copies) in one launch: CTAs [cta_start_b, cta_start_{b+1}) work
+// on block b.  Hands a pre-header and the candidate neighbours (slot-interleaved, so the lanes of a
+// warp write and later read consecutive 8-byte entries) to k_cell_nbrs.
+struct CandSink
+{
+  int2 *cand;          // entry k of this thread at cand[k * n_slots]
+  size_t n_slots;
+  __device__ __forceinline__ void operator()(int k, int u, int t) { cand[(size_t)k * n_slots] = make_int2(u, t); }
+};
+struct CandSource
+{
+  const int2 *cand;
+  size_t n_slots;
+  __device__ __forceinline__ void operator()(int k, int &u, int &t) const
+  {
+    int2 e = cand[(size_t)k * n_slots];
+    u = e.x;
+    t = e.y;
+  }
+};
+
+__global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__restrict__ blocks, int blk_begin, int blk_end, const __grid_constant__ GridGeom g,
+                                                           TopoOut out, CellHdr *__restrict__ pre, int2 *__restrict__ cand)
 {
   extern __shared__ int ws_s[];
   int blk_id = blk_begin;
   for (int b = blk_begin + 1; b < blk_end; b++)
     if (blocks[b].num_orig > 0 && blocks[b].tets != nullptr && blockIdx.x >= blocks[b].cta_start) blk_id = b;
   const DevBlock blk = blocks[blk_id];
-  const int slot = (int)(blockIdx.x - blk.cta_start) * TOPO_THREADS + (int)threadIdx.x;
-  FastWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
-  int status = -1, n_star = 0, n_nbr = 0, cell = 0;
+  const int slot_in_blk = (int)(blockIdx.x - blk.cta_start) * TOPO_THREADS + (int)threadIdx.x;
+  const size_t slot = (size_t)blockIdx.x * TOPO_THREADS + threadIdx.x;
+  const size_t n_slots = (size_t)gridDim.x * TOPO_THREADS;
+  StarWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
+  int status = -1, n_star = 0, cell = 0;
   float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (slot < blk.num_orig && blk.tets != nullptr) {
-    cell = (int)blk.order[slot];
+  if (slot_in_blk < blk.num_orig && blk.tets != nullptr) {
+    cell = (int)blk.order[slot_in_blk];
     int t0 = blk.v2t[cell];
-    status = t0 < 0 ? CELL_NO_TET
-                    : star_bfs_uniform(cell, t0, blk.tets, blk.cc, ws, TOPO_STAR_CAP, TOPO_NBR_CAP, &n_star, &n_nbr, cmin, cmax);
+    CandSink sink{cand + slot, n_slots};
+    status = t0 < 0 ? CELL_NO_TET : star_bfs_cands(cell, t0, blk.tets, blk.cc, ws, TOPO_STAR_CAP, &n_star, cmin, cmax, sink);
   }
   __syncwarp();
-  bool ovf = status == CELL_OVERFLOW;
+  const bool ovf = status == CELL_OVERFLOW;
   uint32_t o_slot = warp_append<unsigned int>(&out.cnt->n_overflow, ovf);
   if (ovf && o_slot < out.cap_overflow) out.overflow[o_slot] = make_uint2((unsigned)blk_id, (unsigned)cell);
-  bfs_finish(ovf ? -1 : status, cell, n_nbr, ws, cmin, cmax, blk, blk_id, g, out);
+  int lo[3] = {0, 0, 0}, n3[3] = {0, 0, 0};
+  if (status == CELL_OK) {
+    // src/dense.cpp:1385-1392
+    for (int d = 0; d < 3; d++)
+      if (cmin[d] < fsub(g.dmin[d], g.dext_eps[d]) || cmax[d] > fadd(g.dmax[d], g.dext_eps[d])) status = CELL_OUTSIDE;
+  }
+  if (status == CELL_OK) {
+    for (int d = 0; d < 3; d++) {
+      lo[d] = phys2idx1(cmin[d], g.step[d], g.gmin[d]);
+      int hi = phys2idx1(cmax[d], g.step[d], g.gmin[d]);
+      n3[d] = hi - lo[d] + 1;
+    }
+    if (n3[0] < 1 || n3[1] < 1 || n3[2] < 1 || n3[0] > 32767 || n3[1] > 32767 || n3[2] > 32767 ||
+        lo[0] < -1 || lo[1] < -1 || lo[2] < -1)
+      status = CELL_BAD_MESH;
+  }
+  CellHdr h;
+  h.cell = blk.cell_base + (uint32_t)cell;
+  h.blk_nf = ((uint32_t)blk_id << 16) | (uint32_t)(n_star + 2);     // candidates, replaced by the face count in k_cell_nbrs
+  h.lo[0] = lo[0]; h.lo[1] = lo[1]; h.lo[2] = lo[2];
+  h.n3[0] = (uint16_t)n3[0]; h.n3[1] = (uint16_t)n3[1]; h.n3[2] = (uint16_t)n3[2];
+  h.pad = status == CELL_OK ? 0 : 0xFFFF;
+  h.plane_off = 0;
+  pre[slot] = h;
+  warp_count(&out.cnt->n_no_tet, status == CELL_NO_TET);
+  warp_count(&out.cnt->n_incomplete, status == CELL_INCOMPLETE);
+  warp_count(&out.cnt->n_outside, status == CELL_OUTSIDE);
+  warp_count(&out.cnt->n_bad, status == CELL_BAD_MESH);
+}
+
+// K3a part 1a': candidates -> distinct Delaunay neighbours with their first tet (neighbor_edges' list),
+// then the warp-aggregated append of the face list, the plane space and the header.  Same launch shape
+// as k_cell_bfs (thread <-> slot).
+__global__ void __launch_bounds__(TOPO_THREADS) k_cell_nbrs(const DevBlock *__restrict__ blocks, TopoOut out, const CellHdr *__restrict__ pre,
+                                                            const int2 *__restrict__ cand)
+{
+  extern __shared__ int ws_s[];
+  const size_t slot = (size_t)blockIdx.x * TOPO_THREADS + threadIdx.x;
+  const size_t n_slots = (size_t)gridDim.x * TOPO_THREADS;
+  NbrWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
+  CellHdr h = pre[slot];
+  const int blk_id = (int)(h.blk_nf >> 16);
+  bool ok = h.pad == 0;
+  int nn = 0;
+  if (ok) {
+    CandSource src{cand + slot, n_slots};
+    nn = nbrs_from_cands(ws, (int)(h.blk_nf & 0xffffu), TOPO_NBR_CAP, src);
+  }
+  __syncwarp();
+  const bool ovf = ok && nn < 0;
+  const uint32_t cell_local = ok ? h.cell - blocks[blk_id].cell_base : 0u;
+  uint32_t o_slot = warp_append<unsigned int>(&out.cnt->n_overflow, ovf);
+  if (ovf && o_slot < out.cap_overflow) out.overflow[o_slot] = make_uint2((unsigned)blk_id, cell_local);
+  ok = ok && nn >= 0;
+  // plane / face-list space in pairs of faces (48-byte units: every cell's planes start 16-byte aligned)
+  const uint32_t want = ok ? (uint32_t)((nn + 1) >> 1) : 0u;
+  const uint32_t poff = warp_alloc<unsigned int>(&out.cnt->plane_cursor, want);
+  if (ok) {
+    FaceRef *fr = out.faces + (size_t)poff * 2;
+    for (int k = 0; k < nn; k++) {
+      FaceRef r;
+      r.site = (int)cell_local; r.u = ws.nu(k); r.ut = ws.nt(k); r.blk = blk_id;
+      fr[k] = r;
+    }
+    if (nn & 1) {
+      FaceRef r;
+      r.site = (int)cell_local; r.u = -1; r.ut = 0; r.blk = blk_id;
+      fr[nn] = r;
+    }
+  }
+  const long long npts = (long long)h.n3[0] * h.n3[1] * h.n3[2];
+  const bool small = ok && nn <= SCAN_FACE_CAP && npts <= SCAN_PTS_CAP;
+  const bool big = ok && !small;
+  h.blk_nf = ((uint32_t)blk_id << 16) | (uint32_t)(ok ? nn : 0);
+  h.plane_off = poff;
+  uint32_t s_slot = warp_append<unsigned int>(&out.cnt->n_small, small);
+  if (small && s_slot < out.cap_small) out.small[s_slot] = h;
+  uint32_t b_slot = warp_append<unsigned int>(&out.cnt->n_big, big);
+  unsigned long long bits = big ? (unsigned long long)((npts + 31) & ~31LL) : 0ull;
+  unsigned long long boff = warp_alloc<unsigned long long>(&out.cnt->big_bits, bits);
+  if (big && b_slot < out.cap_big) {
+    out.big[b_slot] = h;
+    out.big_bit_off[b_slot] = boff;
+  }
 }
 
 // The general star walk for the (rare) cells whose star exceeds the shared-memory workspace or is
@@ -992,6 +1110,31 @@ __global__ void k_grid_stats(const float *__restrict__ v, unsigned long long n, 
   }
 }
 
+// workspace of k_cell_volumes (star + neighbours together: 142 words = 568 B per thread)
+template <int STRIDE>
+struct VolWS
+{
+  int *base;
+  static constexpr int NU = 52, NTI = 88, PAR = 97, VH = 110, NH = 126, WORDS = 142;
+  __device__ __forceinline__ int &star(int i) { return base[(size_t)i * STRIDE]; }
+  __device__ __forceinline__ int &nu(int i) { return base[(size_t)(NU + i) * STRIDE]; }
+  __device__ __forceinline__ unsigned char &byte(int word0, int i)
+  {
+    return reinterpret_cast<unsigned char *>(&base[(size_t)(word0 + (i >> 2)) * STRIDE])[i & 3];
+  }
+  __device__ __forceinline__ unsigned char &nt_idx(int i) { return byte(NTI, i); }
+  __device__ __forceinline__ unsigned char &parent_idx(int i) { return byte(PAR, i); }
+  __device__ __forceinline__ unsigned char &vis_hash(unsigned h) { return byte(VH, (int)h); }
+  __device__ __forceinline__ unsigned char &nbr_hash(unsigned h) { return byte(NH, (int)h); }
+  __device__ __forceinline__ int nt(int i) { return star((int)nt_idx(i)); }
+  __device__ __forceinline__ void hash_clear()
+  {
+#pragma unroll
+    for (int w = VH; w < WORDS; w++) base[(size_t)w * STRIDE] = -1;
+  }
+};
+constexpr size_t VOL_SMEM = (size_t)VolWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
+
 // ---- K2: per-site complete flag, Voronoi volume and zero-order density ------------------------------
 __global__ void __launch_bounds__(TOPO_THREADS) k_cell_volumes(DevBlock blk, int num_sites, float mass, int *__restrict__ complete_out,
                                                                float *__restrict__ volume_out, float *__restrict__ density_out,
@@ -999,7 +1142,7 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_volumes(DevBlock blk, int
 {
   extern __shared__ int ws_s[];
   int site = blockIdx.x * TOPO_THREADS + threadIdx.x;
-  FastWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
+  VolWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
   int status = -1, n_star = 0, n_nbr = 0;
   if (site < num_sites) {
     int t0 = blk.v2t[site];

@@ -64,6 +64,37 @@ struct HashWS
   void hash_clear() { memset(vh, 0xFF, 64); memset(nh, 0xFF, 64); }
 };
 
+// the split fast path of k_cell_bfs + k_cell_nbrs
+struct StarHostWS
+{
+  int s[52];
+  unsigned char par[52];
+  uint32_t vw[16];
+  int &star(int i) { return s[i]; }
+  unsigned char &parent_idx(int i) { return par[i]; }
+  uint32_t &vis_word(unsigned h) { return vw[h]; }
+  void hash_clear_vis() { memset(vw, 0xFF, sizeof(vw)); }
+};
+struct NbrHostWS
+{
+  int u[36], t[36];
+  uint32_t nw[16];
+  int &nu(int i) { return u[i]; }
+  int &nt(int i) { return t[i]; }
+  uint32_t &nbr_word(unsigned h) { return nw[h]; }
+  void hash_clear_nbr() { memset(nw, 0xFF, sizeof(nw)); }
+};
+struct CandVec
+{
+  std::vector<std::pair<int, int> > v;
+  void operator()(int k, int u, int t) { if ((int)v.size() <= k) v.resize(k + 1); v[k] = std::make_pair(u, t); }
+};
+struct CandRead
+{
+  const std::vector<std::pair<int, int> > *v;
+  void operator()(int k, int &u, int &t) const { u = (*v)[k].first; t = (*v)[k].second; }
+};
+
 struct Topo
 {
   HostWS big;
@@ -78,12 +109,30 @@ struct Topo
     int st;
     for (int d = 0; d < 3; d++) { cmin[d] = INFINITY; cmax[d] = -INFINITY; }
     if (cc) {
-      st = star_bfs_uniform(site, t0, tets, cc, fast, 52, 36, &ns, &nn, cmin, cmax);
+      // k_cell_bfs (star + candidates) followed by k_cell_nbrs (dedup), copied into `fast`
+      StarHostWS sw;
+      NbrHostWS nw;
+      CandVec cands;
+      st = star_bfs_cands(site, t0, tets, cc, sw, 52, &ns, cmin, cmax, cands);
+      if (st == CELL_OK) {
+        CandRead rd{&cands.v};
+        nn = nbrs_from_cands(nw, ns + 2, 36, rd);
+        if (nn < 0) st = CELL_OVERFLOW;
+        else {
+          for (int k = 0; k < ns; k++) fast.s[k] = sw.s[k];
+          for (int k = 0; k < nn; k++) {
+            fast.u[k] = nw.u[k];
+            int idx = -1;
+            for (int q = 0; q < ns; q++) if (sw.s[q] == nw.t[k]) idx = q;
+            fast.nti[k] = (unsigned char)idx;
+          }
+        }
+      }
       // the parent-trick BFS must agree with the plain hashed one
       HashWS chk;
       int ns2, nn2;
       int st2 = star_and_neighbors_hashed(site, t0, tets, chk, 52, 36, &ns2, &nn2);
-      if (st2 != st || (st == CELL_OK && (ns2 != ns || nn2 != nn))) { fprintf(stderr, "emul: BFS variants disagree\n"); abort(); }
+      if (st2 != st || (st == CELL_OK && (ns2 != ns || nn2 != nn))) { fprintf(stderr, "emul: BFS variants disagree: st %d/%d ns %d/%d nn %d/%d\n", st, st2, ns, ns2, nn, nn2); abort(); }
       if (st == CELL_OK)
         for (int k = 0; k < nn; k++)
           if (chk.nu(k) != fast.nu(k) || chk.nt(k) != fast.nt(k)) { fprintf(stderr, "emul: BFS variants disagree on faces\n"); abort(); }
