@@ -223,6 +223,8 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = world
     blocks, layout, owner, dmin, dmax, gsize = build_workload(n, rank)
+    from tess2_b200.harness import workloads as _wl
+    host_tess = dict(_wl.LAST_TESS)
     keep = []
     for b in blocks:                      # pinned host buffers: the e2e leg copies from these
         for k in ("particles", "tets", "vert_to_tet"):
@@ -247,7 +249,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    stage = {k: 0.0 for k in ("ms_circumcenters", "ms_cells", "ms_scan", "ms_exchange", "ms_sort", "ms_deposit", "ms_total_device")}
+    stage = {k: 0.0 for k in ("ms_circumcenters", "ms_cells", "ms_bfs", "ms_nbrs", "ms_faces", "ms_scan", "ms_exchange", "ms_sort", "ms_deposit",
+                              "ms_total_device")}
     launches = 0
     st = None
     for _ in range(args.steps):
@@ -302,14 +305,20 @@ def run_ours(args, rank, world, local_rank):
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
     P_orig = cells_local
+    F = int(st.num_faces)              # plane records (Voronoi faces of accepted cells, padded to pairs)
+    Cn = int(st.num_candidates)        # candidate neighbours = sum over accepted cells of (star tets + 2)
+    star = max(Cn - 2 * int(st.num_deposit_cells), 0)   # star tets visited by the BFS (~27 per cell)
     alg_bytes = {
-        "k_circumcenters": 32 * T_local + 12 * P_local,                 # 16 B verts + 16 B float4 out per tet, particles once
-        "k_cell_topo": 48 * T_local + 16 * P_orig + 24 * int(15.5 * P_orig) + 32 * P_orig,  # tet records + circumcenters once, site+v2t, planes + header out
-        "k_cell_scan": 24 * int(15.5 * P_orig) + 32 * P_orig + 16 * spans,                  # planes + headers in, span records out
+        "k_circumcenters": 32 * T_local + 12 * P_local,            # 16 B verts + 16 B float4 out per tet, particles once
+        "k_cell_bfs": 48 * T_local + 16 * P_orig + 8 * Cn + 32 * P_orig,   # each tet record + circumcenter once, site + v2t, candidates + pre-header out
+        "k_cell_nbrs": 8 * Cn + 32 * P_orig + 16 * F + 32 * P_orig,       # candidates + pre-header in, face list + header out
+        "k_cell_faces": 16 * F + 48 * T_local + 24 * F,                   # face refs in, tet records + circumcenters once, planes out
+        "k_cell_scan": 24 * F + 32 * P_orig + 16 * spans,                 # planes + headers in, span records out
         "sort (cub radix, 64-bit key + 64-bit payload)": 2 * 16 * spans,
-        "k_rows": 16 * spans + 4 * G_local,                             # span records in, every grid point written once
+        "k_rows": 16 * spans + 4 * G_local,                               # span records in, every grid point written once
     }
-    stage_ms = {"k_circumcenters": stage["ms_circumcenters"], "k_cell_topo": stage["ms_cells"], "k_cell_scan": stage["ms_scan"],
+    stage_ms = {"k_circumcenters": stage["ms_circumcenters"], "k_cell_bfs": stage["ms_bfs"], "k_cell_nbrs": stage["ms_nbrs"],
+                "k_cell_faces": stage["ms_faces"], "k_cell_scan": stage["ms_scan"],
                 "sort (cub radix, 64-bit key + 64-bit payload)": stage["ms_sort"], "k_rows": stage["ms_deposit"]}
     stage_ms["nccl span exchange"] = stage["ms_exchange"]
     alg_bytes["nccl span exchange"] = 0
@@ -320,12 +329,12 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom)
     ach = alg_bytes[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+    whole = 32 * T_local + 16 * P_local + 4 * G_local
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes": alg_bytes[dom], "kernel_ms": stage_ms[dom],
+                "note": "the cell kernels are latency / L2-sector / issue bound, not HBM bound: see DESIGN.md 3 and profiles/",
                 "stages": {k: {"ms": stage_ms[k], "algorithmic_GBps": (alg_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None)} for k in stage_ms},
-                "whole_stage": {"algorithmic_bytes": 32 * T_local + 16 * P_local + 4 * G_local,
-                                "achieved": (32 * T_local + 16 * P_local + 4 * G_local) / (dev_ms * 1e-3) / 1e9,
-                                "frac": (32 * T_local + 16 * P_local + 4 * G_local) / (dev_ms * 1e-3) / 1e9 / peak}}
+                "whole_stage": {"algorithmic_bytes": whole, "achieved": whole / (dev_ms * 1e-3) / 1e9, "frac": whole / (dev_ms * 1e-3) / 1e9 / peak}}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------------
     cpu = None
@@ -355,7 +364,10 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "stats": {"cells": cells_local, "tets": T_local, "particles_with_ghosts": P_local, "grid_points": G_local, "spans": spans,
+            "host_tess": {"engine": "SciPy Qhull 'Qt', one process per block", "seconds": host_tess.get("seconds"), "workers": host_tess.get("workers"),
+                          "from_cache": host_tess.get("cached"),
+                          "tess_plus_dense_seconds": (host_tess["seconds"] + e2e_ms * 1e-3) if host_tess.get("seconds") else None},
+            "stats": {"cells": cells_local, "tets": T_local, "particles_with_ghosts": P_local, "grid_points": G_local, "spans": spans, "faces": F, "candidates": Cn,
                       "deposit_cells": int(st.num_deposit_cells), "cic_fallback_cells": int(st.num_cic_fallback), "slow_cells": int(st.num_slow_cells),
                       "tot_mass": float(st.tot_mass)},
         }

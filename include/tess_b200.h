@@ -113,6 +113,9 @@ typedef struct tessb200_dense_stats
   float max_dense;            /* max over the final grid */
   float ms_upload, ms_circumcenters, ms_cells, ms_scan, ms_sort, ms_deposit, ms_exchange, ms_download;
   float ms_total_device;      /* inputs resident -> grid complete in device memory */
+  float ms_bfs, ms_nbrs, ms_faces; /* the three kernels inside ms_cells (resident runs only) */
+  int64_t num_faces;          /* Voronoi faces of the depositing cells (plane records) */
+  int64_t num_candidates;     /* candidate neighbours handed from k_cell_bfs to k_cell_nbrs */
 } tessb200_dense_stats;
 
 typedef struct tessb200_ctx tessb200_ctx;

@@ -161,7 +161,7 @@ struct tessb200_ctx
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
-  cudaEvent_t ev[12];
+  cudaEvent_t ev[16];
   bool ran = false;
   long long launches = 0;           // kernels launched by the current run
   tessb200_dense_params last_params;
@@ -677,7 +677,9 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       TRY(c->cand.ensure(sizeof(int2) * n_slots * TOPO_CAND_CAP));
       k_cell_bfs<<<gctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to,
                                                         c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
+      if (timed) CU(cudaEventRecord(c->ev[11], s));
       k_cell_nbrs<<<gctas, TOPO_THREADS, NBRS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), to, c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
+      if (timed) CU(cudaEventRecord(c->ev[12], s));
       COUNT_LAUNCH(c, 2);
     }
     CU(cudaGetLastError());
@@ -693,6 +695,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       done_ovf = c->h_cnt->n_overflow;
       TRY(read_counters(c));
     }
+    if (timed) CU(cudaEventRecord(c->ev[13], s));
     if (c->h_cnt->plane_cursor > done_pairs) {
       const size_t f0 = (size_t)done_pairs * 2, f1 = (size_t)c->h_cnt->plane_cursor * 2;
       k_cell_faces<<<cdiv((long long)(f1 - f0), 256), 256, 0, s>>>(c->face_list.as<FaceRef>(), f0, f1, c->d_blocks.as<DevBlock>(), c->plane_pool.as<float>(), cnt);
@@ -852,6 +855,12 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     st->ms_deposit = ms(8, 9);
     st->ms_total_device = ms(2, 9);
     st->ms_download = 0;
+    const bool sub = one && tess && cells > 0;
+    st->ms_bfs = sub ? ms(4, 11) : 0;
+    st->ms_nbrs = sub ? ms(11, 12) : 0;
+    st->ms_faces = sub ? ms(13, 5) : 0;
+    st->num_faces = (int64_t)c->h_cnt->plane_cursor * 2;
+    st->num_candidates = (int64_t)c->h_cnt->n_cands;
   }
   return 0;
 }

@@ -55,6 +55,7 @@ struct Counters
   unsigned int plane_cursor;                   // units of 2 faces
   unsigned long long big_bits;                 // bits needed by the big-cell list (multiples of 32)
   unsigned long long n_spans;                  // span records requested (may exceed capacity)
+  unsigned long long n_cands;                  // candidate neighbours written by k_cell_bfs
 };
 
 struct FaceRef;
@@ -110,6 +111,16 @@ __device__ __forceinline__ T warp_alloc(T *counter, T want)
     base = __shfl_sync(0xffffffffu, base, 31);
   }
   return base + incl - want;
+}
+
+__device__ __forceinline__ unsigned long long warp_incl_scan_ull(unsigned long long v)
+{
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned long long o = __shfl_up_sync(0xffffffffu, v, d);
+    if ((int)lane_id() >= d) v += o;
+  }
+  return v;
 }
 
 __device__ __forceinline__ void warp_count(unsigned long long *counter, bool pred)
@@ -388,6 +399,11 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__res
   warp_count(&out.cnt->n_no_tet, status == CELL_NO_TET);
   warp_count(&out.cnt->n_incomplete, status == CELL_INCOMPLETE);
   warp_count(&out.cnt->n_outside, status == CELL_OUTSIDE);
+  {
+    // candidates of accepted cells (for the roofline's algorithmic bytes)
+    unsigned long long nc = warp_incl_scan_ull(status == CELL_OK ? (unsigned long long)(n_star + 2) : 0ull);
+    if (lane_id() == 31 && nc) atomicAdd(&out.cnt->n_cands, nc);
+  }
   warp_count(&out.cnt->n_bad, status == CELL_BAD_MESH);
 }
 

@@ -9,15 +9,17 @@ import numpy as np
 from . import particles, decomp, delaunay
 
 CACHE_DIR = os.environ.get("TESSB200_CACHE", "/tmp/tess2_b200_cache")
+# host tessellation time of the last workload built or loaded (reported beside the dense numbers)
+LAST_TESS = {"seconds": None, "workers": None, "cached": False}
 
 
 def _cache_path(key):
     return os.path.join(CACHE_DIR, hashlib.sha1(key.encode()).hexdigest()[:16] + ".npz")
 
 
-def _save(path, blocks):
+def _save(path, blocks, tess_seconds=0.0, workers=0):
     os.makedirs(os.path.dirname(path), exist_ok=True)
-    out = {"n": np.array(len(blocks))}
+    out = {"n": np.array(len(blocks)), "tess_seconds": np.array(float(tess_seconds)), "tess_workers": np.array(int(workers))}
     for i, b in enumerate(blocks):
         out[f"{i}_gid"] = np.array(b["gid"])
         out[f"{i}_particles"] = b["particles"]
@@ -32,6 +34,8 @@ def _save(path, blocks):
 
 def _load(path):
     z = np.load(path)
+    LAST_TESS.update(seconds=float(z["tess_seconds"]) if "tess_seconds" in z else None,
+                     workers=int(z["tess_workers"]) if "tess_workers" in z else None, cached=True)
     blocks = []
     for i in range(int(z["n"])):
         blocks.append(dict(gid=int(z[f"{i}_gid"]), particles=z[f"{i}_particles"], tets=z[f"{i}_tets"],
@@ -63,7 +67,7 @@ def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log
                 layout.append((len(layout), mn, mx))
     if gids is None:
         gids = list(range(len(layout)))
-    key = f"uniform_regular:{n_side}:{blocks_xyz}:{sorted(gids)}:v4"
+    key = f"uniform_regular:{n_side}:{blocks_xyz}:{sorted(gids)}:v5"
     path = _cache_path(key)
     if cache and os.path.exists(path):
         if log:
@@ -90,6 +94,9 @@ def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log
     if log:
         log(f"tessellated {len(gids)} blocks ({sum(b['num_orig'] for b in blocks)} particles, "
             f"{sum(len(b['tets']) for b in blocks)} tets) in {time.time() - t0:.1f} s")
+    import os as _os
+    nworkers = workers if workers is not None else min(len(gids), _os.cpu_count() or 1)
+    LAST_TESS.update(seconds=time.time() - t0, workers=nworkers, cached=False)
     if cache:
-        _save(path, blocks)
+        _save(path, blocks, LAST_TESS["seconds"], nworkers)
     return blocks, layout, dom_min, dom_max

@@ -63,6 +63,8 @@ class DenseStats(C.Structure):
         ("ms_upload", C.c_float), ("ms_circumcenters", C.c_float), ("ms_cells", C.c_float),
         ("ms_scan", C.c_float), ("ms_sort", C.c_float), ("ms_deposit", C.c_float),
         ("ms_exchange", C.c_float), ("ms_download", C.c_float), ("ms_total_device", C.c_float),
+        ("ms_bfs", C.c_float), ("ms_nbrs", C.c_float), ("ms_faces", C.c_float),
+        ("num_faces", C.c_int64), ("num_candidates", C.c_int64),
     ]
 
     def as_dict(self):
