@@ -47,7 +47,10 @@ enum
 enum
 {
   TESSB200_DENSE_TESS = 0, /* DENSE_TESS: Voronoi-cell deposit (src/dense.cpp:220-313) */
-  TESSB200_DENSE_CIC = 1   /* DENSE_CIC : cloud-in-cell    (src/dense.cpp:486-562) */
+  TESSB200_DENSE_CIC = 1,  /* DENSE_CIC : cloud-in-cell    (src/dense.cpp:486-562) */
+  TESSB200_DENSE_DTFE = 2  /* NOT in the reference (its enum stops at DENSE_CIC): first-order DTFE, per-vertex
+                              density 4m / (volume of the star) interpolated linearly inside every Delaunay tet.
+                              3-D output only.  See DESIGN.md 3.6; checked against oracle/dense_oracle.c only. */
 };
 
 /* One DIY block = the fields of `struct dblock_t` (include/tess/delaunay.h:38-63) that the

@@ -8,6 +8,6 @@ Only what the hot path needs lives here:
   multi.py   one-process-per-GPU driver (torch.distributed for the plumbing, NCCL inside the library)
   harness/   host-side input staging: particle generators, block decomposition, SciPy-Qhull
 """
-from .dense import (DENSE_TESS, DENSE_CIC, Context, DenseResult, dense, WriteGrid, fill_vert_to_tet,  # noqa: F401
+from .dense import (DENSE_TESS, DENSE_CIC, DENSE_DTFE, Context, DenseResult, dense, WriteGrid, fill_vert_to_tet,  # noqa: F401
                     fill_circumcenters, volume, complete, default_context)
 from .lib import TessB200Error, LIB_PATH  # noqa: F401

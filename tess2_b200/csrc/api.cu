@@ -129,7 +129,7 @@ struct BlockRes
   int num_orig = 0, num_particles = 0, num_tets = 0;
   float bmin[3], bmax[3];
   bool have_v2t = false;
-  Buf particles, tets, v2t, cc;
+  Buf particles, tets, v2t, cc, rho;
   // geometry of the last run
   int mn[3], num[3];
   long long npts = 0, nrows = 0, row_base = 0, out_off = 0;
@@ -198,6 +198,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   CU(cudaFuncSetAttribute(k_cell_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
   CU(cudaFuncSetAttribute(k_cell_volumes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOL_SMEM));
   CU(cudaFuncSetAttribute(k_cell_nbrs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NBRS_SMEM));
+  CU(cudaFuncSetAttribute(k_vertex_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
   *out = c;
   return 0;
 }
@@ -205,7 +206,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
 static void free_blocks(tessb200_ctx *c)
 {
   for (BlockRes *b : c->blocks) {
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release();
     delete b;
   }
   c->blocks.clear();
@@ -250,7 +251,8 @@ struct Geometry
 static int check_params(const tessb200_dense_params *p)
 {
   if (!p) return fail(TESSB200_EINVAL, "params is NULL");
-  if (p->alg != TESSB200_DENSE_TESS && p->alg != TESSB200_DENSE_CIC) return fail(TESSB200_EINVAL, "unknown alg %d", p->alg);
+  if (p->alg != TESSB200_DENSE_TESS && p->alg != TESSB200_DENSE_CIC && p->alg != TESSB200_DENSE_DTFE) return fail(TESSB200_EINVAL, "unknown alg %d", p->alg);
+  if (p->alg == TESSB200_DENSE_DTFE && p->project) return fail(TESSB200_EINVAL, "the DTFE mode has no projected variant");
   for (int d = 0; d < 3; d++)
     if (p->glo_num_idx[d] < 2 || p->glo_num_idx[d] > 32767)
       return fail(TESSB200_ELIMIT, "glo_num_idx[%d] = %d outside [2, 32767]", d, p->glo_num_idx[d]);
@@ -391,7 +393,7 @@ static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *block
     if (blocks[order[i]].gid == blocks[order[i - 1]].gid) return fail(TESSB200_EINVAL, "duplicate gid %d", blocks[order[i]].gid);
   while ((int)c->blocks.size() > nblocks) {
     BlockRes *b = c->blocks.back();
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release();
     delete b;
     c->blocks.pop_back();
   }
@@ -549,12 +551,102 @@ static int copy_block_out(tessb200_ctx *c, const tessb200_dense_params &p, Block
   return 0;
 }
 
+// alg 2 (DTFE, first order): per block, vertex densities from the star volumes, then one thread per
+// tet writes the grid points it owns inside the block's sub-grid.  No span records, no exchange: a
+// block rasterises its own sub-grid from its own (ghost-padded) tessellation.
+static int run_dtfe(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_stats *st, const PipeIO &io, const Geometry &G)
+{
+  cudaStream_t s = c->stream;
+  const int nloc = (int)c->blocks.size();
+  long long cells = 0, tets = 0;
+  for (BlockRes *b : c->blocks) { cells += b->num_orig; tets += b->num_tets; }
+  c->launches = 0;
+  TRY(c->out.ensure(sizeof(float) * (size_t)std::max<long long>(4, G.out_floats)));
+  TRY(c->d_cnt.ensure(sizeof(Counters)));
+  Counters *cnt = c->d_cnt.as<Counters>();
+  CU(cudaEventRecord(c->ev[2], s));
+  CU(cudaMemsetAsync(c->out.p, 0, sizeof(float) * (size_t)G.out_floats, s));
+  long long n_slow = 0;
+  for (int k = 0; k < nloc; k++) {
+    BlockRes *b = c->blocks[k];
+    if (io.pipelined && io.h2d_done) CU(cudaStreamWaitEvent(s, (*io.h2d_done)[k], 0));
+    TRY(prep_block_geometry(c, b));
+    if (b->num_particles && b->num_tets && b->npts) {
+      TRY(b->rho.ensure(4 * (size_t)b->num_particles));
+      const uint32_t cap = (uint32_t)std::max(1024, b->num_particles / 64);
+      TRY(c->overflow.ensure(sizeof(uint2) * (size_t)cap));
+      CU(cudaMemsetAsync(c->d_cnt.p, 0, sizeof(Counters), s));
+      DevBlock db = dev_block(b);
+      k_vertex_density<<<cdiv(b->num_particles, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, s>>>(db, p->mass, b->rho.as<float>(), c->overflow.as<uint32_t>(),
+                                                                                           &cnt->n_overflow, cap);
+      COUNT_LAUNCH(c, 1);
+      CU(cudaGetLastError());
+      TRY(read_counters(c));
+      if (c->h_cnt->n_overflow > cap) return fail(TESSB200_ELIMIT, "%u vertices exceed the fast star workspace", c->h_cnt->n_overflow);
+      if (c->h_cnt->n_overflow) {
+        const int n = (int)c->h_cnt->n_overflow;
+        TRY(c->ws_big.ensure(sizeof(int) * (size_t)BIG_STAR_CAP * (size_t)n));
+        k_vertex_density_big<<<cdiv((long long)n * 32, 128), 128, 0, s>>>(db, p->mass, b->rho.as<float>(), c->overflow.as<uint32_t>(), n, c->ws_big.as<int>());
+        COUNT_LAUNCH(c, 1);
+        n_slow += n;
+      }
+      k_dtfe_raster<<<cdiv(b->num_tets, 128), 128, 0, s>>>(db, b->rho.as<float>(), G.g, make_int3(b->mn[0], b->mn[1], b->mn[2]),
+                                                          make_int3(b->num[0], b->num[1], b->num[2]), c->out.as<float>() + b->out_off);
+      COUNT_LAUNCH(c, 1);
+      CU(cudaGetLastError());
+    }
+    if (io.pipelined) {
+      CU(cudaEventRecord(c->blk_ev[k % 64], s));
+      CU(cudaStreamWaitEvent(c->copy_stream, c->blk_ev[k % 64], 0));
+      tessb200_block *ob = nullptr;
+      for (int j = 0; j < io.nblocks_out; j++) if (io.out_blocks[j].gid == b->gid) ob = &io.out_blocks[j];
+      TRY(copy_block_out(c, *p, b, ob, io.global_grid, c->copy_stream));
+    }
+  }
+  CU(cudaEventRecord(c->ev[9], s));
+  if (st) {
+    memset(st, 0, sizeof(*st));
+    const int nb = 592;
+    TRY(c->stat_sum.ensure(sizeof(double) * nb));
+    TRY(c->stat_max.ensure(sizeof(float) * nb));
+    double tot = 0.0;
+    float mx = 0.0f;
+    if (G.out_floats) {
+      k_grid_stats<<<nb, 256, 0, s>>>(c->out.as<float>(), (unsigned long long)G.out_floats, c->stat_sum.as<double>(), c->stat_max.as<float>());
+      CU(cudaMemcpyAsync(c->h_sum, c->stat_sum.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync(c->h_max, c->stat_max.p, sizeof(float) * nb, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      for (int i = 0; i < nb; i++) { tot += c->h_sum[i]; mx = std::max(mx, c->h_max[i]); }
+    }
+    st->tot_mass = tot * (double)G.g.div;
+    st->max_dense = mx;
+  }
+  CU(cudaStreamSynchronize(s));
+  if (io.pipelined) CU(cudaStreamSynchronize(c->copy_stream));
+  c->ran = true;
+  c->last_params = *p;
+  c->out_floats = G.out_floats;
+  if (st) {
+    st->num_cells = cells;
+    st->num_tets = tets;
+    st->num_slow_cells = n_slow;
+    st->num_kernel_launches = c->launches;
+    for (BlockRes *b : c->blocks) st->num_grid_pts += b->npts;
+    float m = 0;
+    cudaEventElapsedTime(&m, c->ev[2], c->ev[9]);
+    st->ms_total_device = m;
+    st->ms_cells = m;
+  }
+  return 0;
+}
+
 static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_stats *st, const PipeIO &io)
 {
   if (c->blocks.empty()) return fail(TESSB200_ESTATE, "tessb200_dense_run before tessb200_dense_upload");
   CU(cudaSetDevice(c->device));
   Geometry G;
   TRY(make_geometry(c, p, &G));
+  if (p->alg == TESSB200_DENSE_DTFE) return run_dtfe(c, p, st, io, G);
   cudaStream_t s = c->stream;
   const int nloc = (int)c->blocks.size();
   const int nall = (int)G.boxes.size();
@@ -952,7 +1044,7 @@ extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nbl
 struct TmpBlock
 {
   BlockRes b;
-  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); }
+  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.rho.release(); }
 };
 
 static int upload_tmp(tessb200_ctx *c, TmpBlock &t, int num_particles, const float *particles, int num_tets, const int *tets, const int *v2t)

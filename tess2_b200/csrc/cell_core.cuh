@@ -89,7 +89,7 @@ TB_HD float idx2phys1(int idx, float step, float gmin) { return fadd(fmul((float
 TB_HD int phys2idx1(float pos, float step, float gmin) { return (int)fdiv(fsub(pos, gmin), step); }
 
 // ---- circumcenter, src/tet.cpp:37-66 (norm :122-128, cross :131-136, determinant :139-143) ----
-TB_HD void circumcenter(const float *a, const float *b, const float *c, const float *d, float *center)
+TB_HD void circumcenter(const float *a, const float *b, const float *c, const float *d, float *center, float *det_out = nullptr)
 {
   float t[3], u[3], v[3];
   for (int i = 0; i < 3; i++) {
@@ -108,6 +108,7 @@ TB_HD void circumcenter(const float *a, const float *b, const float *c, const fl
   det = fsub(det, fmul(fmul(v[0], u[1]), t[2]));
   det = fsub(det, fmul(fmul(u[0], t[1]), v[2]));
   det = fsub(det, fmul(fmul(t[0], v[1]), u[2]));
+  if (det_out) *det_out = det;
   float den = fmul(2.0f, det);
   float uv[3], vt[3], tu[3];
   uv[0] = fsub(fmul(u[1], v[2]), fmul(u[2], v[1]));
@@ -436,7 +437,7 @@ TB_HD int vis_find_or_insert(WS &ws, int key, int *count, int cap)
 
 template <class WS, class Sink>
 TB_HD int star_bfs_cands(int site, int t0, const int4 *tets, const float4 *cc, WS &ws, int star_cap, int *n_star, float *cmin,
-                         float *cmax, Sink &sink)
+                         float *cmax, Sink &sink, double *vsum = nullptr)
 {
   ws.hash_clear_vis();
   int ns = 0, ncand = 0;
@@ -447,6 +448,7 @@ TB_HD int star_bfs_cands(int site, int t0, const int4 *tets, const float4 *cc, W
     float4 c = cc[t0];
     cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
     cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+    if (vsum) *vsum += (double)c.w;   // tet volume rides in the circumcenter record's 4th component
     int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
     if (is < 0) return CELL_OVERFLOW;
     for (int q = 0; q < 3; q++) {
@@ -481,6 +483,7 @@ TB_HD int star_bfs_cands(int site, int t0, const int4 *tets, const float4 *cc, W
     }
     cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
     cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+    if (vsum) *vsum += (double)c.w;   // tet volume rides in the circumcenter record's 4th component
     const int par = ws.star((int)ws.parent_idx(head));
     const int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
     const int ip = nb.x == par ? 0 : (nb.y == par ? 1 : (nb.z == par ? 2 : (nb.w == par ? 3 : -1)));
@@ -801,6 +804,69 @@ TB_HD void cic_weights(const float *pt, float scalar, const GridGeom &g, int *id
       }
   for (int i = 0; i < 8; i++) vals[i] = fmul(fdiv(w[i], tot), scalar);
 }
+
+// ---- DTFE, first order (alg 2; not in the reference) ------------------------------
+// determinant in tet.cpp:139-143's term order
+TB_HD float det3(const float *t, const float *u, const float *v)
+{
+  float r = fmul(fmul(t[0], u[1]), v[2]);
+  r = fadd(r, fmul(fmul(u[0], v[1]), t[2]));
+  r = fadd(r, fmul(fmul(v[0], t[1]), u[2]));
+  r = fsub(r, fmul(fmul(v[0], u[1]), t[2]));
+  r = fsub(r, fmul(fmul(u[0], t[1]), v[2]));
+  r = fsub(r, fmul(fmul(t[0], v[1]), u[2]));
+  return r;
+}
+// One tet prepared for rasterisation.  Face i is opposite vertex i; its three vertices are taken in
+// ascending index order so that the two tets sharing a face evaluate bit-identical determinants.
+struct DtfeTet
+{
+  float a[4][3], t[4][3], u[4][3];   // per face: first vertex, (second - first), (third - first)
+  float sd[4];                       // determinant of the face with the opposite vertex
+  float rho[4];
+  TB_HD float face_det(int f, const float *x) const
+  {
+    float v[3] = {fsub(x[0], a[f][0]), fsub(x[1], a[f][1]), fsub(x[2], a[f][2])};
+    return det3(t[f], u[f], v);
+  }
+  // false when the tet is degenerate
+  TB_HD bool setup(const int *tv, const float *p0, const float *p1, const float *p2, const float *p3, const float *r)
+  {
+    const float *pos[4] = {p0, p1, p2, p3};
+    bool ok = true;
+    for (int i = 0; i < 4; i++) {
+      int id[3], k = 0;
+      for (int j = 0; j < 4; j++) if (j != i) id[k++] = j;
+      // sort the three slots by vertex index
+      if (tv[id[0]] > tv[id[1]]) { int s = id[0]; id[0] = id[1]; id[1] = s; }
+      if (tv[id[1]] > tv[id[2]]) { int s = id[1]; id[1] = id[2]; id[2] = s; }
+      if (tv[id[0]] > tv[id[1]]) { int s = id[0]; id[0] = id[1]; id[1] = s; }
+      for (int d = 0; d < 3; d++) {
+        a[i][d] = pos[id[0]][d];
+        t[i][d] = fsub(pos[id[1]][d], pos[id[0]][d]);
+        u[i][d] = fsub(pos[id[2]][d], pos[id[0]][d]);
+      }
+      sd[i] = face_det(i, pos[i]);
+      if (!(sd[i] != 0.0f)) ok = false;
+      rho[i] = r[i];
+    }
+    return ok;
+  }
+  // value at x if this tet owns x: for every face the point is on the opposite vertex's side, a point
+  // exactly on a face belonging to the tet on the face's positive side
+  TB_HD bool eval(const float *x, float *val) const
+  {
+    float acc = 0.0f;
+    for (int f = 0; f < 4; f++) {
+      float sp = face_det(f, x);
+      if (sp == 0.0f) { if (!(sd[f] > 0.0f)) return false; }
+      else if ((sp > 0.0f) != (sd[f] > 0.0f)) return false;
+      acc = fadd(acc, fmul(fdiv(sp, sd[f]), rho[f]));
+    }
+    *val = acc;
+    return true;
+  }
+};
 
 // ---- span records ----------------------------------------------------------------------------
 // One x-run of deposits in one row of one block's density array.

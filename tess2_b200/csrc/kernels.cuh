@@ -147,7 +147,7 @@ __global__ void k_vert_to_tet(const int4 *__restrict__ tets, int num_tets, int *
 }
 
 // ---- K1: circumcenters, one thread per tet ---------------------------------------------------------
-// reads 16 B of the tet record (verts only) + 4 gathered particles, writes one float4
+// reads 16 B of the tet record (verts only) + 4 gathered particles, writes one float4 (x, y, z, volume)
 __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ tets, int num_tets,
                                                         const float *__restrict__ particles, float4 *__restrict__ cc)
 {
@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ 
     c[i] = __ldg(&particles[3 * (size_t)v.z + i]);
     d[i] = __ldg(&particles[3 * (size_t)v.w + i]);
   }
-  circumcenter(a, b, c, d, o);
-  cc[t] = make_float4(o[0], o[1], o[2], 0.0f);
+  float det;
+  circumcenter(a, b, c, d, o, &det);
+  cc[t] = make_float4(o[0], o[1], o[2], fdiv(fabsf(det), 6.0f));   // w = tet volume (used by the DTFE mode)
 }
 
 // ---- K3a part 1: topology + faces, one thread per cell --------------------------------------------
@@ -1227,6 +1228,108 @@ __global__ void __launch_bounds__(128) k_cell_volumes_big(DevBlock blk, const ui
   if (complete_out) complete_out[site] = comp;
   if (volume_out) volume_out[site] = vol;
   if (density_out) density_out[site] = vol > 0.0f ? fdiv(mass, vol) : 0.0f;
+}
+
+// ---- DTFE mode (alg 2) -------------------------------------------------------------------------------
+struct NoSink
+{
+  __device__ __forceinline__ void operator()(int, int, int) {}
+};
+
+// rho(v) = 4 m / sum of the volumes of the tets of v's star (double sum in BFS order); -1 where the
+// star is infinite or v is in no tet.  One thread per particle (ghosts too: tets near the block
+// border use their densities).
+__global__ void __launch_bounds__(TOPO_THREADS) k_vertex_density(DevBlock blk, float mass, float *__restrict__ rho, uint32_t *overflow,
+                                                                 unsigned int *n_overflow, uint32_t cap_overflow)
+{
+  extern __shared__ int ws_s[];
+  const int v = blockIdx.x * TOPO_THREADS + threadIdx.x;
+  StarWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
+  int status = -1, n_star = 0;
+  double sum = 0.0;
+  if (v < blk.num_particles) {
+    float cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
+    NoSink sink;
+    int t0 = blk.v2t[v];
+    status = t0 < 0 ? CELL_NO_TET : star_bfs_cands(v, t0, blk.tets, blk.cc, ws, TOPO_STAR_CAP, &n_star, cmin, cmax, sink, &sum);
+  }
+  __syncwarp();
+  const bool ovf = status == CELL_OVERFLOW;
+  uint32_t slot = warp_append<unsigned int>(n_overflow, ovf);
+  if (ovf && slot < cap_overflow) overflow[slot] = (uint32_t)v;
+  if (v < blk.num_particles && !ovf) rho[v] = (status == CELL_OK && sum > 0.0) ? (float)(4.0 * (double)mass / sum) : -1.0f;
+}
+
+// the same for stars that do not fit the shared-memory workspace: one warp per vertex
+__global__ void __launch_bounds__(128) k_vertex_density_big(DevBlock blk, float mass, float *__restrict__ rho, const uint32_t *__restrict__ verts,
+                                                            int n_verts, int *ws_g)
+{
+  const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = (int)lane_id();
+  if (wi >= n_verts) return;
+  const int v = (int)verts[wi];
+  int *star = ws_g + (size_t)wi * BIG_STAR_CAP;
+  int ns = 1;
+  bool finite = true, bad = false;
+  double sum = 0.0;
+  if (lane == 0) star[0] = blk.v2t[v];
+  __syncwarp();
+  for (int head = 0; head < ns && finite && !bad; head++) {
+    const int t = star[head];
+    const int4 vv4 = blk.tets[2 * (size_t)t], nb = blk.tets[2 * (size_t)t + 1];
+    sum += (double)blk.cc[t].w;
+    const int vv[4] = {vv4.x, vv4.y, vv4.z, vv4.w}, bb[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (!finite || bad || vv[i] == v) continue;
+      const int next = bb[i];
+      if (next < 0) { finite = false; continue; }
+      if (!warp_contains(star, ns, next)) {
+        if (ns >= BIG_STAR_CAP) { bad = true; continue; }
+        if (lane == 0) star[ns] = next;
+        ns++;
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) rho[v] = (finite && !bad && sum > 0.0) ? (float)(4.0 * (double)mass / sum) : -1.0f;
+}
+
+// tet-to-grid rasterisation: one thread per tet walks the grid points of the tet's bounding box that
+// lie in this block's sub-grid, and writes the linearly interpolated density at the points the tet
+// owns.  Every grid point has exactly one owner (DtfeTet::eval), so the stores need no atomics.
+__global__ void __launch_bounds__(128) k_dtfe_raster(DevBlock blk, const float *__restrict__ rho, const __grid_constant__ GridGeom g, int3 b_lo, int3 b_num,
+                                                     float *__restrict__ out)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= blk.num_tets) return;
+  const int4 v = blk.tets[2 * (size_t)t];
+  const int tv[4] = {v.x, v.y, v.z, v.w};
+  float r[4], p[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    r[i] = rho[tv[i]];
+    for (int d = 0; d < 3; d++) p[i][d] = blk.particles[3 * (size_t)tv[i] + d];
+  }
+  if (r[0] < 0.0f || r[1] < 0.0f || r[2] < 0.0f || r[3] < 0.0f) return;
+  DtfeTet T;
+  if (!T.setup(tv, p[0], p[1], p[2], p[3], r)) return;
+  int lo[3], hi[3];
+  const int blo[3] = {b_lo.x, b_lo.y, b_lo.z}, bnum[3] = {b_num.x, b_num.y, b_num.z};
+  for (int d = 0; d < 3; d++) {
+    float mn = fminf(fminf(p[0][d], p[1][d]), fminf(p[2][d], p[3][d])), mx = fmaxf(fmaxf(p[0][d], p[1][d]), fmaxf(p[2][d], p[3][d]));
+    lo[d] = phys2idx1(mn, g.step[d], g.gmin[d]);
+    hi[d] = phys2idx1(mx, g.step[d], g.gmin[d]) + 1;
+    if (lo[d] < blo[d]) lo[d] = blo[d];
+    if (hi[d] > blo[d] + bnum[d] - 1) hi[d] = blo[d] + bnum[d] - 1;
+  }
+  for (int k = lo[2]; k <= hi[2]; k++)
+    for (int j = lo[1]; j <= hi[1]; j++)
+      for (int i = lo[0]; i <= hi[0]; i++) {
+        const float pos[3] = {idx2phys1(i, g.step[0], g.gmin[0]), idx2phys1(j, g.step[1], g.gmin[1]), idx2phys1(k, g.step[2], g.gmin[2])};
+        float val;
+        if (T.eval(pos, &val)) out[((size_t)(k - blo[2]) * bnum[1] + (j - blo[1])) * bnum[0] + (i - blo[0])] = val;
+      }
 }
 
 } // namespace tb

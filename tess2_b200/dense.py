@@ -22,6 +22,7 @@ from . import lib as _l
 
 DENSE_TESS = 0   # include/tess/dense.hpp:35
 DENSE_CIC = 1    # include/tess/dense.hpp:36
+DENSE_DTFE = 2   # not in the reference: first-order DTFE
 
 
 def _fp(a):

@@ -223,9 +223,9 @@ static std::vector<float4> make_cc(int num_tets, const int *tets, const float *p
   std::vector<float4> cc(num_tets);
   for (int t = 0; t < num_tets; t++) {
     const int *v = &tets[8 * t];
-    float o[3];
-    circumcenter(&particles[3 * v[0]], &particles[3 * v[1]], &particles[3 * v[2]], &particles[3 * v[3]], o);
-    cc[t] = float4{o[0], o[1], o[2], 0.0f};
+    float o[3], det;
+    circumcenter(&particles[3 * v[0]], &particles[3 * v[1]], &particles[3 * v[2]], &particles[3 * v[3]], o, &det);
+    cc[t] = float4{o[0], o[1], o[2], fdiv(fabsf(det), 6.0f)};
   }
   return cc;
 }
@@ -263,6 +263,54 @@ extern "C" void emu_volumes(int num_verts, int num_tets, const int *tets, const 
       vol = fadd(vol, fdiv(fmul(aa.area, fsqrt(n)), 6.0f));
     }
     out[v] = vol;
+  }
+}
+
+// alg 2 (DTFE): k_vertex_density + k_dtfe_raster single-stepped
+struct NoSinkH { void operator()(int, int, int) {} };
+static void emu_dtfe_block(const emu_block_t &b, const int *v2t, const BlockBox &bx, const GridGeom &g)
+{
+  std::vector<float4> cc = make_cc(b.num_tets, b.tets, b.particles);
+  std::vector<float> rho(b.num_particles, -1.0f);
+  HostWS big;
+  for (int v = 0; v < b.num_particles; v++) {
+    if (v2t[v] < 0) continue;
+    StarHostWS sw;
+    NoSinkH sink;
+    int ns;
+    float cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
+    double sum = 0.0;
+    int st = star_bfs_cands(v, v2t[v], (const int4 *)b.tets, cc.data(), sw, 52, &ns, cmin, cmax, sink, &sum);
+    if (st == CELL_OVERFLOW) {
+      int nn;
+      st = star_and_neighbors(v, v2t[v], (const int4 *)b.tets, big, 4096, 1024, &ns, &nn);
+      sum = 0.0;
+      if (st == CELL_OK) for (int k = 0; k < ns; k++) sum += (double)cc[big.star(k)].w;
+    }
+    if (st == CELL_OK && sum > 0.0) rho[v] = (float)(4.0 * (double)g.mass / sum);
+  }
+  for (int t = 0; t < b.num_tets; t++) {
+    const int *tv = &b.tets[8 * t];
+    float r[4] = {rho[tv[0]], rho[tv[1]], rho[tv[2]], rho[tv[3]]};
+    if (r[0] < 0 || r[1] < 0 || r[2] < 0 || r[3] < 0) continue;
+    DtfeTet T;
+    if (!T.setup(tv, &b.particles[3 * tv[0]], &b.particles[3 * tv[1]], &b.particles[3 * tv[2]], &b.particles[3 * tv[3]], r)) continue;
+    int lo[3], hi[3];
+    for (int d = 0; d < 3; d++) {
+      float mn = b.particles[3 * tv[0] + d], mx = mn;
+      for (int j = 1; j < 4; j++) { mn = fminf(mn, b.particles[3 * tv[j] + d]); mx = fmaxf(mx, b.particles[3 * tv[j] + d]); }
+      lo[d] = phys2idx1(mn, g.step[d], g.gmin[d]);
+      hi[d] = phys2idx1(mx, g.step[d], g.gmin[d]) + 1;
+      if (lo[d] < bx.b_lo[d]) lo[d] = bx.b_lo[d];
+      if (hi[d] > bx.b_lo[d] + bx.b_num[d] - 1) hi[d] = bx.b_lo[d] + bx.b_num[d] - 1;
+    }
+    for (int k = lo[2]; k <= hi[2]; k++)
+      for (int j = lo[1]; j <= hi[1]; j++)
+        for (int i = lo[0]; i <= hi[0]; i++) {
+          const float pos[3] = {idx2phys1(i, g.step[0], g.gmin[0]), idx2phys1(j, g.step[1], g.gmin[1]), idx2phys1(k, g.step[2], g.gmin[2])};
+          float val;
+          if (T.eval(pos, &val)) b.density[((size_t)(k - bx.b_lo[2]) * bx.b_num[1] + (j - bx.b_lo[1])) * bx.b_num[0] + (i - bx.b_lo[0])] = val;
+        }
   }
 }
 
@@ -316,6 +364,26 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
   kl.cell_bits = ceil_log2(cb + 1);
   kl.z_bits = p.project ? ceil_log2((unsigned long long)p.glo_num_idx[2] + 2) : 0;
 
+  if (p.alg == TESSB200_DENSE_DTFE) {
+    for (int bi = 0; bi < nblocks; bi++) {
+      emu_block_t &b = blocks[bi];
+      memset(b.density, 0, sizeof(float) * (size_t)b.num_grid_pts);
+      std::vector<int> v2t_own;
+      const int *v2t = b.vert_to_tet;
+      if (!v2t) {
+        v2t_own.resize(b.num_particles);
+        emu_fill_vert_to_tet(b.num_particles, b.num_tets, b.tets, v2t_own.data());
+        v2t = v2t_own.data();
+      }
+      emu_dtfe_block(b, v2t, boxes[bi], g);
+    }
+    for (int d = 0; d < 3; d++) {
+      ep->data_mins[d] = p.data_mins[d]; ep->data_maxs[d] = p.data_maxs[d];
+      ep->grid_phys_mins[d] = p.grid_phys_mins[d]; ep->grid_phys_maxs[d] = p.grid_phys_maxs[d];
+      ep->grid_step_size[d] = p.grid_step_size[d];
+    }
+    return 0;
+  }
   std::vector<Rec> recs;
   VecEmit emit{&recs};
   Topo tp;

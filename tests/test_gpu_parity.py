@@ -228,3 +228,39 @@ def test_full_size_properties(ctx, port):
     # the oracle on the same inputs (a few seconds per block): bit equality of the whole grid
     o = port.dense(blocks, gs)
     compare_dense(res, o, "config-2 shape")
+
+
+# ---- alg 2: first-order DTFE (not in the reference; checked against the repo's own CPU statement) ----
+@pytest.mark.parametrize("name,gs", [("c1", (64, 64, 64)), ("u16x8", (32, 32, 32)), ("clump8", (48, 48, 48)), ("aniso", (40, 28, 17))])
+def test_dtfe_matches_cpu_statement(ctx, port, name, gs):
+    blocks = dataset(name)
+    o = port.dense(blocks, gs, alg=2)
+    res = run_gpu(ctx, blocks, gs, alg=2)
+    assert res.block_min_idx == o["block_min_idx"] and res.block_num_idx == o["block_num_idx"]
+    for i, (d1, d2) in enumerate(zip(res.block_density, o["block_density"])):
+        assert_same_bits(d1, d2, f"{name} dtfe block {i}")
+    # three-step (resident) interface gives the same bytes
+    params = ctx.make_params(2, 0, None, None, False, (0.0, 0.0, 1.0), 1.0, 1e-4, gs)
+    ctx.upload(blocks)
+    ctx.run(params)
+    res3 = ctx.download(params)
+    assert_same_bits(res3.grid, res.grid, "dtfe three-step vs one-call")
+
+
+def test_dtfe_properties(ctx):
+    """Properties that do not need an oracle: the DTFE field integrates to the mass of the covered
+    particles (each tet contributes V/4 * sum of its vertex densities), it is linear in the particle
+    mass, and it is continuous (no zero holes strictly inside the covered region)."""
+    blk = dataset("c1")[0]
+    gs = (64, 64, 64)
+    res = run_gpu(ctx, [blk], gs, alg=2)
+    g = res.grid.astype(np.float64)
+    div = float(res.div)
+    tot = g.sum() * div
+    n_int = int((g[8:-8, 8:-8, 8:-8] > 0).sum())
+    assert n_int == g[8:-8, 8:-8, 8:-8].size                      # the interior is fully covered
+    assert 0.85 * blk["num_orig"] < tot < 1.05 * blk["num_orig"]  # grid quadrature of a mass-conserving field
+    res2 = run_gpu(ctx, [blk], gs, alg=2, mass=2.0)
+    assert_same_bits(res2.grid, (res.grid * np.float32(2.0)).astype(np.float32), "dtfe linear in mass")
+    with pytest.raises(Exception):
+        run_gpu(ctx, [blk], gs, alg=2, project=True)
