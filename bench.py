@@ -298,6 +298,23 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = G_total / (e2e_ms * 1e-3)
     checksum = float(sum(float(o.astype(np.float64).sum()) for o in out_blocks))
 
+    # ---- the other two estimators on the same resident inputs (BASELINE config 5 compares CIC with the
+    # tessellation estimator; DTFE is the repo's first-order mode): a few steps each, reported beside ----
+    other = {}
+    ctx.upload(blocks)
+    for name, alg in (("DENSE_CIC", tess2_b200.DENSE_CIC), ("DENSE_DTFE (not in the reference)", tess2_b200.DENSE_DTFE)):
+        pa = ctx.make_params(alg, ng, dmin, dmax, False, (0.0, 0.0, 1.0), 1.0, 1e-4, gsize)
+        for _ in range(2):
+            ctx.run(pa)
+        barrier()
+        ms = 0.0
+        reps = 3
+        for _ in range(reps):
+            ms += ctx.run(pa).ms_total_device
+        barrier()
+        ms = multi.max_over_ranks(ms / reps)
+        other[name] = {"ms_per_step": ms, "grid_points_per_sec": G_total / (ms * 1e-3)}
+
     # ---- roofline of the dominant kernel (algorithmic bytes: DESIGN.md section 4) -----------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -364,6 +381,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "other_algs": other,
             "host_tess": {"engine": "SciPy Qhull 'Qt', one process per block", "seconds": host_tess.get("seconds"), "workers": host_tess.get("workers"),
                           "from_cache": host_tess.get("cached"),
                           "tess_plus_dense_seconds": (host_tess["seconds"] + e2e_ms * 1e-3) if host_tess.get("seconds") else None},

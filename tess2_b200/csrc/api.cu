@@ -590,9 +590,22 @@ static int run_dtfe(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
         COUNT_LAUNCH(c, 1);
         n_slow += n;
       }
-      k_dtfe_raster<<<cdiv(b->num_tets, 128), 128, 0, s>>>(db, b->rho.as<float>(), G.g, make_int3(b->mn[0], b->mn[1], b->mn[2]),
-                                                          make_int3(b->num[0], b->num[1], b->num[2]), c->out.as<float>() + b->out_off);
-      COUNT_LAUNCH(c, 1);
+      // seed grid over the block's bounds (about 8 particles per coarse cell), then point location
+      int cgn = (int)cbrt((double)b->num_orig / 8.0);
+      cgn = std::max(1, std::min(cgn, 256));
+      const int3 cg = make_int3(cgn, cgn, cgn);
+      const float3 bmin = make_float3(b->bmin[0], b->bmin[1], b->bmin[2]);
+      const float3 inv_cell = make_float3((float)cgn / fmaxf(b->bmax[0] - b->bmin[0], 1e-30f), (float)cgn / fmaxf(b->bmax[1] - b->bmin[1], 1e-30f),
+                                          (float)cgn / fmaxf(b->bmax[2] - b->bmin[2], 1e-30f));
+      const size_t nseed = (size_t)cgn * cgn * cgn + 1;
+      TRY(c->hdr_big.ensure(4 * nseed));
+      CU(cudaMemsetAsync(c->hdr_big.p, 0xFF, 4 * nseed, s));
+      k_dtfe_seed<<<cdiv(b->num_particles, 256), 256, 0, s>>>(db, bmin, inv_cell, cg, c->hdr_big.as<int>());
+      const int3 blo = make_int3(b->mn[0], b->mn[1], b->mn[2]), bnum = make_int3(b->num[0], b->num[1], b->num[2]);
+      const long long nthreads = (long long)((b->num[0] + DTFE_CHUNK - 1) / DTFE_CHUNK) * b->num[1] * b->num[2];
+      k_dtfe_raster<<<cdiv(nthreads, 128), 128, 0, s>>>(db, b->rho.as<float>(), G.g, blo, bnum, bmin, inv_cell, cg, c->hdr_big.as<int>(),
+                                                       c->out.as<float>() + b->out_off, &cnt->n_big);
+      COUNT_LAUNCH(c, 2);
       CU(cudaGetLastError());
     }
     if (io.pipelined) {

@@ -852,6 +852,52 @@ struct DtfeTet
     }
     return ok;
   }
+  // set up face i alone (the walk needs only the faces it actually tests)
+  TB_HD void setup_face(int i, const int *tv, const float (*pos)[3])
+  {
+    int id[3], k = 0;
+    for (int j = 0; j < 4; j++) if (j != i) id[k++] = j;
+    if (tv[id[0]] > tv[id[1]]) { int s = id[0]; id[0] = id[1]; id[1] = s; }
+    if (tv[id[1]] > tv[id[2]]) { int s = id[1]; id[1] = id[2]; id[2] = s; }
+    if (tv[id[0]] > tv[id[1]]) { int s = id[0]; id[0] = id[1]; id[1] = s; }
+    for (int d = 0; d < 3; d++) {
+      a[i][d] = pos[id[0]][d];
+      t[i][d] = fsub(pos[id[1]][d], pos[id[0]][d]);
+      u[i][d] = fsub(pos[id[2]][d], pos[id[0]][d]);
+    }
+    sd[i] = face_det(i, pos[i]);
+  }
+  // walk step: faces are set up and tested one at a time; returns -1 if the tet owns x (then all four
+  // faces are set up and sp[] holds the point's determinants), -2 if the tet is degenerate, else the
+  // face to cross.  Same decisions as setup() + locate().
+  TB_HD int locate_lazy(const int *tv, const float (*pos)[3], const float *x, float *sp)
+  {
+    for (int f = 0; f < 4; f++) {
+      setup_face(f, tv, pos);
+      if (!(sd[f] != 0.0f)) return -2;
+      sp[f] = face_det(f, x);
+      if (sp[f] == 0.0f) { if (!(sd[f] > 0.0f)) return f; }
+      else if ((sp[f] > 0.0f) != (sd[f] > 0.0f)) return f;
+    }
+    return -1;
+  }
+  // eval()'s sum from determinants already computed by locate_lazy
+  TB_HD float value_from(const float *sp) const
+  {
+    float acc = 0.0f;
+    for (int f = 0; f < 4; f++) acc = fadd(acc, fmul(fdiv(sp[f], sd[f]), rho[f]));
+    return acc;
+  }
+  // -1 if this tet owns x, else a face through which x lies on the far side (the walk crosses it)
+  TB_HD int locate(const float *x) const
+  {
+    for (int f = 0; f < 4; f++) {
+      float sp = face_det(f, x);
+      if (sp == 0.0f) { if (!(sd[f] > 0.0f)) return f; }
+      else if ((sp > 0.0f) != (sd[f] > 0.0f)) return f;
+    }
+    return -1;
+  }
   // value at x if this tet owns x: for every face the point is on the opposite vertex's side, a point
   // exactly on a face belonging to the tet on the face's positive side
   TB_HD bool eval(const float *x, float *val) const
