@@ -129,7 +129,7 @@ struct BlockRes
   int num_orig = 0, num_particles = 0, num_tets = 0;
   float bmin[3], bmax[3];
   bool have_v2t = false;
-  Buf particles, tets, v2t, cc, rho;
+  Buf particles, tets, v2t, cc, rho, walk;
   // geometry of the last run
   int mn[3], num[3];
   long long npts = 0, nrows = 0, row_base = 0, out_off = 0;
@@ -206,7 +206,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
 static void free_blocks(tessb200_ctx *c)
 {
   for (BlockRes *b : c->blocks) {
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release();
     delete b;
   }
   c->blocks.clear();
@@ -393,7 +393,7 @@ static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *block
     if (blocks[order[i]].gid == blocks[order[i - 1]].gid) return fail(TESSB200_EINVAL, "duplicate gid %d", blocks[order[i]].gid);
   while ((int)c->blocks.size() > nblocks) {
     BlockRes *b = c->blocks.back();
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release();
     delete b;
     c->blocks.pop_back();
   }
@@ -438,6 +438,7 @@ static DevBlock dev_block(const BlockRes *b)
   d.tets = (const int4 *)b->tets.p;
   d.v2t = (const int *)b->v2t.p;
   d.cc = (const float4 *)b->cc.p;
+  d.walk = (const WalkRec *)b->walk.p;
   d.num_orig = b->num_orig; d.num_particles = b->num_particles; d.num_tets = b->num_tets;
   d.cell_base = b->cell_base;
   d.order = nullptr;
@@ -448,8 +449,9 @@ static DevBlock dev_block(const BlockRes *b)
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
-static int prep_block_geometry(tessb200_ctx *c, BlockRes *b)
+static int prep_block_geometry(tessb200_ctx *c, BlockRes *b, bool want_walk = false)
 {
+  if (want_walk && b->num_tets) TRY(b->walk.ensure(sizeof(WalkRec) * (size_t)b->num_tets));
   // vert_to_tet (if not given) and circumcenters for one resident block
   if (!b->have_v2t && b->num_particles) {
     k_fill_i32<<<cdiv(b->num_particles, 256), 256, 0, c->stream>>>((int *)b->v2t.p, b->num_particles, -1);
@@ -457,7 +459,8 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b)
     if (b->num_tets) { k_vert_to_tet<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (int *)b->v2t.p); COUNT_LAUNCH(c, 1); }
   }
   if (b->num_tets) {
-    k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, (float4 *)b->cc.p);
+    k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, (float4 *)b->cc.p,
+                                                                want_walk ? (WalkRec *)b->walk.p : nullptr);
     COUNT_LAUNCH(c, 1);
   }
   CU(cudaGetLastError());
@@ -689,6 +692,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       for (int k = groups[gi].first; k < groups[gi].second; k++) {
         BlockRes *b = c->blocks[k];
         DevBlock &d = hblocks[first_local_all + k];
+        if (tess && b->num_tets) TRY(b->walk.ensure(sizeof(WalkRec) * (size_t)b->num_tets));
         d = dev_block(b);
         d.order = c->order[1].as<uint32_t>() + order_off;
         order_off += b->num_orig;
@@ -771,7 +775,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       continue;
     }
     // K0 / K1 / processing order
-    for (int k = k0; k < k1; k++) TRY(prep_block_geometry(c, c->blocks[k]));
+    for (int k = k0; k < k1; k++) TRY(prep_block_geometry(c, c->blocks[k], true));
     TRY(prep_cell_order(c, k0, k1, cell_off));
     cell_off += gcells;
     if (timed) CU(cudaEventRecord(c->ev[4], s));
@@ -1057,7 +1061,7 @@ extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nbl
 struct TmpBlock
 {
   BlockRes b;
-  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.rho.release(); }
+  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.rho.release(); b.walk.release(); }
 };
 
 static int upload_tmp(tessb200_ctx *c, TmpBlock &t, int num_particles, const float *particles, int num_tets, const int *tets, const int *v2t)
@@ -1100,7 +1104,7 @@ extern "C" int tessb200_circumcenters(tessb200_ctx *c, int num_particles, const 
   TmpBlock t;
   TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, nullptr));
   if (num_tets) {
-    k_circumcenters<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (const float *)t.b.particles.p, (float4 *)t.b.cc.p);
+    k_circumcenters<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (const float *)t.b.particles.p, (float4 *)t.b.cc.p, nullptr);
     CU(cudaGetLastError());
     // float4 -> packed xyz on the way out (the reference's std::vector<float> layout, volume.cpp:8)
     CU(cudaMemcpy2DAsync(out, 12, t.b.cc.p, 16, 12, (size_t)num_tets, cudaMemcpyDeviceToHost, c->stream));

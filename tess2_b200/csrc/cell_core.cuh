@@ -419,8 +419,11 @@ TB_HD int vis_find_or_insert(WS &ws, int key, int *count, int cap)
     const uint32_t w = ws.vis_word(h);
     const unsigned i0 = w & 0xFFu, i1 = (w >> 8) & 0xFFu, i2 = (w >> 16) & 0xFFu, i3 = w >> 24;
     // entries are filled from byte 0 up, so an empty byte ends the bucket
-    const bool hit = (i0 != 0xFFu && ws.star((int)i0) == key) || (i1 != 0xFFu && ws.star((int)i1) == key) ||
-                     (i2 != 0xFFu && ws.star((int)i2) == key) || (i3 != 0xFFu && ws.star((int)i3) == key);
+    // branch-free: the four list entries are loaded unconditionally (an empty byte reads entry 0 and
+    // is masked out), so the lanes of a warp do not split on how full their buckets are
+    const int e0 = ws.star(i0 == 0xFFu ? 0 : (int)i0), e1 = ws.star(i1 == 0xFFu ? 0 : (int)i1);
+    const int e2 = ws.star(i2 == 0xFFu ? 0 : (int)i2), e3 = ws.star(i3 == 0xFFu ? 0 : (int)i3);
+    const bool hit = ((i0 != 0xFFu) & (e0 == key)) | ((i1 != 0xFFu) & (e1 == key)) | ((i2 != 0xFFu) & (e2 == key)) | ((i3 != 0xFFu) & (e3 == key));
     if (hit) return 0;
     if (i3 == 0xFFu) {
       if (*count >= cap) return -1;
@@ -518,8 +521,9 @@ TB_HD int nbr_insert(WS &ws, int u, int t, int *nn, int nbr_cap)
   for (int guard = 0; guard < TB_NBR_BUCKETS; guard++) {
     const uint32_t w = ws.nbr_word(h);
     const unsigned i0 = w & 0xFFu, i1 = (w >> 8) & 0xFFu, i2 = (w >> 16) & 0xFFu, i3 = w >> 24;
-    const bool hit = (i0 != 0xFFu && ws.nu((int)i0) == u) || (i1 != 0xFFu && ws.nu((int)i1) == u) ||
-                     (i2 != 0xFFu && ws.nu((int)i2) == u) || (i3 != 0xFFu && ws.nu((int)i3) == u);
+    const int e0 = ws.nu(i0 == 0xFFu ? 0 : (int)i0), e1 = ws.nu(i1 == 0xFFu ? 0 : (int)i1);
+    const int e2 = ws.nu(i2 == 0xFFu ? 0 : (int)i2), e3 = ws.nu(i3 == 0xFFu ? 0 : (int)i3);
+    const bool hit = ((i0 != 0xFFu) & (e0 == u)) | ((i1 != 0xFFu) & (e1 == u)) | ((i2 != 0xFFu) & (e2 == u)) | ((i3 != 0xFFu) & (e3 == u));
     if (hit) return 0;
     if (i3 == 0xFFu) {
       if (*nn >= nbr_cap) return -1;
@@ -583,6 +587,62 @@ TB_HD int walk_edge_link(int site, int u, int ut, const int4 *tets, const float4
     v = tets[2 * (size_t)next_t];
     nb = tets[2 * (size_t)next_t + 1];
     wi = (v.x == nv) ? 0 : (v.y == nv) ? 1 : (v.z == nv) ? 2 : 3;
+    t = next_t;
+  }
+  return -1;
+}
+
+// ---- the same circulation on 32-byte walk records ----------------------------------------------------
+// WalkRec packs what one circulation step needs into ONE 32-byte sector: the tet's four neighbours,
+// its circumcenter and a permutation word: for face i and slot j != i, bits [(4i+j)*2, +2) hold the
+// slot that vertex verts[j] occupies in the neighbour across face i.  The walk then tracks the slots
+// of the site and of u instead of comparing vertex ids, and never reads a vertex list after the
+// first tet.  Same tets in the same order as walk_edge_link (checked in tests/emul).
+struct
+#if defined(__CUDACC__)
+    __align__(16)
+#endif
+    WalkRec
+{
+  int nb[4];
+  float cx, cy, cz;
+  uint32_t perm;
+};
+
+TB_HD uint32_t walk_perm(const int *verts, const int *nbrs, const int4 *tets)
+{
+  uint32_t p = 0;
+  for (int i = 0; i < 4; i++) {
+    if (nbrs[i] < 0) continue;
+    const int4 nv = tets[2 * (size_t)nbrs[i]];
+    for (int j = 0; j < 4; j++) {
+      if (j == i) continue;
+      const int v = verts[j];
+      const uint32_t s = nv.x == v ? 0u : (nv.y == v ? 1u : (nv.z == v ? 2u : 3u));
+      p |= s << ((4 * i + j) * 2);
+    }
+  }
+  return p;
+}
+
+template <class Visit>
+TB_HD int walk_edge_link_rec(int s_c, int s_u, int ut, const WalkRec *walk, Visit &visit)
+{
+  // circulate_start: the first slot holding neither the site nor u
+  int wi = 0;
+  while (wi == s_c || wi == s_u) wi++;
+  int t = ut;
+  for (int k = 0; k < TB_MAX_LINK; k++) {
+    const WalkRec r = walk[t];
+    float4 c;
+    c.x = r.cx; c.y = r.cy; c.z = r.cz; c.w = 0.0f;
+    visit(k, c);
+    const int nvs = 6 - s_c - s_u - wi;                        // slot of the fourth vertex
+    const int next_t = wi == 0 ? r.nb[0] : (wi == 1 ? r.nb[1] : (wi == 2 ? r.nb[2] : r.nb[3]));
+    if (next_t == ut || next_t < 0) return k + 1;
+    const uint32_t p = r.perm >> (8 * wi);                      // the 4 x 2 bits of face wi
+    const int n_c = (int)((p >> (2 * s_c)) & 3u), n_u = (int)((p >> (2 * s_u)) & 3u), n_w = (int)((p >> (2 * nvs)) & 3u);
+    s_c = n_c; s_u = n_u; wi = n_w;
     t = next_t;
   }
   return -1;

@@ -29,7 +29,8 @@ struct DevBlock
   const float *particles;  // xyz AoS
   const int4 *tets;        // 2 x int4 per tet: verts, neighbours
   const int *v2t;
-  const float4 *cc;        // circumcenter per tet (w unused)
+  const float4 *cc;        // circumcenter per tet, w = tet volume
+  const WalkRec *walk;     // 32-byte circulation record per tet (neighbours, circumcenter, slot permutation)
   int num_orig, num_particles, num_tets;
   uint32_t cell_base;      // global number of this block's cell 0 (blocks in ascending gid order)
   const uint32_t *order;   // cells of the block in Morton order of their sites (processing order only)
@@ -149,7 +150,7 @@ __global__ void k_vert_to_tet(const int4 *__restrict__ tets, int num_tets, int *
 // ---- K1: circumcenters, one thread per tet ---------------------------------------------------------
 // reads 16 B of the tet record (verts only) + 4 gathered particles, writes one float4 (x, y, z, volume)
 __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ tets, int num_tets,
-                                                        const float *__restrict__ particles, float4 *__restrict__ cc)
+                                                        const float *__restrict__ particles, float4 *__restrict__ cc, WalkRec *__restrict__ walk)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tets) return;
@@ -165,6 +166,15 @@ __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ 
   float det;
   circumcenter(a, b, c, d, o, &det);
   cc[t] = make_float4(o[0], o[1], o[2], fdiv(fabsf(det), 6.0f));   // w = tet volume (used by the DTFE mode)
+  if (walk) {
+    const int4 nb = __ldg(&tets[2 * (size_t)t + 1]);
+    const int vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {nb.x, nb.y, nb.z, nb.w};
+    WalkRec r;
+    r.nb[0] = nb.x; r.nb[1] = nb.y; r.nb[2] = nb.z; r.nb[3] = nb.w;
+    r.cx = o[0]; r.cy = o[1]; r.cz = o[2];
+    r.perm = walk_perm(vv, nn, tets);
+    walk[t] = r;
+  }
 }
 
 // ---- K3a part 1: topology + faces, one thread per cell --------------------------------------------
@@ -542,7 +552,11 @@ __global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ 
   const float site[3] = {b.particles[3 * (size_t)r.site], b.particles[3 * (size_t)r.site + 1], b.particles[3 * (size_t)r.site + 2]};
   FaceAccum fa;
   fa.cmin = nullptr; fa.cmax = nullptr;
-  const int n = walk_edge_link(r.site, r.u, r.ut, b.tets, b.cc, fa);
+  // slots of the site and of u in the first tet; from there on the walk follows slot permutations
+  const int4 v0 = b.tets[2 * (size_t)r.ut];
+  const int s_c = v0.x == r.site ? 0 : (v0.y == r.site ? 1 : (v0.z == r.site ? 2 : 3));
+  const int s_u = v0.x == r.u ? 0 : (v0.y == r.u ? 1 : (v0.z == r.u ? 2 : 3));
+  const int n = walk_edge_link_rec(s_c, s_u, r.ut, b.walk, fa);
   float2 *dst = reinterpret_cast<float2 *>(plane_pool + f * 6);
   if (n < 0) {
     // the link did not close (malformed mesh): a NaN plane is never significant in PtInCell

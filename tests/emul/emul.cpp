@@ -411,6 +411,14 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
       continue;
     }
     std::vector<float4> cc = make_cc(b.num_tets, b.tets, b.particles);
+    std::vector<WalkRec> walk(b.num_tets);
+    for (int t = 0; t < b.num_tets; t++) {
+      WalkRec r;
+      for (int q = 0; q < 4; q++) r.nb[q] = b.tets[8 * t + 4 + q];
+      r.cx = cc[t].x; r.cy = cc[t].y; r.cz = cc[t].z;
+      r.perm = walk_perm(&b.tets[8 * t], &b.tets[8 * t + 4], (const int4 *)b.tets);
+      walk[t] = r;
+    }
     for (int cell = 0; cell < b.num_orig_particles; cell++) {
       if (v2t[cell] < 0) continue;
       int st = tp.run(cell, v2t[cell], (const int4 *)b.tets, cc.data());
@@ -425,6 +433,19 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
         fa.cmin = cmin; fa.cmax = cmax;
         int n = walk_edge_link(cell, tp.nu(k), tp.nt(k), (const int4 *)b.tets, cc.data(), fa);
         if (n < 0) { bad = true; break; }
+        {
+          // k_cell_faces' walk on the 32-byte records (slot permutations) must visit the same tets
+          FaceAccum fb;
+          fb.cmin = nullptr; fb.cmax = nullptr;
+          const int *v0 = &b.tets[8 * tp.nt(k)];
+          int s_c = -1, s_u = -1;
+          for (int q = 0; q < 4; q++) { if (v0[q] == cell) s_c = q; if (v0[q] == tp.nu(k)) s_u = q; }
+          int n2 = walk_edge_link_rec(s_c, s_u, tp.nt(k), walk.data(), fb);
+          if (n2 != n || memcmp(fa.nrm, fb.nrm, 12) || memcmp(fa.v0, fb.v0, 12) || memcmp(fa.prev, fb.prev, 12)) {
+            fprintf(stderr, "emul: record walk differs from vertex walk (%d vs %d steps)\n", n2, n);
+            abort();
+          }
+        }
         newell_term(fa.nrm, fa.prev, fa.v0);
         newell_finish(fa.nrm, fa.v0, site);
         for (int d = 0; d < 3; d++) { planes[6 * k + d] = fa.nrm[d]; planes[6 * k + 3 + d] = fa.v0[d]; }
