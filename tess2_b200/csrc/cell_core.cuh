@@ -297,109 +297,14 @@ TB_HD int tb_ffs(uint32_t x)
 #endif
 }
 
-// The BFS of k_cell_bfs: same order and same (u, first tet) pairs as star_and_neighbors_hashed,
-// restructured so that every popped tet runs the SAME three table operations (one vertex, two
-// tets) -- the lanes of a warp stay converged -- and the cell's bounding box is accumulated on
-// the way: the vertices of all Voronoi faces of the cell are exactly the circumcenters of the
-// star's tets, so min/max over the star equals the face loop of CellBounds (src/dense.cpp:700-714).
-// A star that is not a manifold around `site` (no slot leads back to the BFS parent) is reported
-// as CELL_OVERFLOW, which reroutes the cell to the general (linear-search) kernel.
 TB_HD int tb_sel4(int a, int b, int c, int d, int s) { return s == 0 ? a : (s == 1 ? b : (s == 2 ? c : d)); }
-
-template <class WS>
-TB_HD int star_bfs_uniform(int site, int t0, const int4 *tets, const float4 *cc, WS &ws, int star_cap, int nbr_cap,
-                           int *n_star, int *n_nbr, float *cmin, float *cmax)
-{
-  ws.hash_clear();
-  int ns = 0, nn = 0;
-  hash_find_or_insert(ws, false, t0, &ns, star_cap);
-  {
-    // root: its three non-site vertices are new, its three neighbours are pushed in slot order
-    int4 v = tets[2 * (size_t)t0];
-    int4 nb = tets[2 * (size_t)t0 + 1];
-    float4 c = cc[t0];
-    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
-    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
-    int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
-    if (is < 0) return CELL_OVERFLOW;
-    for (int q = 0; q < 3; q++) {
-      int s = q + (q >= is ? 1 : 0);
-      int u = tb_sel4(v.x, v.y, v.z, v.w, s);
-      int next = tb_sel4(nb.x, nb.y, nb.z, nb.w, s);
-      int before = nn;
-      int r = hash_find_or_insert(ws, true, u, &nn, nbr_cap);
-      if (r < 0) return CELL_OVERFLOW;
-      if (r > 0) ws.nt_idx(before) = 0;
-      if (next < 0) return CELL_INCOMPLETE;
-      int before_s = ns;
-      int r2 = hash_find_or_insert(ws, false, next, &ns, star_cap);
-      if (r2 < 0) return CELL_OVERFLOW;
-      if (r2 > 0) ws.parent_idx(before_s) = 0;
-    }
-  }
-  // software pipelining: the record of the next tet in the queue is requested before the table
-  // operations of the current one, so its latency overlaps them
-  int4 v_n = {0, 0, 0, 0}, nb_n = {0, 0, 0, 0};
-  float4 c_n = {0, 0, 0, 0};
-  bool have_n = false;
-  if (ns > 1) {
-    int t1 = ws.star(1);
-    v_n = tets[2 * (size_t)t1]; nb_n = tets[2 * (size_t)t1 + 1]; c_n = cc[t1];
-    have_n = true;
-  }
-  for (int head = 1; head < ns; head++) {
-    int4 v, nb;
-    float4 c;
-    if (have_n) { v = v_n; nb = nb_n; c = c_n; }
-    else {
-      int t = ws.star(head);
-      v = tets[2 * (size_t)t]; nb = tets[2 * (size_t)t + 1]; c = cc[t];
-    }
-    have_n = head + 1 < ns;
-    if (have_n) {
-      int t1 = ws.star(head + 1);
-      v_n = tets[2 * (size_t)t1]; nb_n = tets[2 * (size_t)t1 + 1]; c_n = cc[t1];
-    }
-    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
-    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
-    const int par = ws.star((int)ws.parent_idx(head));
-    const int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
-    const int ip = nb.x == par ? 0 : (nb.y == par ? 1 : (nb.z == par ? 2 : (nb.w == par ? 3 : -1)));
-    if (is < 0 || ip < 0 || is == ip) return CELL_OVERFLOW;
-    // the only vertex that can be new: the one opposite the face shared with the parent
-    {
-      int u = tb_sel4(v.x, v.y, v.z, v.w, ip);
-      int before = nn;
-      int r = hash_find_or_insert(ws, true, u, &nn, nbr_cap);
-      if (r < 0) return CELL_OVERFLOW;
-      if (r > 0) ws.nt_idx(before) = (unsigned char)head;
-    }
-    // the two other neighbours, in slot order
-    unsigned m = 0xFu & ~(1u << is) & ~(1u << ip);
-    const int s1 = tb_ffs(m) - 1;
-    m &= m - 1u;
-    const int s2 = tb_ffs(m) - 1;
-    const int n1 = tb_sel4(nb.x, nb.y, nb.z, nb.w, s1), n2 = tb_sel4(nb.x, nb.y, nb.z, nb.w, s2);
-    if (n1 < 0 || n2 < 0) return CELL_INCOMPLETE;
-    {
-      int before_s = ns;
-      int r = hash_find_or_insert(ws, false, n1, &ns, star_cap);
-      if (r < 0) return CELL_OVERFLOW;
-      if (r > 0) ws.parent_idx(before_s) = (unsigned char)head;
-      before_s = ns;
-      r = hash_find_or_insert(ws, false, n2, &ns, star_cap);
-      if (r < 0) return CELL_OVERFLOW;
-      if (r > 0) ws.parent_idx(before_s) = (unsigned char)head;
-    }
-  }
-  *n_star = ns;
-  *n_nbr = nn;
-  return CELL_OK;
-}
 
 // The star walk split in two (k_cell_bfs + k_cell_nbrs): the BFS keeps only the visited set and hands
 // every CANDIDATE new neighbour to `sink(k, u, t)` in BFS order -- the root's three vertices, then per
-// popped tet the vertex opposite its parent face (the only one that can be new, see above).  A second
+// popped tet the vertex opposite its parent face (the only one that can be new: the other vertices of
+// the popped tet belong to the parent, which was popped earlier).  A star that is not a manifold around
+// `site` (no slot leads back to the BFS parent) is reported as CELL_OVERFLOW, which reroutes the cell
+// to the general (linear-search) kernel.  A second
 // pass (nbrs_from_cands) drops the candidates that were seen before; what remains is neighbor_edges'
 // list of (u, first tet holding u).  ws needs star(), parent_idx(), vis_hash(), hash_clear_vis().
 // Bucketized byte tables: a bucket is one 32-bit word holding four list indices (0xFF = empty, filled
