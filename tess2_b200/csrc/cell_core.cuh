@@ -940,9 +940,33 @@ struct BlockBox
 // whose position lies in the emitting block's closed bounds is local, otherwise it goes to every
 // other block whose closed bounds contain it; in both cases only indices inside the target's
 // sub-grid are kept (the reference writes out of bounds there).
+// The blocks other than e that can receive points of the index box [lo, lo + n3): at most `cap`
+// indices into `boxes` are written to `cand`; returns their number, or -1 if there are more than cap
+// (the caller then lets emit_line scan all blocks).  With many blocks this keeps the per-line loop of
+// boundary cells short (64 blocks: 8 GPUs x 8).
+TB_HD int candidate_blocks(const BlockBox *boxes, int nblocks, int e, const int *lo, const int *n3, int project, int *cand, int cap)
+{
+  int n = 0;
+  for (int j = 0; j < nblocks; j++) {
+    if (j == e) continue;
+    const BlockBox &b = boxes[j];
+    bool hit = true;
+    for (int d = 0; d < 3; d++) {
+      const int hi = lo[d] + n3[d] - 1;
+      if (hi < b.p_lo[d] || lo[d] > b.p_hi[d]) hit = false;
+      if (!(project && d == 2) && (hi < b.b_lo[d] || lo[d] > b.b_lo[d] + b.b_num[d] - 1)) hit = false;
+    }
+    if (!hit) continue;
+    if (n >= cap) return -1;
+    cand[n++] = j;
+  }
+  return n;
+}
+
 template <class Emit>
 TB_HD void emit_line(const BlockBox *boxes, int nblocks, int e, const KeyLayout &kl, int project, uint32_t cell,
-                     int xa, int xb, int y, int z, int float_path_local, float value, Emit &emit)
+                     int xa, int xb, int y, int z, int float_path_local, float value, Emit &emit,
+                     const int *cand = nullptr, int ncand = -1)
 {
   const BlockBox &be = boxes[e];
   bool yz_local = y >= be.p_lo[1] && y <= be.p_hi[1] && z >= be.p_lo[2] && z <= be.p_hi[2];
@@ -965,7 +989,9 @@ TB_HD void emit_line(const BlockBox *boxes, int nblocks, int e, const KeyLayout 
   }
   if (la <= lb && la == xa && lb == xb) return; // whole line was local
   // remote parts: the pieces of [xa, xb] outside [la, lb] (all of it when the line is not local)
-  for (int j = 0; j < nblocks; j++) {
+  const int nloop = ncand >= 0 ? ncand : nblocks;
+  for (int q = 0; q < nloop; q++) {
+    const int j = ncand >= 0 ? cand[q] : q;
     if (j == e) continue;
     const BlockBox &bj = boxes[j];
     if (y < bj.p_lo[1] || y > bj.p_hi[1] || z < bj.p_lo[2] || z > bj.p_hi[2]) continue;

@@ -621,6 +621,12 @@ struct LineEmitter
   float value;
   Emit &emit;
   int tot;
+  int cand[8];       // blocks other than e that the cell's index box can reach (boundary cells)
+  int ncand;         // -1: not computed / more than 8 -> emit_line scans every block
+  __device__ __forceinline__ void find_candidates(const int *n3)
+  {
+    ncand = local_box ? 0 : candidate_blocks(sc.boxes, sc.nblocks, e, lo, n3, sc.project, cand, 8);
+  }
   __device__ __forceinline__ void operator()(int yi, int zi, int min_xi, int max_xi)
   {
     int y = lo[1] + yi, z = lo[2] + zi, xa = lo[0] + min_xi, xb = lo[0] + max_xi;
@@ -630,7 +636,7 @@ struct LineEmitter
       uint64_t row = (uint64_t)(b.row_base + (sc.project ? (long long)ly : (long long)lz * b.b_num[1] + ly));
       emit(make_key(sc.kl, row, 0, cell, sc.project ? (uint32_t)z : 0u), make_data(xa - b.b_lo[0], xb - xa + 1, 0, value));
     } else {
-      emit_line(sc.boxes, sc.nblocks, e, sc.kl, sc.project, cell, xa, xb, y, z, 0, value, emit);
+      emit_line(sc.boxes, sc.nblocks, e, sc.kl, sc.project, cell, xa, xb, y, z, 0, value, emit, cand, ncand);
     }
   }
 };
@@ -875,7 +881,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
           if (nlines <= SCAN_LINE_CAP && local_box) nrec = nlines;
           else if (nlines <= SCAN_LINE_CAP) {
             CountEmit ce{0};
-            LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
+            LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0, {0, 0, 0, 0, 0, 0, 0, 0}, -1};
+            le.find_candidates(n3);
             for (int q = 0; q < nlines; q++) {
               uint32_t pk = lines_w[q * 32 + lane];
               le((int)(pk & 2047u), (int)((pk >> 11) & 2047u), (int)((pk >> 22) & 31u), (int)(pk >> 27));
@@ -883,13 +890,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
             nrec = ce.n;
           } else {
             CountEmit ce{0};
-            LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
+            LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0, {0, 0, 0, 0, 0, 0, 0, 0}, -1};
+            le.find_candidates(n3);
             scan_cell_bits(nx, ny, nz, row, le);
             nrec = ce.n;
           }
         } else {
           CountEmit ce{0};
-          LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
+          LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0, {0, 0, 0, 0, 0, 0, 0, 0}, -1};
+          le.find_candidates(n3);
           tot = scan_cell(nx, ny, nz, inside, le);
           nrec = ce.n;
         }
@@ -910,7 +919,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
         StoreEmit se{out.keys, out.data, base, out.capacity};
         if (tot > 0) {
           float m = fdiv(g.mass, (float)tot); // src/dense.cpp:1692
-          LineEmitter<StoreEmit> le{sc, e, h.cell, h.lo, local_box, m, se, 0};
+          LineEmitter<StoreEmit> le{sc, e, h.cell, h.lo, local_box, m, se, 0, {0, 0, 0, 0, 0, 0, 0, 0}, -1};
+          const int n3e[3] = {nx, ny, nz};
+          le.find_candidates(n3e);
           if (bitpath && nlines <= SCAN_LINE_CAP) {
             for (int q = 0; q < nlines; q++) {
               uint32_t pk = lines_w[q * 32 + lane];
@@ -988,7 +999,8 @@ __global__ void __launch_bounds__(128) k_cell_scan_big(const CellHdr *__restrict
     bool local_box = box_is_local(sc.boxes[e], lo, n3, sc.project);
     GlobalPlanesInsideBits inside{bits, nx, ny};
     CountEmit ce{0};
-    LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0};
+    LineEmitter<CountEmit> le{sc, e, h.cell, h.lo, local_box, 0.0f, ce, 0, {0, 0, 0, 0, 0, 0, 0, 0}, -1};
+    le.find_candidates(n3);
     int tot = scan_cell(nx, ny, nz, inside, le);
     int nrec = ce.n;
     float site[3] = {0, 0, 0};
@@ -1006,7 +1018,8 @@ __global__ void __launch_bounds__(128) k_cell_scan_big(const CellHdr *__restrict
     StoreEmit se{out.keys, out.data, pos0, out.capacity};
     if (tot > 0) {
       float m = fdiv(g.mass, (float)tot);
-      LineEmitter<StoreEmit> le2{sc, e, h.cell, h.lo, local_box, m, se, 0};
+      LineEmitter<StoreEmit> le2{sc, e, h.cell, h.lo, local_box, m, se, 0, {0, 0, 0, 0, 0, 0, 0, 0}, -1};
+      le2.find_candidates(n3);
       scan_cell(nx, ny, nz, inside, le2);
     } else {
       emit_cic(sc, e, h.cell, site, g, 0, se);
