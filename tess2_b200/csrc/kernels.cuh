@@ -834,7 +834,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
       }
       // probe position: cell_min_grid_pos + i * step with cell_min_grid_pos = idx2phys(lo)  (src/dense.cpp:1404,1530-1532)
       const float bx = idx2phys1(lx, g.step[0], g.gmin[0]), by = idx2phys1(ly, g.step[1], g.gmin[1]), bz = idx2phys1(lz, g.step[2], g.gmin[2]);
-      const float inv_nx = 1.0f / (float)nx, inv_ny = 1.0f / (float)ny;
+      const float inv_nx = __fdividef(1.0f, (float)nx), inv_ny = __fdividef(1.0f, (float)ny);   // approximate is enough: divmod_small fixes +-1
       for (int l0 = 0; l0 < np; l0 += 32) {
         const int l = l0 + lane;
         const bool valid = l < np;
@@ -846,15 +846,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__res
         // dist < -eps.  Tracked as running max / min of dist (NaN never counts, as in the reference).
         float dmax = -INFINITY, dmin = INFINITY;
         const float neg_eps = -g.eps;
-#pragma unroll 4
-        for (int f = 0; f < cnf; f++) {
+        auto plane_test = [&](int f) {
           const float2 *p = reinterpret_cast<const float2 *>(pl + 6 * f);
           const float2 a = p[0], b = p[1], cc2 = p[2];
           const float dist = fadd(fadd(fmul(a.x, fsub(pt[0], b.y)), fmul(a.y, fsub(pt[1], cc2.x))), fmul(b.x, fsub(pt[2], cc2.y)));
           dmax = fmaxf(dmax, dist);
           dmin = fminf(dmin, dist);
-          if ((f & 3) == 3 && __all_sync(0xffffffffu, !valid || (dmax > g.eps && dmin < neg_eps))) break;
+        };
+        // groups of four faces without per-face loop tests; after each group the warp leaves early
+        // when every point is already outside (a step with no inside point: most steps past the first)
+        int f = 0;
+        const int cnf4 = cnf & ~3;
+        while (f < cnf4) {
+          plane_test(f); plane_test(f + 1); plane_test(f + 2); plane_test(f + 3);
+          f += 4;
+          if (__all_sync(0xffffffffu, !valid || (dmax > g.eps && dmin < neg_eps))) f = 1 << 20;
         }
+        for (; f < cnf; f++) plane_test(f);
         const unsigned w = __ballot_sync(0xffffffffu, valid && !(dmax > g.eps && dmin < neg_eps));
         if (lane == 0) bits_w[wbase + (l0 >> 5)] = w;
       }
@@ -1075,6 +1083,7 @@ struct RowBlock
 };
 
 constexpr int ROWS_WARPS = 4;
+constexpr int ROWS_SHORT_SPAN = 16;   // spans up to this length are applied one record per lane
 
 __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__restrict__ data, const unsigned long long *__restrict__ row_start,
                                                           unsigned long long row0, unsigned long long r_begin, unsigned long long nrows, const RowBlock *__restrict__ rblocks,
@@ -1107,6 +1116,35 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__rest
     const int my_fp = (int)((mine >> 31) & 1u);
     const double my_q = my_fp ? (double)fdiv(my_m, div) : (double)my_m / (double)div;
     int cnt = (int)(s1 - sb < 32 ? s1 - sb : 32);
+    const unsigned my_lo = (unsigned)mine;
+    const int my_x0 = (int)(my_lo & 0xffffu);
+    const int my_len = lane < cnt ? (int)((my_lo >> 16) & 0x7fffu) : 0;
+    if (__all_sync(0xffffffffu, my_len <= ROWS_SHORT_SPAN)) {
+      // short spans (the common case: a cell covers a few points of a row): one record per lane.
+      // Only records that share a grid point need the sorted order, so each lane collects the
+      // earlier records of the batch its span overlaps and waits for exactly those.
+      const int my_x1 = my_x0 + my_len;              // empty spans overlap nothing
+      unsigned dep = 0;
+#pragma unroll
+      for (int d = 1; d < 32; d++) {
+        const int o0 = __shfl_up_sync(0xffffffffu, my_x0, d), o1 = __shfl_up_sync(0xffffffffu, my_x1, d);
+        if (lane >= d && o0 < my_x1 && my_x0 < o1) dep |= 1u << (lane - d);
+      }
+      unsigned done = __ballot_sync(0xffffffffu, my_len == 0);
+      const int my_fpath = (int)(my_lo >> 31);
+      while (done != 0xffffffffu) {
+        const bool ready = !((done >> lane) & 1u) && (dep & ~done) == 0u;
+        if (ready) {
+          for (int x = 0; x < my_len; x++) {
+            const int xx = my_x0 + x;
+            if (xx < nx) buf[xx] = my_fpath ? fadd(buf[xx], (float)my_q) : (float)((double)buf[xx] + my_q);
+          }
+        }
+        __syncwarp();
+        done |= __ballot_sync(0xffffffffu, ready);
+      }
+      continue;
+    }
     for (int j = 0; j < cnt; j++) {
       const unsigned lo32 = __shfl_sync(0xffffffffu, (unsigned)mine, j);
       const double q = __shfl_sync(0xffffffffu, my_q, j);
