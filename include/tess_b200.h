@@ -119,6 +119,8 @@ typedef struct tessb200_dense_stats
   float ms_bfs, ms_nbrs, ms_faces; /* the three kernels inside ms_cells (resident runs only) */
   int64_t num_faces;          /* Voronoi faces of the depositing cells (plane records) */
   int64_t num_candidates;     /* candidate neighbours handed from k_cell_bfs to k_cell_nbrs */
+  float ms_slow_path;         /* general BFS for oversized stars + per-CTA scan of oversized cells (after the fast kernels) */
+  float reserved0;
 } tessb200_dense_stats;
 
 typedef struct tessb200_ctx tessb200_ctx;

@@ -30,7 +30,8 @@ params = ctx.make_params(0, 0, None, None, False, (0, 0, 1), 1.0, 1e-4, gs)
 ctx.upload(blocks)
 for _ in range(3):
     st = ctx.run(params)
-out = {k: getattr(st, k) for k in ("num_cells", "num_deposit_cells", "num_cic_fallback", "num_slow_cells", "num_spans", "num_incomplete", "num_outside",
-                                   "ms_circumcenters", "ms_cells", "ms_scan", "ms_sort", "ms_deposit", "ms_total_device", "tot_mass")}
+out = {k: getattr(st, k) for k in ("num_cells", "num_tets", "num_deposit_cells", "num_cic_fallback", "num_slow_cells", "num_spans", "num_faces",
+                                   "num_incomplete", "num_outside", "ms_circumcenters", "ms_bfs", "ms_nbrs", "ms_faces", "ms_cells", "ms_scan",
+                                   "ms_sort", "ms_deposit", "ms_total_device", "tot_mass")}
 out["grid_points_per_sec"] = gs[0] ** 3 / (st.ms_total_device * 1e-3)
 print(json.dumps(out))

@@ -129,7 +129,7 @@ struct BlockRes
   int num_orig = 0, num_particles = 0, num_tets = 0;
   float bmin[3], bmax[3];
   bool have_v2t = false;
-  Buf particles, tets, v2t, cc, rho, walk;
+  Buf particles, tets, v2t, cc, rho, walk, hull;
   // geometry of the last run
   int mn[3], num[3];
   long long npts = 0, nrows = 0, row_base = 0, out_off = 0;
@@ -149,6 +149,12 @@ struct tessb200_ctx
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t blk_ev[64];
+  cudaEvent_t grp_ev[64];   // end of each group's cell kernels (TESSB200_TRACE)
+  cudaEvent_t part_ev = nullptr;
+  std::vector<cudaEvent_t> tr_ev;          // TESSB200_TRACE: fine-grained marks inside the groups
+  std::vector<const char *> tr_name;
+  size_t tr_used = 0;
+  bool tracing = false;
   std::vector<cudaEvent_t> h2d_ev;
   std::vector<BlockRes *> blocks;   // uploaded blocks of this rank, ascending gid
   std::vector<LayoutBlock> layout;  // every block of the decomposition (multi-GPU), ascending gid
@@ -189,7 +195,9 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   c->device = device;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  for (auto &ev : c->blk_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &ev : c->blk_ev) CU(cudaEventCreate(&ev));
+  for (auto &ev : c->grp_ev) CU(cudaEventCreate(&ev));
+  CU(cudaEventCreateWithFlags(&c->part_ev, cudaEventDisableTiming));
   CU(cudaMallocHost(&c->h_cnt, sizeof(Counters)));
   CU(cudaMallocHost(&c->h_sum, sizeof(double) * 1024));
   CU(cudaMallocHost(&c->h_max, sizeof(float) * 1024));
@@ -206,7 +214,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
 static void free_blocks(tessb200_ctx *c)
 {
   for (BlockRes *b : c->blocks) {
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release(); b->hull.release();
     delete b;
   }
   c->blocks.clear();
@@ -228,6 +236,8 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   cudaFreeHost(c->h_cnt); cudaFreeHost(c->h_sum); cudaFreeHost(c->h_max);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->blk_ev) cudaEventDestroy(ev);
+  for (auto &ev : c->grp_ev) cudaEventDestroy(ev);
+  if (c->part_ev) cudaEventDestroy(c->part_ev);
   for (auto &ev : c->h2d_ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
@@ -382,7 +392,7 @@ static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *block
   CU(cudaEventRecord(c->ev[0], cs));
   while ((int)c->h2d_ev.size() < nblocks) {
     cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventCreate(&e));               // timed: the TESSB200_TRACE timeline reads them
     c->h2d_ev.push_back(e);
   }
   // reuse device buffers of a previous upload where possible
@@ -393,11 +403,13 @@ static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *block
     if (blocks[order[i]].gid == blocks[order[i - 1]].gid) return fail(TESSB200_EINVAL, "duplicate gid %d", blocks[order[i]].gid);
   while ((int)c->blocks.size() > nblocks) {
     BlockRes *b = c->blocks.back();
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release(); b->hull.release();
     delete b;
     c->blocks.pop_back();
   }
   while ((int)c->blocks.size() < nblocks) c->blocks.push_back(new BlockRes);
+  // particles and vert_to_tet of every block first (small): the cells' processing order needs only
+  // those and is computed while the tets (93 % of the bytes) are still on their way
   for (int k = 0; k < nblocks; k++) {
     const tessb200_block &hb = blocks[order[k]];
     BlockRes *b = c->blocks[k];
@@ -414,10 +426,15 @@ static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *block
     TRY(b->v2t.ensure(sizeof(int) * (size_t)std::max(1, hb.num_particles)));
     TRY(b->cc.ensure(16 * (size_t)std::max(1, hb.num_tets)));
     if (hb.num_particles) CU(cudaMemcpyAsync(b->particles.p, hb.particles, sizeof(float) * 3 * (size_t)hb.num_particles, cudaMemcpyHostToDevice, cs));
-    if (hb.num_tets) CU(cudaMemcpyAsync(b->tets.p, hb.tets, 32 * (size_t)hb.num_tets, cudaMemcpyHostToDevice, cs));
     b->have_v2t = hb.vert_to_tet != nullptr;
     if (b->have_v2t && hb.num_particles)
       CU(cudaMemcpyAsync(b->v2t.p, hb.vert_to_tet, sizeof(int) * (size_t)hb.num_particles, cudaMemcpyHostToDevice, cs));
+  }
+  CU(cudaEventRecord(c->part_ev, cs));
+  for (int k = 0; k < nblocks; k++) {
+    const tessb200_block &hb = blocks[order[k]];
+    BlockRes *b = c->blocks[k];
+    if (hb.num_tets) CU(cudaMemcpyAsync(b->tets.p, hb.tets, 32 * (size_t)hb.num_tets, cudaMemcpyHostToDevice, cs));
     CU(cudaEventRecord(c->h2d_ev[k], cs));
   }
   CU(cudaEventRecord(c->ev[1], cs));
@@ -439,6 +456,7 @@ static DevBlock dev_block(const BlockRes *b)
   d.v2t = (const int *)b->v2t.p;
   d.cc = (const float4 *)b->cc.p;
   d.walk = (const WalkRec *)b->walk.p;
+  d.hull = (const unsigned char *)b->hull.p;
   d.num_orig = b->num_orig; d.num_particles = b->num_particles; d.num_tets = b->num_tets;
   d.cell_base = b->cell_base;
   d.order = nullptr;
@@ -452,6 +470,10 @@ static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b
 static int prep_block_geometry(tessb200_ctx *c, BlockRes *b, bool want_walk = false)
 {
   if (want_walk && b->num_tets) TRY(b->walk.ensure(sizeof(WalkRec) * (size_t)b->num_tets));
+  if (want_walk) {
+    TRY(b->hull.ensure((size_t)std::max(1, b->num_particles)));
+    CU(cudaMemsetAsync(b->hull.p, 0, (size_t)std::max(1, b->num_particles), c->stream));
+  }
   // vert_to_tet (if not given) and circumcenters for one resident block
   if (!b->have_v2t && b->num_particles) {
     k_fill_i32<<<cdiv(b->num_particles, 256), 256, 0, c->stream>>>((int *)b->v2t.p, b->num_particles, -1);
@@ -460,7 +482,7 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b, bool want_walk = fa
   }
   if (b->num_tets) {
     k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, (float4 *)b->cc.p,
-                                                                want_walk ? (WalkRec *)b->walk.p : nullptr);
+                                                                want_walk ? (WalkRec *)b->walk.p : nullptr, want_walk ? (unsigned char *)b->hull.p : nullptr);
     COUNT_LAUNCH(c, 1);
   }
   CU(cudaGetLastError());
@@ -502,6 +524,19 @@ static int prep_cell_order(tessb200_ctx *c, int k0, int k1, long long cell_off)
   return 0;
 }
 
+static void trace_mark(tessb200_ctx *c, const char *name)
+{
+  if (!c->tracing) return;
+  if (c->tr_used == c->tr_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    c->tr_ev.push_back(e);
+    c->tr_name.push_back(name);
+  }
+  c->tr_name[c->tr_used] = name;
+  cudaEventRecord(c->tr_ev[c->tr_used++], c->stream);
+}
+
 static int read_counters(tessb200_ctx *c)
 {
   CU(cudaMemcpyAsync(c->h_cnt, c->d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
@@ -526,6 +561,7 @@ struct PipeIO
   int nblocks_out = 0;
   tessb200_block *out_blocks = nullptr;           // caller's blocks: density pointers for the streamed download
   float *global_grid = nullptr;
+  cudaEvent_t particles_done = nullptr;           // particles (+ vert_to_tet) of every block are on the device
 };
 
 static int copy_block_out(tessb200_ctx *c, const tessb200_dense_params &p, BlockRes *b, tessb200_block *ob, float *global_grid, cudaStream_t s)
@@ -664,6 +700,8 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   TRY(make_geometry(c, p, &G));
   if (p->alg == TESSB200_DENSE_DTFE) return run_dtfe(c, p, st, io, G);
   cudaStream_t s = c->stream;
+  c->tracing = io.pipelined && getenv("TESSB200_TRACE") != nullptr;
+  c->tr_used = 0;
   const int nloc = (int)c->blocks.size();
   const int nall = (int)G.boxes.size();
   long long cells = 0, tets = 0;
@@ -693,6 +731,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
         BlockRes *b = c->blocks[k];
         DevBlock &d = hblocks[first_local_all + k];
         if (tess && b->num_tets) TRY(b->walk.ensure(sizeof(WalkRec) * (size_t)b->num_tets));
+        if (tess) TRY(b->hull.ensure((size_t)std::max(1, b->num_particles)));
         d = dev_block(b);
         d.order = c->order[1].as<uint32_t>() + order_off;
         order_off += b->num_orig;
@@ -729,17 +768,24 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   TopoOut to;
   memset(&to, 0, sizeof(to));
   uint32_t cap_ovf = 0;
+  uint32_t fast_pairs = 0;
+  const int slow_warps = 148 * 4 * 4;          // persistent warps of the general star walk (four 4-warp CTAs per SM)
   if (tess) {
-    TRY(c->plane_pool.ensure(48 * ((size_t)2 * tets + (size_t)cells + 64)));   // sum of faces <= 4 T
-    TRY(c->face_list.ensure(32 * ((size_t)2 * tets + (size_t)cells + 64)));
+    cap_ovf = (uint32_t)std::max<long long>(1024, cells / 64);
+    // plane pool / face list: sum of faces <= 4 T, in pairs of faces
+    if ((unsigned long long)2 * tets + (unsigned long long)cells + 64 >= 0xffffffffull) return fail(TESSB200_ELIMIT, "plane pool exceeds 2^32 face pairs");
+    fast_pairs = (uint32_t)((unsigned long long)2 * tets + (unsigned long long)cells + 64);
+    TRY(c->plane_pool.ensure(48 * (size_t)fast_pairs));
+    TRY(c->face_list.ensure(32 * (size_t)fast_pairs));
     TRY(c->hdr_small.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
     TRY(c->hdr_big.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
     TRY(c->big_bitoff.ensure(8 * (size_t)std::max<long long>(1, cells)));
-    cap_ovf = (uint32_t)std::max<long long>(1024, cells / 64);
     TRY(c->overflow.ensure(sizeof(uint2) * (size_t)cap_ovf));
+    TRY(c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)slow_warps));
     to.small = c->hdr_small.as<CellHdr>(); to.big = c->hdr_big.as<CellHdr>();
     to.big_bit_off = c->big_bitoff.as<unsigned long long>();
     to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.faces = c->face_list.as<FaceRef>(); to.cnt = cnt;
+    to.cap_pairs = fast_pairs;
     to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
     TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells), 0));
   } else {
@@ -747,10 +793,15 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   }
 
   CU(cudaEventRecord(c->ev[3], s));
-  float ms_cc = 0, ms_cells = 0, ms_scan = 0;
-  unsigned done_small = 0, done_big = 0, done_ovf = 0, done_pairs = 0;
-  unsigned long long done_bits = 0;
   long long cell_off = 0;
+  // one-call path: the processing order of every block was computed while the tets were still on
+  // their way (it needs the particles only)
+  bool order_ready = false;
+  if (tess && io.pipelined && io.particles_done) {
+    CU(cudaStreamWaitEvent(s, io.particles_done, 0));
+    TRY(prep_cell_order(c, 0, nloc, 0));
+    order_ready = true;
+  }
   for (size_t gi = 0; gi < groups.size(); gi++) {
     const int k0 = groups[gi].first, k1 = groups[gi].second;
     long long gcells = 0;
@@ -775,63 +826,96 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       continue;
     }
     // K0 / K1 / processing order
+    trace_mark(c, "group");
     for (int k = k0; k < k1; k++) TRY(prep_block_geometry(c, c->blocks[k], true));
-    TRY(prep_cell_order(c, k0, k1, cell_off));
+    trace_mark(c, "cc");
+    if (!order_ready) TRY(prep_cell_order(c, k0, k1, cell_off));
+    trace_mark(c, "order");
     cell_off += gcells;
     if (timed) CU(cudaEventRecord(c->ev[4], s));
-    // K3a part 1: BFS (+ general BFS for overflowing stars) and faces
+    // K3a: star BFS, neighbours, faces, scan of the cells the fast kernels can hold.  No host
+    // read-back in here: faces and scan take their ranges from the device-side counters, so the
+    // launches of a group (and of the next group) queue up behind one another.
     if (gctas) {
       const size_t n_slots = (size_t)gctas * TOPO_THREADS;
+      long long gtets = 0;
+      for (int k = k0; k < k1; k++) gtets += c->blocks[k]->num_tets;
       TRY(c->pre_hdr.ensure(sizeof(CellHdr) * n_slots));
       TRY(c->cand.ensure(sizeof(int2) * n_slots * TOPO_CAND_CAP));
       k_cell_bfs<<<gctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to,
                                                         c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
       if (timed) CU(cudaEventRecord(c->ev[11], s));
+      trace_mark(c, "bfs");
       k_cell_nbrs<<<gctas, TOPO_THREADS, NBRS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), to, c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
       if (timed) CU(cudaEventRecord(c->ev[12], s));
-      COUNT_LAUNCH(c, 2);
+      trace_mark(c, "nbrs");
+      // stars that did not fit the fast workspace: general BFS, persistent warps, the list range is read on
+      // the device; it appends to the same lists, so the faces and scan launches below cover its cells too
+      k_cell_bfs_big<<<slow_warps / 4, 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>(), c->ws_big.as<int>());
+      if (timed) CU(cudaEventRecord(c->ev[13], s));
+      trace_mark(c, "big");
+      if (!io.pipelined) {
+        // inputs resident, one group: nothing to overlap, so read the face count and launch exactly
+        TRY(read_counters(c));
+        if (timed) CU(cudaEventRecord(c->ev[13], s));
+        const size_t f1 = (size_t)std::min(c->h_cnt->plane_cursor, fast_pairs) * 2;
+        if (f1) k_cell_faces<<<cdiv((long long)f1, 256), 256, 0, s>>>(c->face_list.as<FaceRef>(), 0, f1, c->d_blocks.as<DevBlock>(), c->plane_pool.as<float>(), cnt);
+      } else {
+        // one-call path: no host read-back between the launches of a group, the kernel takes its range from the
+        // device-side counters; persistent CTAs (one resident wave) stride over it whatever its length
+        long long gparts = 0;
+        for (int k = k0; k < k1; k++) gparts += c->blocks[k]->num_particles;
+        const long long face_est = 2 * gtets + 2 * gparts + gcells + 256;     // faces ~ 2 T + 2 P (Euler)
+        static int faces_ctas = 0;
+        if (!faces_ctas) {
+          int per_sm = 0, sms = 0;
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cell_faces_dev, 256, 0));
+          CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+          faces_ctas = std::max(1, per_sm * sms);
+        }
+        k_cell_faces_dev<<<std::min<unsigned>(cdiv(face_est, 256), (unsigned)faces_ctas), 256, 0, s>>>(c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(),
+                                                                                                      c->plane_pool.as<float>(), cnt, &cnt->pairs_done,
+                                                                                                      &cnt->plane_cursor, fast_pairs);
+      }
+      if (timed) CU(cudaEventRecord(c->ev[5], s));
+      trace_mark(c, "faces");
+      SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
+      k_cell_scan<<<cdiv(gcells, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), 0, c->plane_pool.as<float>(),
+                                                                              c->d_blocks.as<DevBlock>(), sc, G.g, so, &cnt->small_done,
+                                                                              &cnt->n_small, to.cap_small);
+      k_advance<<<1, 1, 0, s>>>(cnt, to.cap_small);
+      COUNT_LAUNCH(c, 6);
+    } else {
+      if (timed) { CU(cudaEventRecord(c->ev[11], s)); CU(cudaEventRecord(c->ev[12], s)); CU(cudaEventRecord(c->ev[13], s)); CU(cudaEventRecord(c->ev[5], s)); }
     }
     CU(cudaGetLastError());
-    TRY(read_counters(c));
-    if (c->h_cnt->n_overflow > cap_ovf) return fail(TESSB200_ELIMIT, "%u cells exceed the fast star workspace (capacity %u)", c->h_cnt->n_overflow, cap_ovf);
-    if (c->h_cnt->n_overflow > done_ovf) {
-      const int n = (int)(c->h_cnt->n_overflow - done_ovf);
-      TRY(c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)n));
-      k_cell_bfs_big<<<cdiv((long long)n * 32, 128), 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>() + done_ovf, n, c->ws_big.as<int>());
-      COUNT_LAUNCH(c, 1);
-      CU(cudaGetLastError());
-      n_slow += n;
-      done_ovf = c->h_cnt->n_overflow;
-      TRY(read_counters(c));
-    }
-    if (timed) CU(cudaEventRecord(c->ev[13], s));
-    if (c->h_cnt->plane_cursor > done_pairs) {
-      const size_t f0 = (size_t)done_pairs * 2, f1 = (size_t)c->h_cnt->plane_cursor * 2;
-      k_cell_faces<<<cdiv((long long)(f1 - f0), 256), 256, 0, s>>>(c->face_list.as<FaceRef>(), f0, f1, c->d_blocks.as<DevBlock>(), c->plane_pool.as<float>(), cnt);
-      COUNT_LAUNCH(c, 1);
-      CU(cudaGetLastError());
-      done_pairs = c->h_cnt->plane_cursor;
-    }
-    if (timed) CU(cudaEventRecord(c->ev[5], s));
-    // K3a part 2: scan
-    const unsigned n_small = std::min(c->h_cnt->n_small, to.cap_small), n_big = std::min(c->h_cnt->n_big, to.cap_big);
-    if (n_big > done_big) TRY(c->bits_big.ensure((size_t)((c->h_cnt->big_bits - done_bits) / 8) + 64));
+    CU(cudaEventRecord(c->grp_ev[gi % 64], s));
+    trace_mark(c, "scan");
+  }
+  CU(cudaEventRecord(c->ev[15], s));
+
+  // After the one host read-back of the stage: the cells whose index box or face count exceeds the
+  // warp-autonomous scan (one CTA per cell).
+  unsigned done_small = 0, done_big = 0;
+  auto scan_big_list = [&](const SpanOut &so) -> int {
+    TRY(c->bits_big.ensure((size_t)(c->h_cnt->big_bits / 8) + 64));
+    k_cell_scan_big<<<done_big, 128, 0, s>>>(to.big, to.big_bit_off, (int)done_big, c->plane_pool.as<float>(), c->bits_big.as<uint32_t>(), 0ull,
+                                             c->d_blocks.as<DevBlock>(), sc, G.g, so);
+    COUNT_LAUNCH(c, 1);
+    return 0;
+  };
+  if (tess && cells > 0) {
     SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
-    if (n_small > done_small) {
-      const unsigned n = n_small - done_small;
-      k_cell_scan<<<cdiv(n, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>() + done_small, n, c->plane_pool.as<float>(),
-                                                                         c->d_blocks.as<DevBlock>(), sc, G.g, so);
-      COUNT_LAUNCH(c, 1);
-    }
-    if (n_big > done_big) {
-      const unsigned n = n_big - done_big;
-      k_cell_scan_big<<<n, 128, 0, s>>>(c->hdr_big.as<CellHdr>() + done_big, c->big_bitoff.as<unsigned long long>() + done_big, (int)n,
-                                        c->plane_pool.as<float>(), c->bits_big.as<uint32_t>(), done_bits, c->d_blocks.as<DevBlock>(), sc, G.g, so);
-      COUNT_LAUNCH(c, 1);
-      n_slow += n;
-    }
+    // resident runs read the counters before the faces launch, and no header is appended after that
+    if (io.pipelined) TRY(read_counters(c));
+    const Counters &h = *c->h_cnt;
+    if (h.n_overflow > cap_ovf) return fail(TESSB200_ELIMIT, "%u cells exceed the fast star workspace (capacity %u)", h.n_overflow, cap_ovf);
+    if (h.plane_cursor > fast_pairs) return fail(TESSB200_ELIMIT, "face pool overflow: %u pairs (capacity %u)", h.plane_cursor, fast_pairs);
+    done_small = std::min(h.n_small, to.cap_small);
+    done_big = std::min(h.n_big, to.cap_big);
+    n_slow += h.n_overflow + done_big;
+    if (done_big) TRY(scan_big_list(so));
     CU(cudaGetLastError());
-    done_small = n_small; done_big = n_big; done_bits = c->h_cnt->big_bits;
   }
   // span count (and the rare regrow: the span buffer was too small -> redo the scans of every group)
   TRY(read_counters(c));
@@ -845,13 +929,9 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     CU(cudaStreamSynchronize(s));
     SpanOut so{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
     if (done_small)
-      k_cell_scan<<<cdiv(done_small, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), done_small, c->plane_pool.as<float>(),
-                                                                                  c->d_blocks.as<DevBlock>(), sc, G.g, so);
-    if (done_big) {
-      TRY(c->bits_big.ensure((size_t)(c->h_cnt->big_bits / 8) + 64));
-      k_cell_scan_big<<<done_big, 128, 0, s>>>(c->hdr_big.as<CellHdr>(), c->big_bitoff.as<unsigned long long>(), (int)done_big, c->plane_pool.as<float>(),
-                                               c->bits_big.as<uint32_t>(), 0ull, c->d_blocks.as<DevBlock>(), sc, G.g, so);
-    }
+      k_cell_scan<<<cdiv(done_small, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(to.small, done_small, c->plane_pool.as<float>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
+                                                                                  nullptr, nullptr, 0);
+    if (done_big) TRY(scan_big_list(so));
     COUNT_LAUNCH(c, 2);
     CU(cudaGetLastError());
     TRY(read_counters(c));
@@ -887,10 +967,13 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
                                                                  c->row_start.as<unsigned long long>());
   COUNT_LAUNCH(c, 1);
   {
-    size_t smem = sizeof(float) * (size_t)ROWS_WARPS * (size_t)G.nx_max;
+    // one row buffer per warp; long rows (up to 32767 points) leave room for fewer warps per CTA
+    int rw = ROWS_WARPS;
+    while (rw > 1 && sizeof(float) * (size_t)rw * (size_t)G.nx_max > 160 * 1024) rw--;
+    size_t smem = sizeof(float) * (size_t)rw * (size_t)G.nx_max;
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!io.pipelined) {
-      k_rows<<<cdiv((long long)G.nrows, ROWS_WARPS), ROWS_WARPS * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0, 0ull,
+      k_rows<<<cdiv((long long)G.nrows, rw), rw * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0, 0ull,
                                                                                  G.nrows, c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div,
                                                                                  G.nx_max, c->out.as<float>());
       COUNT_LAUNCH(c, 1);
@@ -899,7 +982,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       for (int k = 0; k < nloc; k++) {
         BlockRes *b = c->blocks[k];
         if (b->nrows) {
-          k_rows<<<cdiv(b->nrows, ROWS_WARPS), ROWS_WARPS * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0,
+          k_rows<<<cdiv(b->nrows, rw), rw * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0,
                                                                             (unsigned long long)(b->row_base - (long long)G.row0), (unsigned long long)b->nrows,
                                                                             c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div, G.nx_max, c->out.as<float>());
           COUNT_LAUNCH(c, 1);
@@ -914,6 +997,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(c->ev[9], s));
+  if (io.pipelined) CU(cudaEventRecord(c->ev[14], c->copy_stream));
 
   if (st) {
     // dense_stats (src/dense.cpp:1284-1333): max density and total mass, from the final grid
@@ -939,6 +1023,20 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   c->ran = true;
   c->last_params = *p;
   c->out_floats = G.out_floats;
+  if (io.pipelined && getenv("TESSB200_TRACE")) {
+    // timeline of the one-call path, ms since the first host-to-device copy was enqueued
+    auto at = [&](cudaEvent_t e) { float m = 0; cudaEventElapsedTime(&m, c->ev[0], e); return m; };
+    fprintf(stderr, "[tessb200 trace] h2d done:");
+    for (int k = 0; k < nloc; k++) fprintf(stderr, " %.2f", at(c->h2d_ev[k]));
+    fprintf(stderr, " | run start %.2f groups:", at(c->ev[2]));
+    for (size_t gi = 0; gi < groups.size() && gi < 64; gi++) fprintf(stderr, " %.2f", at(c->grp_ev[gi]));
+    fprintf(stderr, " | cells done %.2f exchange %.2f sort %.2f rows:", at(c->ev[6]), at(c->ev[7]), at(c->ev[8]));
+    for (int k = 0; k < nloc && k < 64; k++) fprintf(stderr, " %.2f", at(c->blk_ev[k]));
+    fprintf(stderr, " | d2h done %.2f end %.2f\n", at(c->ev[14]), at(c->ev[10]));
+    fprintf(stderr, "[tessb200 trace] marks:");
+    for (size_t i = 0; i < c->tr_used; i++) fprintf(stderr, " %s %.3f", c->tr_name[i], at(c->tr_ev[i]));
+    fprintf(stderr, "\n");
+  }
   if (st) {
     st->num_cells = cells;
     st->num_no_tet = (int64_t)c->h_cnt->n_no_tet;
@@ -953,17 +1051,17 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     st->num_grid_pts = 0;
     for (BlockRes *b : c->blocks) st->num_grid_pts += b->npts;
     auto ms = [&](int a, int b) { float m = 0; cudaEventElapsedTime(&m, c->ev[a], c->ev[b]); return m; };
-    (void)ms_cc; (void)ms_cells; (void)ms_scan;
     const bool one = groups.size() == 1;
-    st->ms_upload = 0;
+    st->ms_upload = io.pipelined ? ms(0, 1) : 0;
     st->ms_circumcenters = one ? ms(3, 4) : 0;
     st->ms_cells = one ? ms(4, 5) : 0;
-    st->ms_scan = one ? ms(5, 6) : ms(3, 6);      // pipelined: all cell stages together (they overlap the copies)
+    st->ms_scan = one ? ms(5, 15) : ms(3, 15);    // pipelined: all cell stages together (they overlap the copies)
+    st->ms_slow_path = ms(15, 6) + (one && tess && cells > 0 ? ms(12, 13) : 0);   // oversized stars (general BFS) + oversized index boxes (per-CTA scan)
     st->ms_exchange = ms(6, 7);
     st->ms_sort = ms(7, 8);
     st->ms_deposit = ms(8, 9);
     st->ms_total_device = ms(2, 9);
-    st->ms_download = 0;
+    st->ms_download = io.pipelined ? ms(9, 14) : 0;
     const bool sub = one && tess && cells > 0;
     st->ms_bfs = sub ? ms(4, 11) : 0;
     st->ms_nbrs = sub ? ms(11, 12) : 0;
@@ -1047,6 +1145,7 @@ extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nbl
   PipeIO io;
   io.pipelined = true;
   io.h2d_done = &c->h2d_ev;
+  io.particles_done = c->part_ev;
   io.nblocks_out = nblocks;
   io.out_blocks = blocks;
   io.global_grid = global_grid;
@@ -1061,7 +1160,7 @@ extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nbl
 struct TmpBlock
 {
   BlockRes b;
-  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.rho.release(); b.walk.release(); }
+  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.rho.release(); b.walk.release(); b.hull.release(); }
 };
 
 static int upload_tmp(tessb200_ctx *c, TmpBlock &t, int num_particles, const float *particles, int num_tets, const int *tets, const int *v2t)
@@ -1104,7 +1203,7 @@ extern "C" int tessb200_circumcenters(tessb200_ctx *c, int num_particles, const 
   TmpBlock t;
   TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, nullptr));
   if (num_tets) {
-    k_circumcenters<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (const float *)t.b.particles.p, (float4 *)t.b.cc.p, nullptr);
+    k_circumcenters<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (const float *)t.b.particles.p, (float4 *)t.b.cc.p, nullptr, nullptr);
     CU(cudaGetLastError());
     // float4 -> packed xyz on the way out (the reference's std::vector<float> layout, volume.cpp:8)
     CU(cudaMemcpy2DAsync(out, 12, t.b.cc.p, 16, 12, (size_t)num_tets, cudaMemcpyDeviceToHost, c->stream));

@@ -31,6 +31,7 @@ struct DevBlock
   const int *v2t;
   const float4 *cc;        // circumcenter per tet, w = tet volume
   const WalkRec *walk;     // 32-byte circulation record per tet (neighbours, circumcenter, slot permutation)
+  const unsigned char *hull;   // 1 = the vertex belongs to a hull face, i.e. complete() is false (src/tet.cpp:337-378)
   int num_orig, num_particles, num_tets;
   uint32_t cell_base;      // global number of this block's cell 0 (blocks in ascending gid order)
   const uint32_t *order;   // cells of the block in Morton order of their sites (processing order only)
@@ -57,6 +58,9 @@ struct Counters
   unsigned long long big_bits;                 // bits needed by the big-cell list (multiples of 32)
   unsigned long long n_spans;                  // span records requested (may exceed capacity)
   unsigned long long n_cands;                  // candidate neighbours written by k_cell_bfs
+  // progress marks kept on the device (k_advance): the cell kernels of a group work on what was
+  // appended since the previous group, so the host never has to read a count between launches
+  unsigned int pairs_done, small_done, ovf_done;
 };
 
 struct FaceRef;
@@ -68,7 +72,7 @@ struct TopoOut
   float *plane_pool;
   struct FaceRef *faces;   // face list, parallel to the plane pool
   Counters *cnt;
-  uint32_t cap_small, cap_big, cap_overflow;
+  uint32_t cap_small, cap_big, cap_overflow, cap_pairs;
 };
 
 struct SpanOut
@@ -150,7 +154,8 @@ __global__ void k_vert_to_tet(const int4 *__restrict__ tets, int num_tets, int *
 // ---- K1: circumcenters, one thread per tet ---------------------------------------------------------
 // reads 16 B of the tet record (verts only) + 4 gathered particles, writes one float4 (x, y, z, volume)
 __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ tets, int num_tets,
-                                                        const float *__restrict__ particles, float4 *__restrict__ cc, WalkRec *__restrict__ walk)
+                                                        const float *__restrict__ particles, float4 *__restrict__ cc, WalkRec *__restrict__ walk,
+                                                        unsigned char *__restrict__ hull)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tets) return;
@@ -174,6 +179,15 @@ __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ 
     r.cx = o[0]; r.cy = o[1]; r.cz = o[2];
     r.perm = walk_perm(vv, nn, tets);
     walk[t] = r;
+    if (hull && (nb.x | nb.y | nb.z | nb.w) < 0) {
+      // a face without a neighbour: its three vertices have infinite Voronoi cells.  complete()
+      // finds exactly these by walking the star; the flag answers it before the walk starts.
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (nn[i] < 0)
+          for (int j = 0; j < 4; j++)
+            if (j != i) hull[vv[j]] = 1;
+    }
   }
 }
 
@@ -232,6 +246,7 @@ constexpr size_t NBRS_SMEM = (size_t)NbrWS<TOPO_THREADS>::WORDS * TOPO_THREADS *
 constexpr int TOPO_CAND_CAP = TOPO_STAR_CAP + 2;   // candidates per cell: 3 at the root + 1 per further star tet
 constexpr int BIG_STAR_CAP = 4096;
 constexpr int BIG_NBR_CAP = 1024;
+constexpr int BIG_SMEM_STAR = 192, BIG_SMEM_NBR = 96;   // shared-memory part of the general star walk (per warp: 1.5 KB)
 
 constexpr int SCAN_FACE_CAP = 32;     // faces per cell held in shared memory by k_cell_scan
 constexpr int SCAN_PTS_CAP = 2048;    // index-box points per cell handled by k_cell_scan
@@ -270,10 +285,12 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
       status = CELL_BAD_MESH;
     npts = (long long)n3[0] * n3[1] * n3[2];
   }
-  const bool ok = status == CELL_OK;
+  bool ok = status == CELL_OK;
   // plane / face-list space in pairs of faces (48-byte units: every cell's planes start 16-byte aligned)
   const uint32_t want = ok ? (uint32_t)((n_nbr + 1) >> 1) : 0u;
   const uint32_t poff = warp_alloc<unsigned int>(&out.cnt->plane_cursor, want);
+  // a pool that is too small drops the cell; the host sees the cursor past the capacity and reports it
+  ok = ok && poff + want <= out.cap_pairs;
   if (ok) {
     FaceRef *fr = out.faces + (size_t)poff * 2;
     for (int k = 0; k < n_nbr; k++) {
@@ -336,6 +353,14 @@ __global__ void k_morton_keys(const float *__restrict__ particles, int n, float3
   ids[i] = (uint32_t)i;
 }
 
+// src/dense.cpp:1385-1392: a cell whose box leaves the data bounds (plus eps) is skipped
+__device__ __forceinline__ bool box_outside_data(const float *cmin, const float *cmax, const GridGeom &g)
+{
+  bool out = false;
+  for (int d = 0; d < 3; d++) out = out || cmin[d] < fsub(g.dmin[d], g.dext_eps[d]) || cmax[d] > fadd(g.dmax[d], g.dext_eps[d]);
+  return out;
+}
+
 // K3a part 1a: star BFS + cell bbox + data-bounds filter + index box, one thread per cell, every block
 // of a group (all blocks of this GPU when the inputs are resident; one block at a time when the run is
 // pipelined against the host-to-device copies) in one launch: CTAs [cta_start_b, cta_start_{b+1}) work
@@ -375,9 +400,13 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__res
   float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
   if (slot_in_blk < blk.num_orig && blk.tets != nullptr) {
     cell = (int)blk.order[slot_in_blk];
-    int t0 = blk.v2t[cell];
+    const int t0 = blk.v2t[cell];
     CandSink sink{cand + slot, n_slots};
     status = t0 < 0 ? CELL_NO_TET : star_bfs_cands(cell, t0, blk.tets, blk.cc, ws, TOPO_STAR_CAP, &n_star, cmin, cmax, sink);
+    // A star too large for this kernel usually belongs to a cell at the edge of the data whose Voronoi
+    // vertices reach beyond the data bounds: the filter of src/dense.cpp:1385-1392 drops it whatever the
+    // rest of the star holds (the box only grows; the hull flag says the cell is complete), so the part seen so far decides.
+    if (status == CELL_OVERFLOW && !blk.hull[cell] && box_outside_data(cmin, cmax, g)) status = CELL_OUTSIDE;
   }
   __syncwarp();
   const bool ovf = status == CELL_OVERFLOW;
@@ -445,6 +474,7 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_nbrs(const DevBlock *__re
   // plane / face-list space in pairs of faces (48-byte units: every cell's planes start 16-byte aligned)
   const uint32_t want = ok ? (uint32_t)((nn + 1) >> 1) : 0u;
   const uint32_t poff = warp_alloc<unsigned int>(&out.cnt->plane_cursor, want);
+  ok = ok && poff + want <= out.cap_pairs;
   if (ok) {
     FaceRef *fr = out.faces + (size_t)poff * 2;
     for (int k = 0; k < nn; k++) {
@@ -492,60 +522,82 @@ __device__ __forceinline__ bool warp_contains(const int *list, int n, int key)
 }
 
 __global__ void __launch_bounds__(128) k_cell_bfs_big(const DevBlock *__restrict__ blocks, const __grid_constant__ GridGeom g, TopoOut out,
-                                                       const uint2 *__restrict__ cells, int n_cells, int *ws_g)
+                                                       const uint2 *__restrict__ cells, int *ws_g)
 {
-  const int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // persistent warps: the list length is read on the device (no host round trip before the launch),
+  // each warp keeps one workspace and takes cells warp_id, warp_id + n_warps, ...
+  const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+  const int warp_id = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)lane_id();
-  if (wi >= n_cells) return;                      // whole warp
-  const int blk_id = (int)cells[wi].x, cell = (int)cells[wi].y;
-  const DevBlock blk = blocks[blk_id];
-  int *base = ws_g + (size_t)wi * (BIG_STAR_CAP + 2 * BIG_NBR_CAP);
-  GlobalListWS ws{base, base + BIG_STAR_CAP, base + BIG_STAR_CAP + BIG_NBR_CAP};
-  float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
-  int status = CELL_OK, ns = 1, nn = 0;
-  if (lane == 0) ws.star_[0] = blk.v2t[cell];
-  __syncwarp();
-  for (int head = 0; head < ns && status == CELL_OK; head++) {
-    const int t = ws.star_[head];
-    const int4 v = blk.tets[2 * (size_t)t], nb = blk.tets[2 * (size_t)t + 1];
-    const float4 c = blk.cc[t];
-    cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
-    cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
-    const int vv[4] = {v.x, v.y, v.z, v.w}, bb[4] = {nb.x, nb.y, nb.z, nb.w};
+  const unsigned n_list = out.cnt->n_overflow < out.cap_overflow ? out.cnt->n_overflow : out.cap_overflow;
+  const unsigned n_first = out.cnt->ovf_done;     // cells of earlier groups are done (k_advance)
+  // lists start in shared memory (most oversized stars are only a little over the fast kernels'
+  // capacity) and move to the warp's global workspace when they outgrow it
+  __shared__ int lists_s[4][BIG_SMEM_STAR + 2 * BIG_SMEM_NBR];
+  int *const sm = lists_s[threadIdx.x >> 5];
+  int *const gbase = ws_g + (size_t)warp_id * (BIG_STAR_CAP + 2 * BIG_NBR_CAP);
+  for (unsigned wi = n_first + (unsigned)warp_id; wi < n_list; wi += (unsigned)n_warps) {
+    const int blk_id = (int)cells[wi].x, cell = (int)cells[wi].y;
+    const DevBlock blk = blocks[blk_id];
+    GlobalListWS ws{sm, sm + BIG_SMEM_STAR, sm + BIG_SMEM_STAR + BIG_SMEM_NBR};
+    int star_room = BIG_SMEM_STAR, nbr_room = BIG_SMEM_NBR;
+    float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int status = blk.hull[cell] ? CELL_INCOMPLETE : CELL_OK, ns = 1, nn = 0;
+    __syncwarp();
+    if (lane == 0) ws.star_[0] = blk.v2t[cell];
+    __syncwarp();
+    for (int head = 0; head < ns && status == CELL_OK; head++) {
+      const int t = ws.star_[head];
+      const int4 v = blk.tets[2 * (size_t)t], nb = blk.tets[2 * (size_t)t + 1];
+      const float4 c = blk.cc[t];
+      cmin[0] = fminf(cmin[0], c.x); cmin[1] = fminf(cmin[1], c.y); cmin[2] = fminf(cmin[2], c.z);
+      cmax[0] = fmaxf(cmax[0], c.x); cmax[1] = fmaxf(cmax[1], c.y); cmax[2] = fmaxf(cmax[2], c.z);
+      if (box_outside_data(cmin, cmax, g)) { status = CELL_OUTSIDE; break; }   // complete and already outside: see k_cell_bfs
+      const int vv[4] = {v.x, v.y, v.z, v.w}, bb[4] = {nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (status != CELL_OK) break;
-      const int u = vv[i];
-      if (u == cell) continue;
-      if (!warp_contains(ws.nu_, nn, u)) {
-        if (nn >= BIG_NBR_CAP) { status = CELL_BAD_MESH; break; }   // documented limit: > 1024 faces on one cell
-        if (lane == 0) { ws.nu_[nn] = u; ws.nt_[nn] = t; }
-        nn++;
-        __syncwarp();
-      }
-      const int next = bb[i];
-      if (next < 0) { status = CELL_INCOMPLETE; break; }
-      if (!warp_contains(ws.star_, ns, next)) {
-        if (ns >= BIG_STAR_CAP) { status = CELL_BAD_MESH; break; }  // documented limit: > 4096 tets around one site
-        if (lane == 0) ws.star_[ns] = next;
-        ns++;
-        __syncwarp();
+      for (int i = 0; i < 4; i++) {
+        if (status != CELL_OK) break;
+        const int u = vv[i];
+        if (u == cell) continue;
+        if (!warp_contains(ws.nu_, nn, u)) {
+          if (nn >= BIG_NBR_CAP) { status = CELL_BAD_MESH; break; }   // documented limit: > 1024 faces on one cell
+          if (nn == nbr_room) {
+            int *gu = gbase + BIG_STAR_CAP, *gt = gbase + BIG_STAR_CAP + BIG_NBR_CAP;
+            for (int j = lane; j < nn; j += 32) { gu[j] = ws.nu_[j]; gt[j] = ws.nt_[j]; }
+            ws.nu_ = gu; ws.nt_ = gt; nbr_room = BIG_NBR_CAP;
+            __syncwarp();
+          }
+          if (lane == 0) { ws.nu_[nn] = u; ws.nt_[nn] = t; }
+          nn++;
+          __syncwarp();
+        }
+        const int next = bb[i];
+        if (next < 0) { status = CELL_INCOMPLETE; break; }
+        if (!warp_contains(ws.star_, ns, next)) {
+          if (ns >= BIG_STAR_CAP) { status = CELL_BAD_MESH; break; }  // documented limit: > 4096 tets around one site
+          if (ns == star_room) {
+            for (int j = lane; j < ns; j += 32) gbase[j] = ws.star_[j];
+            ws.star_ = gbase; star_room = BIG_STAR_CAP;
+            __syncwarp();
+          }
+          if (lane == 0) ws.star_[ns] = next;
+          ns++;
+          __syncwarp();
+        }
       }
     }
+    __syncwarp();
+    // lane 0 carries the cell through the common tail; the other lanes pass "no cell"
+    bfs_finish(lane == 0 ? status : -1, cell, nn, ws, cmin, cmax, blk, blk_id, g, out);
   }
-  __syncwarp();
-  // lane 0 carries the cell through the common tail; the other lanes pass "no cell"
-  bfs_finish(lane == 0 ? status : -1, cell, nn, ws, cmin, cmax, blk, blk_id, g, out);
 }
 
 // K3a part 1b: one thread per Voronoi face: walk the tets around the Delaunay edge in the
 // reference's order, Newell normal, orientation, plane = (normal, first vertex) -> plane pool.
 // Tiny per-thread state and no shared memory: full occupancy hides the dependent gathers.
-__global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ faces, size_t f_begin, size_t f_end, const DevBlock *__restrict__ blocks,
-                                                     float *__restrict__ plane_pool, Counters *cnt)
+__device__ __forceinline__ void cell_face(const FaceRef *__restrict__ faces, size_t f, const DevBlock *__restrict__ blocks,
+                                          float *__restrict__ plane_pool, Counters *cnt)
 {
-  const size_t f = f_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= f_end) return;
   const FaceRef r = faces[f];
   if (r.u < 0) return;
   const DevBlock &b = blocks[r.blk];
@@ -570,6 +622,25 @@ __global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ 
   dst[0] = make_float2(fa.nrm[0], fa.nrm[1]);
   dst[1] = make_float2(fa.nrm[2], fa.v0[0]);
   dst[2] = make_float2(fa.v0[1], fa.v0[2]);
+}
+
+__global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ faces, size_t f_begin, size_t f_end, const DevBlock *__restrict__ blocks,
+                                                     float *__restrict__ plane_pool, Counters *cnt)
+{
+  const size_t f = f_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= f_end) return;
+  cell_face(faces, f, blocks, plane_pool, cnt);
+}
+
+// The same over a range kept on the device, in pairs of faces: [*range_lo, min(*range_hi, cap)).  Persistent
+// CTAs stride over it, so the launch needs no count from the host.
+__global__ void __launch_bounds__(256, 6) k_cell_faces_dev(const FaceRef *__restrict__ faces, const DevBlock *__restrict__ blocks, float *__restrict__ plane_pool,
+                                                         Counters *cnt, const unsigned int *range_lo, const unsigned int *range_hi, uint32_t range_cap)
+{
+  const uint32_t hi = *range_hi < range_cap ? *range_hi : range_cap;
+  const size_t f_end = (size_t)hi * 2;
+  for (size_t f = (size_t)*range_lo * 2 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < f_end; f += (size_t)gridDim.x * blockDim.x)
+    cell_face(faces, f, blocks, plane_pool, cnt);
 }
 
 // ---- span emission shared by the scan kernels and k_cic --------------------------------------------
@@ -765,10 +836,17 @@ __device__ __forceinline__ T warp_incl_scan(T v)
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_cell_scan(const CellHdr *__restrict__ hdrs, uint32_t n_hdrs,
                                                              const float *__restrict__ plane_pool, const DevBlock *__restrict__ blocks,
-                                                             ScanCtx sc, const __grid_constant__ GridGeom g, SpanOut out)
+                                                             ScanCtx sc, const __grid_constant__ GridGeom g, SpanOut out, const unsigned int *range_lo,
+                                                             const unsigned int *range_hi, uint32_t range_cap)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (range_hi) {
+    // header range kept on the device (the grid is an upper bound): [*range_lo, min(*range_hi, cap))
+    const uint32_t lo = range_lo ? *range_lo : 0u, hi = *range_hi < range_cap ? *range_hi : range_cap;
+    hdrs += lo;
+    n_hdrs = hi > lo ? hi - lo : 0u;
+  }
   unsigned char *mine = smem_raw + (size_t)warp * SCAN_WARP_BYTES;
   float *planes_w = reinterpret_cast<float *>(mine);                       // [2][SCAN_SLOT_FLOATS]
   uint32_t *bits_w = reinterpret_cast<uint32_t *>(planes_w + 2 * SCAN_SLOT_FLOATS);
@@ -1057,6 +1135,14 @@ __global__ void __launch_bounds__(256) k_cic(DevBlock blk, int blk_id, ScanCtx s
   }
 }
 
+// after the cell kernels of a group: what was appended so far is done
+__global__ void k_advance(Counters *cnt, uint32_t cap_small)
+{
+  cnt->pairs_done = cnt->plane_cursor;
+  cnt->small_done = cnt->n_small < cap_small ? cnt->n_small : cap_small;
+  cnt->ovf_done = cnt->n_overflow;
+}
+
 // ---- K3b: deposit.  Spans sorted by (row, remote, cell, z); one warp owns one row -----------------
 // row_start[r] = first sorted record of row r (r in [row0, row0 + nrows]); rows without records get
 // an empty range
@@ -1092,7 +1178,7 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__rest
   // rows [r_begin, r_begin + nrows) of this GPU's row range (row ids row0 + r)
   extern __shared__ float rowbuf_all[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned long long r = (unsigned long long)blockIdx.x * ROWS_WARPS + warp;
+  unsigned long long r = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + warp;   // 1..ROWS_WARPS warps per CTA (host: what fits shared memory)
   if (r >= nrows) return;
   r += r_begin;
   float *buf = rowbuf_all + (size_t)warp * nx_max;

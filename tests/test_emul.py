@@ -10,7 +10,7 @@ from golden_util import load_small
 
 
 @pytest.mark.parametrize("name,gs", [("c1", (64, 64, 64)), ("u16x8", (32, 32, 32)), ("clump8", (48, 48, 48)),
-                                     ("aniso", (40, 28, 17)), ("tiny", (8, 8, 8))])
+                                     ("aniso", (40, 28, 17)), ("tiny", (8, 8, 8)), ("clump8", (20000, 6, 6))])
 def test_emul_matches_port(port, emul, name, gs):
     blocks = dataset(name)
     for b in blocks[:2]:

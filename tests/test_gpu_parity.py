@@ -160,6 +160,18 @@ def test_big_cells_and_many_faces(ctx, port):
                                         port.fill_vert_to_tet(len(pts), blocks[0]["tets"])), "large star volume")
 
 
+def test_long_rows(ctx, port):
+    # a grid 20000 points wide: the deposit kernel's per-warp row buffer no longer fits four warps per
+    # CTA, index boxes are wider than 32 points (generic scan-line walk), spans are long
+    gs = (20000, 6, 6)
+    for name in ("tiny", "clump8"):
+        blocks = dataset(name)
+        for alg in (0, 1):
+            o = port.dense(blocks, gs, alg=alg)
+            res = run_gpu(ctx, blocks, gs, alg=alg)
+            compare_dense(res, o, f"long rows {name} alg {alg}")
+
+
 def test_edge_cases(ctx):
     import tess2_b200
     # a block with particles but no tets, next to a normal block: nothing deposits from it
