@@ -225,6 +225,15 @@ def run_ours(args, rank, world, local_rank):
     blocks, layout, owner, dmin, dmax, gsize = build_workload(n, rank)
     from tess2_b200.harness import workloads as _wl
     host_tess = dict(_wl.LAST_TESS)
+    # the package's own host driver + Delaunay engine on the same particles (same set of tets), timed beside SciPy's Qhull
+    native_tess = None
+    if n == 1 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        nb_blocks, _, _, _ = _wl.uniform_regular(H, (2, 2, 2), gids=list(range(8)), cache=False, engine="native")
+        native_tess = {"engine": "tess2_b200/host (C++ incremental Delaunay, exact predicates), one thread per block", "seconds": time.perf_counter() - t0,
+                       "threads": min(8, os.cpu_count() or 1), "tets": int(sum(len(b["tets"]) for b in nb_blocks)),
+                       "same_tet_count_as_qhull": int(sum(len(b["tets"]) for b in nb_blocks)) == int(sum(len(b["tets"]) for b in blocks))}
+        del nb_blocks
     keep = []
     for b in blocks:                      # pinned host buffers: the e2e leg copies from these
         for k in ("particles", "tets", "vert_to_tet"):
@@ -387,7 +396,9 @@ def run_ours(args, rank, world, local_rank):
             "other_algs": other,
             "host_tess": {"engine": "SciPy Qhull 'Qt', one process per block", "seconds": host_tess.get("seconds"), "workers": host_tess.get("workers"),
                           "from_cache": host_tess.get("cached"),
-                          "tess_plus_dense_seconds": (host_tess["seconds"] + e2e_ms * 1e-3) if host_tess.get("seconds") else None},
+                          "tess_plus_dense_seconds": (host_tess["seconds"] + e2e_ms * 1e-3) if host_tess.get("seconds") else None,
+                          "native": native_tess,
+                          "native_tess_plus_dense_seconds": (native_tess["seconds"] + e2e_ms * 1e-3) if native_tess else None},
             "stats": {"cells": cells_local, "tets": T_local, "particles_with_ghosts": P_local, "grid_points": G_local, "spans": spans, "faces": F, "candidates": Cn,
                       "deposit_cells": int(st.num_deposit_cells), "cic_fallback_cells": int(st.num_cic_fallback), "slow_cells": int(st.num_slow_cells),
                       "tot_mass": float(st.tot_mass)},

@@ -1,0 +1,63 @@
+/* tess_b200_host.h -- host side of the tessellation stage (CPU only, libtess_b200_host.so).
+ *
+ * the serial Delaunay engine stays on the host (north_star).  The reference plugs
+ * Qhull or CGAL behind local_cells() / gen_delaunay_output() (src/tess-qhull.c:31-165,
+ * src/tess-cgal.cpp); neither library is installed here, so the engine is this repo's own
+ * (tess2_b200/host/delaunay3.hpp).  Output layout = struct tet_t (include/tess/tet.h:4-7).
+ */
+#ifndef TESS_B200_HOST_H
+#define TESS_B200_HOST_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Delaunay tetrahedralisation of num_particles float32 points (xyz AoS).
+ * *tets receives a malloc'ed array of *num_tets records {int verts[4]; int tets[4]} with tets[i]
+ * opposite verts[i] and -1 on the convex hull (free with tessb200_host_free or free()).
+ * Returns 0 on success (also when the points admit no tet: *num_tets = 0), < 0 on error. */
+int tessb200_host_delaunay(int num_particles, const float *particles, int *num_tets, int **tets);
+
+/* One block after tessellation: the dblock_t fields dense() reads (include/tess/delaunay.h:38-63).
+ * Arrays are malloc'ed (tess2 frees them with free(), src/tess.cpp:166-178). */
+typedef struct tessb200_host_block {
+  int gid;
+  float bounds_min[3], bounds_max[3];
+  int num_orig_particles;    /* particles owned by the block: first in `particles`, in input order */
+  int num_particles;         /* originals + ghosts */
+  int num_tets;
+  float *particles;          /* [3 * num_particles] */
+  int *tets;                 /* [8 * num_tets]: verts[4], tets[4] */
+  int *vert_to_tet;          /* [num_particles], last tet holding the vertex (src/tess.cpp:767-787), -1 if none */
+  int *global_ids;           /* [num_particles] index of each local particle in the input array */
+  float ghost_margin;        /* width of the ghost region that was finally used */
+  int rounds;                /* tessellation rounds (the region grows until every original cell is settled) */
+  double seconds;            /* time spent in the Delaunay engine for this block */
+} tessb200_host_block;
+
+/* tess() for one process holding all particles (replaces the round loop of src/tess.cpp:52-116 with
+ * its ghost exchange, :351-457, for the single-node case): every block takes the particles it owns
+ * plus the ghosts inside a margin around its bounds, tessellates them, and widens the margin until
+ * the circumsphere of every tet at an original, finite cell stays inside the searched region (the
+ * test of incomplete_cells, src/tess.cpp:492-628, against the region instead of neighbour bounds).
+ *   owner        [num_particles] gid of the owning block, or NULL: ownership by containment in
+ *                block_bounds (min <= x < max; the upper domain faces are inclusive)
+ *   block_bounds [6 * nblocks]: min xyz, max xyz of block gid = index
+ *   gids         [num_gids] the blocks to tessellate (a rank's share), or NULL: all nblocks
+ *   margin0      first ghost margin; <= 0: three mean particle spacings of the block
+ *   max_rounds   tessellation rounds per block at most (<= 0: 3)
+ *   max_growth   the margin never exceeds max_growth * margin0 (<= 0: 2.5)
+ *   num_threads  blocks in flight (<= 0: hardware concurrency)
+ * blocks_out[num_gids (or nblocks)] is filled in gids order; release with tessb200_host_free_block. */
+int tessb200_host_tess(int num_particles, const float *particles, const int *owner, const float *domain_min, const float *domain_max,
+                       int nblocks, const float *block_bounds, int num_gids, const int *gids, float margin0, int max_rounds,
+                       float max_growth, int num_threads, tessb200_host_block *blocks_out);
+void tessb200_host_free_block(tessb200_host_block *b);
+
+void tessb200_host_free(void *p);
+const char *tessb200_host_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -44,12 +44,15 @@ def _load(path):
     return blocks
 
 
-def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log=None):
+def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log=None, engine="qhull"):
     """`gen_particles` workload (TESS_DENSE_TEST semantics): domain
     [0, n_x-1] x [0, n_y-1] x [0, n_z-1] with n = n_side * blocks per axis / ... each block holds
     (block extent + 1)^3-ish particles drawn with srand(gid).  blocks_xyz = (bx, by, bz); every
     block spans n_side/..: the domain is (bx*h, by*h, bz*h) - 1 wide with h = n_side.
     gids: the blocks to tessellate (default all); ghosts come from the neighbouring blocks.
+    engine: "qhull" (SciPy's Qhull with 'Qt', the reference's engine and options, one process per
+    block) or "native" (the package's C++ driver and Delaunay engine, tess2_b200/host): same
+    particles, same set of tets, different tet numbering.
     Returns (blocks, layout) where layout lists (gid, bounds_min, bounds_max) of EVERY block."""
     bx, by, bz = blocks_xyz
     h = n_side
@@ -67,7 +70,7 @@ def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log
                 layout.append((len(layout), mn, mx))
     if gids is None:
         gids = list(range(len(layout)))
-    key = f"uniform_regular:{n_side}:{blocks_xyz}:{sorted(gids)}:v5"
+    key = f"uniform_regular:{n_side}:{blocks_xyz}:{sorted(gids)}:v5" + ("" if engine == "qhull" else ":" + engine)
     path = _cache_path(key)
     if cache and os.path.exists(path):
         if log:
@@ -87,10 +90,15 @@ def uniform_regular(n_side, blocks_xyz, gids=None, workers=None, cache=True, log
     owner = np.concatenate([np.full(len(ps[g]), g, np.int32) for g in need])
     bounds = {g: (layout[g][1], layout[g][2]) for g in gids}
     # tessellate only the wanted gids
-    delaunay._G.update(points=allp, owner=owner, bounds=bounds, dmin=dom_min, dmax=dom_max, margin0=None, max_growth=1.0)
-    blocks = delaunay.tessellate_gids(gids, workers)
-    for b in blocks:   # dblock_t::vert_to_tet is part of what tess hands to dense (src/tess.cpp:767-787)
-        b["vert_to_tet"] = delaunay.fill_vert_to_tet(len(b["particles"]), b["tets"])
+    if engine == "native":
+        from .. import host_tess
+        blocks = host_tess.tess(allp, owner, [(mn, mx) for _, mn, mx in layout], dom_min, dom_max, gids=list(gids), max_growth=1.0,
+                                threads=workers or 0)
+    else:
+        delaunay._G.update(points=allp, owner=owner, bounds=bounds, dmin=dom_min, dmax=dom_max, margin0=None, max_growth=1.0)
+        blocks = delaunay.tessellate_gids(gids, workers)
+        for b in blocks:   # dblock_t::vert_to_tet is part of what tess hands to dense (src/tess.cpp:767-787)
+            b["vert_to_tet"] = delaunay.fill_vert_to_tet(len(b["particles"]), b["tets"])
     if log:
         log(f"tessellated {len(gids)} blocks ({sum(b['num_orig'] for b in blocks)} particles, "
             f"{sum(len(b['tets']) for b in blocks)} tets) in {time.time() - t0:.1f} s")

@@ -1,0 +1,250 @@
+// host_tess.cpp -- C ABI of the host-side tessellation driver (libtess_b200_host.so, no CUDA).
+// See include/tess_b200_host.h.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tess_b200_host.h"
+#include "delaunay3.hpp"
+
+static thread_local std::string g_err;
+
+extern "C" const char *tessb200_host_last_error(void) { return g_err.c_str(); }
+
+extern "C" int tessb200_host_delaunay(int num_particles, const float *particles, int *num_tets, int **tets)
+{
+  if (!particles || !num_tets || !tets || num_particles < 0) { g_err = "NULL argument"; return -1; }
+  *num_tets = 0;
+  *tets = nullptr;
+  try {
+    tb_host::Delaunay3 d;
+    if (!d.build(particles, num_particles)) return 0;    // fewer than 4 points in general position: no tets
+    std::vector<int> out;
+    d.export_tets(out);
+    *num_tets = (int)(out.size() / 8);
+    *tets = (int *)malloc(out.size() * sizeof(int) + 8);  // malloc: tess2 frees dblock_t::tets with free() (src/tess.cpp:170)
+    if (!*tets) { g_err = "out of memory"; return -2; }
+    memcpy(*tets, out.data(), out.size() * sizeof(int));
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -3;
+  }
+  return 0;
+}
+
+extern "C" void tessb200_host_free(void *p) { free(p); }
+
+// ---- tess() for one process: blocks = originals + ghosts within a margin, widened until settled --------
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <thread>
+
+namespace
+{
+
+struct Sphere { double c[3], r; bool ok; };
+
+// circumsphere in double (only used to decide whether the ghost region is wide enough)
+Sphere circumsphere(const float *a, const float *b, const float *c, const float *d)
+{
+  const double ux = (double)b[0] - a[0], uy = (double)b[1] - a[1], uz = (double)b[2] - a[2];
+  const double vx = (double)c[0] - a[0], vy = (double)c[1] - a[1], vz = (double)c[2] - a[2];
+  const double wx = (double)d[0] - a[0], wy = (double)d[1] - a[1], wz = (double)d[2] - a[2];
+  const double u2 = ux * ux + uy * uy + uz * uz, v2 = vx * vx + vy * vy + vz * vz, w2 = wx * wx + wy * wy + wz * wz;
+  const double cvw[3] = {vy * wz - vz * wy, vz * wx - vx * wz, vx * wy - vy * wx};
+  const double cwu[3] = {wy * uz - wz * uy, wz * ux - wx * uz, wx * uy - wy * ux};
+  const double cuv[3] = {uy * vz - uz * vy, uz * vx - ux * vz, ux * vy - uy * vx};
+  const double det = 2.0 * (ux * cvw[0] + uy * cvw[1] + uz * cvw[2]);
+  Sphere s;
+  s.ok = det != 0.0;
+  if (!s.ok) { s.c[0] = s.c[1] = s.c[2] = 0; s.r = INFINITY; return s; }
+  double o[3];
+  for (int k = 0; k < 3; k++) o[k] = (u2 * cvw[k] + v2 * cwu[k] + w2 * cuv[k]) / det;
+  s.r = std::sqrt(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+  for (int k = 0; k < 3; k++) s.c[k] = a[k] + o[k];
+  return s;
+}
+
+struct BlockJob
+{
+  int gid;
+  double bmin[3], bmax[3];
+  std::vector<int> mine;     // global ids of the originals, input order
+};
+
+int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, const double *dmin, const double *dmax, double margin0,
+               int max_rounds, double max_growth, tessb200_host_block *out)
+{
+  const int n_orig = (int)job.mine.size();
+  if (margin0 <= 0.0) {
+    const double vol = (job.bmax[0] - job.bmin[0]) * (job.bmax[1] - job.bmin[1]) * (job.bmax[2] - job.bmin[2]);
+    margin0 = 3.0 * std::cbrt(vol / std::max(n_orig, 1));
+  }
+  double margin = margin0;
+  std::vector<float> P;
+  std::vector<int> gids, tets;
+  int rounds = 0;
+  double secs = 0.0;
+  for (;;) {
+    rounds++;
+    gids.assign(job.mine.begin(), job.mine.end());
+    for (int i = 0; i < n; i++) {
+      if (owner[i] == job.gid) continue;
+      const float *q = pts + 3 * (size_t)i;
+      bool in = true;
+      for (int d = 0; d < 3; d++) in = in && (double)q[d] >= job.bmin[d] - margin && (double)q[d] <= job.bmax[d] + margin;
+      if (in) gids.push_back(i);
+    }
+    const int np = (int)gids.size();
+    P.resize(3 * (size_t)np);
+    for (int i = 0; i < np; i++) memcpy(&P[3 * (size_t)i], pts + 3 * (size_t)gids[i], 12);
+    const auto t0 = std::chrono::steady_clock::now();
+    tb_host::Delaunay3 dt;
+    tets.clear();
+    if (dt.build(P.data(), np)) dt.export_tets(tets);
+    secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const size_t nt = tets.size() / 8;
+    bool covered = true;
+    for (int d = 0; d < 3; d++) covered = covered && job.bmin[d] - margin <= dmin[d] && job.bmax[d] + margin >= dmax[d];
+    if (covered || rounds >= max_rounds || np == n_orig) break;
+    // originals on the local hull have unbounded cells; fine next to the domain boundary, a sign of too
+    // few ghosts anywhere else
+    std::vector<char> on_hull(np, 0);
+    for (size_t t = 0; t < nt; t++)
+      for (int k = 0; k < 4; k++)
+        if (tets[8 * t + 4 + k] < 0)
+          for (int j = 0; j < 4; j++) if (j != k) on_hull[tets[8 * t + j]] = 1;
+    bool grow = false;
+    for (int i = 0; i < n_orig && !grow; i++) {
+      if (!on_hull[i]) continue;
+      double dist = INFINITY;
+      for (int d = 0; d < 3; d++) dist = std::min(dist, std::min((double)P[3 * (size_t)i + d] - dmin[d], dmax[d] - (double)P[3 * (size_t)i + d]));
+      if (dist > margin) grow = true;
+    }
+    // circumspheres of the tets at original, finite cells must stay inside the searched region
+    // (clipped at the domain: nothing lives beyond it)
+    double req = 0.0;
+    for (size_t t = 0; t < nt; t++) {
+      const int *v = &tets[8 * t];
+      bool need = false;
+      for (int j = 0; j < 4; j++) need = need || (v[j] < n_orig && !on_hull[v[j]]);
+      if (!need) continue;
+      const Sphere s = circumsphere(&P[3 * (size_t)v[0]], &P[3 * (size_t)v[1]], &P[3 * (size_t)v[2]], &P[3 * (size_t)v[3]]);
+      for (int d = 0; d < 3; d++) {
+        const double lo_need = job.bmin[d] - (s.c[d] - s.r), hi_need = (s.c[d] + s.r) - job.bmax[d];
+        req = std::max(req, std::min(lo_need, job.bmin[d] - dmin[d]));
+        req = std::max(req, std::min(hi_need, dmax[d] - job.bmax[d]));
+      }
+    }
+    if (grow) req = std::max(req, 2.0 * margin);
+    if (req <= margin || margin >= max_growth * margin0) break;
+    margin = std::min(req * 1.05, max_growth * margin0);
+  }
+  const int np = (int)gids.size();
+  const size_t nt = tets.size() / 8;
+  out->gid = job.gid;
+  for (int d = 0; d < 3; d++) { out->bounds_min[d] = (float)job.bmin[d]; out->bounds_max[d] = (float)job.bmax[d]; }
+  out->num_orig_particles = n_orig;
+  out->num_particles = np;
+  out->num_tets = (int)nt;
+  out->particles = (float *)malloc(sizeof(float) * 3 * (size_t)std::max(np, 1));
+  out->tets = (int *)malloc(sizeof(int) * 8 * std::max<size_t>(nt, 1));
+  out->vert_to_tet = (int *)malloc(sizeof(int) * (size_t)std::max(np, 1));
+  out->global_ids = (int *)malloc(sizeof(int) * (size_t)std::max(np, 1));
+  if (!out->particles || !out->tets || !out->vert_to_tet || !out->global_ids) return -2;
+  if (np > 0) { memcpy(out->particles, P.data(), sizeof(float) * 3 * (size_t)np); memcpy(out->global_ids, gids.data(), sizeof(int) * (size_t)np); }
+  if (nt) memcpy(out->tets, tets.data(), sizeof(int) * 8 * nt);
+  // fill_vert_to_tet (src/tess.cpp:767-787): the last tet holding the vertex wins
+  for (int i = 0; i < np; i++) out->vert_to_tet[i] = -1;
+  for (size_t t = 0; t < nt; t++)
+    for (int j = 0; j < 4; j++) out->vert_to_tet[tets[8 * t + j]] = (int)t;
+  out->ghost_margin = (float)margin;
+  out->rounds = rounds;
+  out->seconds = secs;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int tessb200_host_tess(int num_particles, const float *particles, const int *owner, const float *domain_min, const float *domain_max,
+                                  int nblocks, const float *block_bounds, int num_gids, const int *gids, float margin0, int max_rounds,
+                                  float max_growth, int num_threads, tessb200_host_block *blocks_out)
+{
+  if (!particles || !domain_min || !domain_max || !block_bounds || !blocks_out || nblocks < 1 || num_particles < 0) { g_err = "bad argument"; return -1; }
+  const double dmin[3] = {domain_min[0], domain_min[1], domain_min[2]}, dmax[3] = {domain_max[0], domain_max[1], domain_max[2]};
+  std::vector<BlockJob> jobs(nblocks);
+  for (int b = 0; b < nblocks; b++) {
+    jobs[b].gid = b;
+    for (int d = 0; d < 3; d++) { jobs[b].bmin[d] = block_bounds[6 * b + d]; jobs[b].bmax[d] = block_bounds[6 * b + 3 + d]; }
+  }
+  std::vector<int> own;
+  if (!owner) {
+    own.assign(num_particles, -1);
+    for (int i = 0; i < num_particles; i++) {
+      const float *q = particles + 3 * (size_t)i;
+      for (int b = 0; b < nblocks && own[i] < 0; b++) {
+        bool in = true;
+        for (int d = 0; d < 3; d++) {
+          const bool top = jobs[b].bmax[d] >= dmax[d];     // the upper domain faces belong to the last block
+          in = in && (double)q[d] >= jobs[b].bmin[d] && ((double)q[d] < jobs[b].bmax[d] || (top && (double)q[d] <= jobs[b].bmax[d]));
+        }
+        if (in) own[i] = b;
+      }
+      if (own[i] < 0) { g_err = "a particle lies in no block"; return -1; }
+    }
+    owner = own.data();
+  }
+  for (int i = 0; i < num_particles; i++) {
+    if (owner[i] < 0 || owner[i] >= nblocks) { g_err = "owner gid out of range"; return -1; }
+    jobs[owner[i]].mine.push_back(i);
+  }
+  std::vector<int> todo;
+  if (gids) {
+    for (int i = 0; i < num_gids; i++) {
+      if (gids[i] < 0 || gids[i] >= nblocks) { g_err = "gid out of range"; return -1; }
+      todo.push_back(gids[i]);
+    }
+  } else {
+    for (int b = 0; b < nblocks; b++) todo.push_back(b);
+  }
+  const int ntodo = (int)todo.size();
+  if (max_rounds <= 0) max_rounds = 3;
+  if (!(max_growth > 0.0f)) max_growth = 2.5f;
+  for (int b = 0; b < ntodo; b++) memset(&blocks_out[b], 0, sizeof(tessb200_host_block));
+  int nthreads = num_threads > 0 ? num_threads : (int)std::thread::hardware_concurrency();
+  nthreads = std::max(1, std::min(nthreads, ntodo));
+  std::atomic<int> next(0), rc(0);
+  std::vector<std::string> errs(nthreads);
+  auto work = [&](int tid) {
+    for (;;) {
+      const int b = next.fetch_add(1);
+      if (b >= ntodo) return;
+      try {
+        const int r = tess_block(particles, num_particles, owner, jobs[todo[b]], dmin, dmax, margin0, max_rounds, max_growth, &blocks_out[b]);
+        if (r) { rc = r; errs[tid] = "out of memory"; }
+      } catch (const std::exception &e) {
+        rc = -3;
+        errs[tid] = e.what();
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &t : th) t.join();
+  if (rc) {
+    for (auto &e : errs) if (!e.empty()) g_err = e;
+    for (int b = 0; b < ntodo; b++) tessb200_host_free_block(&blocks_out[b]);
+    return rc;
+  }
+  return 0;
+}
+
+extern "C" void tessb200_host_free_block(tessb200_host_block *b)
+{
+  if (!b) return;
+  free(b->particles); free(b->tets); free(b->vert_to_tet); free(b->global_ids);
+  b->particles = nullptr; b->tets = nullptr; b->vert_to_tet = nullptr; b->global_ids = nullptr;
+}

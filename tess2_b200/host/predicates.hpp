@@ -120,13 +120,17 @@ inline int orient3d_exact(const float *a, const float *b, const float *c, const 
   return sign(det);
 }
 
-inline int orient3d(const float *a, const float *b, const float *c, const float *d)
+// static_bound: 0, or a bound on the rounding error valid for every call of a run (StaticFilter below):
+// most calls are decided by one comparison, before the per-call bound is even computed
+inline int orient3d(const float *a, const float *b, const float *c, const float *d, double static_bound = 0.0)
 {
   const double adx = (double)a[0] - d[0], ady = (double)a[1] - d[1], adz = (double)a[2] - d[2];
   const double bdx = (double)b[0] - d[0], bdy = (double)b[1] - d[1], bdz = (double)b[2] - d[2];
   const double cdx = (double)c[0] - d[0], cdy = (double)c[1] - d[1], cdz = (double)c[2] - d[2];
   const double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy, cdxady = cdx * ady, adxcdy = adx * cdy, adxbdy = adx * bdy, bdxady = bdx * ady;
   const double det = adz * (bdxcdy - cdxbdy) + bdz * (cdxady - adxcdy) + cdz * (adxbdy - bdxady);
+  if (det > static_bound && static_bound > 0.0) return 1;
+  if (det < -static_bound && static_bound > 0.0) return -1;
   const double permanent = (std::fabs(bdxcdy) + std::fabs(cdxbdy)) * std::fabs(adz) + (std::fabs(cdxady) + std::fabs(adxcdy)) * std::fabs(bdz) +
                            (std::fabs(adxbdy) + std::fabs(bdxady)) * std::fabs(cdz);
   // float32 inputs: the differences above are exact unless the exponents are far apart; the bound
@@ -156,7 +160,7 @@ inline int insphere_exact(const float *a, const float *b, const float *c, const 
   return sign(det);
 }
 
-inline int insphere(const float *a, const float *b, const float *c, const float *d, const float *e)
+inline int insphere(const float *a, const float *b, const float *c, const float *d, const float *e, double static_bound = 0.0)
 {
   const double aex = (double)a[0] - e[0], aey = (double)a[1] - e[1], aez = (double)a[2] - e[2];
   const double bex = (double)b[0] - e[0], bey = (double)b[1] - e[1], bez = (double)b[2] - e[2];
@@ -175,6 +179,8 @@ inline int insphere(const float *a, const float *b, const float *c, const float 
   const double alift = aex * aex + aey * aey + aez * aez, blift = bex * bex + bey * bey + bez * bez;
   const double clift = cex * cex + cey * cey + cez * cez, dlift = dex * dex + dey * dey + dez * dez;
   const double det = (dlift * abc - clift * dab) + (blift * cda - alift * bcd);
+  if (det > static_bound && static_bound > 0.0) return 1;
+  if (det < -static_bound && static_bound > 0.0) return -1;
   const double aezp = std::fabs(aez), bezp = std::fabs(bez), cezp = std::fabs(cez), dezp = std::fabs(dez);
   const double aexbeyp = std::fabs(aexbey), bexaeyp = std::fabs(bexaey), bexceyp = std::fabs(bexcey), cexbeyp = std::fabs(cexbey);
   const double cexdeyp = std::fabs(cexdey), dexceyp = std::fabs(dexcey), dexaeyp = std::fabs(dexaey), aexdeyp = std::fabs(aexdey);
@@ -188,6 +194,19 @@ inline int insphere(const float *a, const float *b, const float *c, const float 
   if (det < -errbound) return -1;
   return insphere_exact(a, b, c, d, e);
 }
+
+// Error bounds that hold for every predicate call on points whose coordinate differences are at
+// most D in magnitude: the per-call bounds above are (coefficient) x permanent, and the permanents
+// are at most 6 D^3 (orient3d) and 72 D^5 (insphere).
+struct StaticFilter
+{
+  double orient = 0.0, sphere = 0.0;
+  void set_extent(double D)
+  {
+    orient = 1.6e-15 * 6.0 * D * D * D;
+    sphere = 3.6e-15 * 72.0 * D * D * D * D * D;
+  }
+};
 
 }  // namespace tb_host
 

@@ -9,8 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    txt = open(os.path.join(ROOT, "include", "tess_b200.h")).read()
+def header_symbols(name="tess_b200.h"):
+    txt = open(os.path.join(ROOT, "include", name)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(tessb200_[a-z0-9_]+)\s*\(", txt)))
 
@@ -26,6 +26,26 @@ def test_library_exports_every_declared_symbol():
     for name in header_symbols():
         assert hasattr(l, name), f"libtess_b200.so does not export {name}"
     assert l.tessb200_version() == 1
+
+
+def test_host_library_exports_every_declared_symbol(tmp_path):
+    # the CPU side of the tessellation stage (include/tess_b200_host.h, libtess_b200_host.so)
+    import subprocess
+    from tess2_b200 import host_tess
+    syms = [s for s in header_symbols("tess_b200_host.h")]
+    assert sorted(syms) == sorted(host_tess.EXPORTS)
+    l = host_tess.load()
+    for name in syms:
+        assert hasattr(l, name), f"libtess_b200_host.so does not export {name}"
+    src = tmp_path / "szh.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "tess_b200_host.h"
+int main(void) { printf("%zu %zu %zu\\n", sizeof(tessb200_host_block), offsetof(tessb200_host_block, particles), offsetof(tessb200_host_block, seconds)); return 0; }''')
+    exe = tmp_path / "szh"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [C.sizeof(host_tess.HostBlock), host_tess.HostBlock.particles.offset, host_tess.HostBlock.seconds.offset]
 
 
 def test_struct_layouts_match_the_header(tmp_path):

@@ -172,6 +172,19 @@ def test_long_rows(ctx, port):
             compare_dense(res, o, f"long rows {name} alg {alg}")
 
 
+def test_dense_on_native_tess_blocks(ctx, port):
+    # blocks from the C++ tess() driver and its own Delaunay engine (include/tess_b200_host.h): the GPU
+    # and the oracle take the same tets, so the bar is bit equality as everywhere else
+    from tess2_b200 import host_tess
+    from tess2_b200.harness import particles, decomp
+    dom = ([0, 0, 0], [19, 19, 19])
+    p = particles.clustered_particles(20 ** 3, *dom, seed=12)
+    b, own = decomp.kdtree_blocks(p, *dom, 4)
+    blocks = host_tess.tess(p, own, b, *dom)
+    for alg in (0, 1):
+        compare_dense(run_gpu(ctx, blocks, (40, 40, 40), alg=alg), port.dense(blocks, (40, 40, 40), alg=alg), f"native tess alg {alg}")
+
+
 def test_edge_cases(ctx):
     import tess2_b200
     # a block with particles but no tets, next to a normal block: nothing deposits from it

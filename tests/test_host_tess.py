@@ -1,0 +1,114 @@
+"""Host side of the tessellation stage: the C++ tess() driver and its Delaunay
+engine (include/tess_b200_host.h).  CPU tests: the engine against SciPy's Qhull ('Qt', the options
+of src/tess-qhull.c:46) -- for points in general position the Delaunay triangulation is unique, so
+the tets must be the same SETS; the driver against the Python/SciPy harness block by block; the
+dense oracle on the driver's blocks against the oracle on the harness's blocks (same triangulation,
+different tet numbering: the fp32 tolerance north_star states)."""
+import numpy as np
+import pytest
+
+from tess2_b200 import host_tess
+from tess2_b200.harness import particles, decomp, delaunay
+
+
+def tet_set(tets):
+    return set(map(tuple, np.sort(np.asarray(tets)[:, :4], axis=1)))
+
+
+def check_adjacency(tets, limit=4000):
+    v, nb = tets[:, :4], tets[:, 4:]
+    for t in range(min(len(tets), limit)):
+        for i in range(4):
+            u = nb[t, i]
+            if u < 0:
+                continue
+            face = set(v[t]) - {v[t, i]}
+            assert face <= set(v[u])
+            j = [k for k in range(4) if v[u, k] not in face]
+            assert len(j) == 1 and nb[u, j[0]] == t
+
+
+def signed_volumes(p, t):
+    a, b, c, d = [p[t[:, i]].astype(np.float64) for i in range(4)]
+    return np.einsum("ij,ij->i", np.cross(a - d, b - d), c - d) / 6.0
+
+
+@pytest.mark.parametrize("kind,n", [("uniform", 50), ("uniform", 3000), ("clustered", 3000), ("gen_particles", 4096)])
+def test_engine_matches_qhull(kind, n):
+    from scipy.spatial import Delaunay
+    dom = ([0, 0, 0], [15, 15, 15])
+    if kind == "uniform":
+        p = particles.uniform_particles(n, *dom, seed=n)
+    elif kind == "clustered":
+        p = particles.clustered_particles(n, *dom, seed=n)
+    else:
+        p = particles.gen_particles(0, dom[0], dom[1])
+    t = host_tess.delaunay(p)
+    q = Delaunay(p.astype(np.float64), qhull_options="Qt")
+    assert tet_set(t) == tet_set(q.simplices)
+    check_adjacency(t)
+    assert (signed_volumes(p, t[:, :4]) > 0).all()      # consistently oriented, no flat tets
+
+
+def test_engine_degenerate_inputs():
+    # a lattice (every cube cospherical): any triangulation is acceptable, it must be one
+    g = np.stack(np.meshgrid(*[np.arange(5)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    t = host_tess.delaunay(g)
+    v = signed_volumes(g, t[:, :4])
+    assert (v > 0).all() and abs(v.sum() - 64.0) < 1e-9 and len(np.unique(t[:, :4])) == len(g)
+    check_adjacency(t)
+    # exact duplicates are left out (Qhull drops them too)
+    p = np.random.default_rng(0).random((300, 3)).astype(np.float32)
+    t2 = host_tess.delaunay(np.concatenate([p, p]))
+    assert tet_set(t2[:, :4] % len(p)) == tet_set(host_tess.delaunay(p))     # either copy of a point may be the one kept
+    # nothing to tessellate: no tets, no error
+    assert len(host_tess.delaunay(np.eye(3, dtype=np.float32))) == 0
+    assert len(host_tess.delaunay(np.c_[np.random.default_rng(1).random((40, 2)), np.zeros(40)].astype(np.float32))) == 0
+    # coordinates Qhull refuses (extreme scales) still triangulate: exact predicates
+    for scale in (1e-20, np.array([1e-6, 1.0, 1e6])):
+        q = (np.random.default_rng(2).random((500, 3)) * scale).astype(np.float32)
+        t3 = host_tess.delaunay(q)
+        assert len(np.unique(t3[:, :4])) == len(q) and (signed_volumes(q, t3[:, :4]) > 0).all()
+
+
+@pytest.mark.parametrize("nblocks,kind", [(8, "regular"), (4, "kdtree")])
+def test_driver_matches_python_harness(nblocks, kind):
+    dom = ([0, 0, 0], [23, 23, 23])
+    if kind == "regular":
+        p = particles.uniform_particles(24 ** 3 // 2, *dom, seed=4)
+        b = decomp.regular_blocks(*dom, nblocks)
+        own = decomp.assign_regular(p, b)
+    else:
+        p = particles.clustered_particles(24 ** 3 // 2, *dom, seed=4)
+        b, own = decomp.kdtree_blocks(p, *dom, nblocks)
+    ref = delaunay.tessellate(p, own, b, *dom, workers=1)
+    mine = host_tess.tess(p, own, b, *dom, threads=2)
+    for r, m in zip(ref, mine):
+        assert r["gid"] == m["gid"] and r["num_orig"] == m["num_orig"]
+        assert np.array_equal(r["particles"], m["particles"])          # same ghosts, same order
+        assert tet_set(r["tets"]) == tet_set(m["tets"])
+        assert np.array_equal(m["vert_to_tet"], delaunay.fill_vert_to_tet(len(m["particles"]), m["tets"]))
+        assert np.array_equal(p[m["global_ids"]], m["particles"])
+    if kind == "regular":
+        # ownership by containment gives the same blocks
+        mine2 = host_tess.tess(p, None, b, *dom, threads=1)
+        assert all(np.array_equal(a["global_ids"], c["global_ids"]) for a, c in zip(mine, mine2))
+
+
+def test_dense_on_driver_blocks_agrees_with_qhull_blocks(port):
+    # same Delaunay triangulation, different tet numbering and vertex order: the grids agree to the
+    # fp32 tolerance north_star states (1e-5 relative) and deposit the same mass
+    dom = ([0, 0, 0], [15, 15, 15])
+    p = particles.uniform_particles(16 ** 3, *dom, seed=8)
+    b = decomp.regular_blocks(*dom, 2)
+    own = decomp.assign_regular(p, b)
+    ref = delaunay.tessellate(p, own, b, *dom, workers=1)
+    for r in ref:
+        r["vert_to_tet"] = delaunay.fill_vert_to_tet(len(r["particles"]), r["tets"])
+    mine = host_tess.tess(p, own, b, *dom, threads=1)
+    g1 = port.dense(ref, (32, 32, 32))["grid"]
+    g2 = port.dense(mine, (32, 32, 32))["grid"]
+    scale = np.abs(g1).max()
+    close = np.abs(g1 - g2) <= 1e-5 * np.maximum(np.abs(g1), 1e-3 * scale)
+    assert close.mean() > 0.999                      # all but tie points (a point within eps of a cell face)
+    assert abs(float(g1.astype(np.float64).sum()) - float(g2.astype(np.float64).sum())) <= 1e-5 * float(g1.astype(np.float64).sum())
