@@ -40,28 +40,32 @@ class Delaunay3
   // pts: n x 3 float32.  Returns false when fewer than 4 points in general position exist.
   bool build(const float *pts, int n, uint32_t seed = 12345u)
   {
-    p_ = pts;
     n_ = n;
     tets_.clear(); free_.clear(); mark_.clear();
     if (n < 4) return false;
-    std::vector<int> order;
-    insertion_order(order, seed);
+    p_ = pts;
+    insertion_order(order_, seed);
+    // work on a copy of the points in insertion order (internal id = rank in the order): the vertices of
+    // the tets around the point being inserted then sit close together in memory
+    sorted_.resize(3 * (size_t)n);
+    for (int i = 0; i < n; i++) memcpy(&sorted_[3 * (size_t)i], pts + 3 * (size_t)order_[i], 12);
+    p_ = sorted_.data();
+    tets_.reserve(7 * (size_t)n + 64);
+    mark_.reserve(7 * (size_t)n + 64);
     // first tet: four points in general position, taken from the front of the order
-    int i0 = order[0], i1 = -1, i2 = -1, i3 = -1;
-    size_t k = 1;
-    for (; k < order.size(); k++) if (!same_point(i0, order[k])) { i1 = order[k]; break; }
+    int i0 = 0, i1 = -1, i2 = -1, i3 = -1;
+    for (int k = 1; k < n; k++) if (!same_point(i0, k)) { i1 = k; break; }
     if (i1 < 0) return false;
-    for (k = 1; k < order.size(); k++) if (order[k] != i1 && !collinear(i0, i1, order[k])) { i2 = order[k]; break; }
+    for (int k = 1; k < n; k++) if (k != i1 && !collinear(i0, i1, k)) { i2 = k; break; }
     if (i2 < 0) return false;
-    for (k = 1; k < order.size(); k++)
-      if (order[k] != i1 && order[k] != i2 && orient3d(P(i0), P(i1), P(i2), P(order[k])) != 0) { i3 = order[k]; break; }
+    for (int k = 1; k < n; k++)
+      if (k != i1 && k != i2 && orient3d(P(i0), P(i1), P(i2), P(k)) != 0) { i3 = k; break; }
     if (i3 < 0) return false;
+    const int seed4[4] = {i0, i1, i2, i3};
     if (orient3d(P(i0), P(i1), P(i2), P(i3)) < 0) std::swap(i0, i1);
     first_tet(i0, i1, i2, i3);
-    std::vector<char> used(n, 0);
-    used[i0] = used[i1] = used[i2] = used[i3] = 1;
-    for (int id : order) {
-      if (used[id]) continue;
+    for (int id = 0; id < n; id++) {
+      if (id == seed4[0] || id == seed4[1] || id == seed4[2] || id == seed4[3]) continue;
       insert(id);
     }
     return true;
@@ -79,7 +83,7 @@ class Delaunay3
       if (newid[t] < 0) continue;
       int *o = &out[(size_t)newid[t] * 8];
       for (int i = 0; i < 4; i++) {
-        o[i] = tets_[t].v[i];
+        o[i] = order_[tets_[t].v[i]];          // back to the caller's numbering
         o[4 + i] = newid[tets_[t].n[i]];
       }
     }
@@ -91,6 +95,8 @@ class Delaunay3
  private:
   const float *p_ = nullptr;
   int n_ = 0;
+  std::vector<int> order_;           // internal id -> index in the caller's array
+  std::vector<float> sorted_;        // the points in insertion order
   std::vector<Tet> tets_;
   std::vector<int> free_;
   std::vector<uint32_t> mark_;       // per tet: epoch * 2 + conflict bit of the current insertion
