@@ -54,6 +54,17 @@ int tessb200_host_tess(int num_particles, const float *particles, const int *own
                        float max_growth, int num_threads, tessb200_host_block *blocks_out);
 void tessb200_host_free_block(tessb200_host_block *b);
 
+/* Block decompositions (the reference delegates both to DIY: RegularDecomposer,
+ * examples/tess-dense/main.cpp:190-195, and diy::kdtree, src/tess-kdtree.cpp:83-107; DIY is not
+ * vendored, so the split positions are this repo's: SURVEY 8(c) "parity unpinned").
+ * bounds_out: [6 * nblocks] min xyz, max xyz of block gid = index.
+ *   regular: nblocks factored as evenly as possible (8 -> 2x2x2, 64 -> 4x4x4), gid x-fastest.
+ *   kdtree : nblocks a power of two; exact-median splits cycling x, y, z per level;
+ *            owner_out [num_particles] receives the gid of every particle (may be NULL). */
+int tessb200_host_regular_blocks(const float *domain_min, const float *domain_max, int nblocks, float *bounds_out);
+int tessb200_host_kdtree_blocks(int num_particles, const float *particles, const float *domain_min, const float *domain_max, int nblocks,
+                                float *bounds_out, int *owner_out);
+
 void tessb200_host_free(void *p);
 const char *tessb200_host_last_error(void);
 

@@ -248,3 +248,80 @@ extern "C" void tessb200_host_free_block(tessb200_host_block *b)
   free(b->particles); free(b->tets); free(b->vert_to_tet); free(b->global_ids);
   b->particles = nullptr; b->tets = nullptr; b->vert_to_tet = nullptr; b->global_ids = nullptr;
 }
+
+// ---- decompositions -----------------------------------------------------------------------------------
+#include <algorithm>
+#include <numeric>
+
+extern "C" int tessb200_host_regular_blocks(const float *domain_min, const float *domain_max, int nblocks, float *bounds_out)
+{
+  if (!domain_min || !domain_max || !bounds_out || nblocks < 1) { g_err = "bad argument"; return -1; }
+  // factor nblocks as evenly as possible: largest prime factors first onto the smallest dimension
+  int dims[3] = {1, 1, 1};
+  std::vector<int> factors;
+  for (int n = nblocks, f = 2; n > 1; f++)
+    while (n % f == 0) { factors.push_back(f); n /= f; }
+  std::sort(factors.rbegin(), factors.rend());
+  for (int f : factors) *std::min_element(dims, dims + 3) *= f;
+  std::sort(dims, dims + 3, std::greater<int>());
+  int gid = 0;
+  for (int k = 0; k < dims[2]; k++)
+    for (int j = 0; j < dims[1]; j++)
+      for (int i = 0; i < dims[0]; i++, gid++) {
+        const int c[3] = {i, j, k};
+        for (int d = 0; d < 3; d++) {
+          const float lo = domain_min[d], ext = domain_max[d] - domain_min[d];
+          bounds_out[6 * gid + d] = lo + ext * (float)c[d] / (float)dims[d];
+          bounds_out[6 * gid + 3 + d] = c[d] == dims[d] - 1 ? domain_max[d] : lo + ext * (float)(c[d] + 1) / (float)dims[d];
+        }
+      }
+  return 0;
+}
+
+extern "C" int tessb200_host_kdtree_blocks(int num_particles, const float *particles, const float *domain_min, const float *domain_max, int nblocks,
+                                           float *bounds_out, int *owner_out)
+{
+  if (!particles || !domain_min || !domain_max || !bounds_out || nblocks < 1 || (nblocks & (nblocks - 1)) || num_particles < 0) {
+    g_err = "bad argument (nblocks must be a power of two)";
+    return -1;
+  }
+  struct Box { float mn[3], mx[3]; std::vector<int> idx; };
+  std::vector<Box> boxes(1);
+  for (int d = 0; d < 3; d++) { boxes[0].mn[d] = domain_min[d]; boxes[0].mx[d] = domain_max[d]; }
+  boxes[0].idx.resize(num_particles);
+  std::iota(boxes[0].idx.begin(), boxes[0].idx.end(), 0);
+  std::vector<float> x;
+  for (int level = 0; (int)boxes.size() < nblocks; level++) {
+    const int d = level % 3;
+    std::vector<Box> next;
+    next.reserve(boxes.size() * 2);
+    for (Box &b : boxes) {
+      float split;
+      const size_t n = b.idx.size();
+      if (n >= 2) {
+        x.resize(n);
+        for (size_t i = 0; i < n; i++) x[i] = particles[3 * (size_t)b.idx[i] + d];
+        const size_t m = n / 2;
+        std::nth_element(x.begin(), x.begin() + m, x.end());
+        const float hi = x[m], lo = *std::max_element(x.begin(), x.begin() + m);
+        split = (float)(((double)lo + (double)hi) * 0.5);
+        if (!(lo < split && split < hi)) split = hi;
+      } else {
+        split = (float)(((double)b.mn[d] + (double)b.mx[d]) * 0.5);
+      }
+      Box l, r;
+      memcpy(l.mn, b.mn, 12); memcpy(l.mx, b.mx, 12); memcpy(r.mn, b.mn, 12); memcpy(r.mx, b.mx, 12);
+      l.mx[d] = split; r.mn[d] = split;
+      for (int id : b.idx) (particles[3 * (size_t)id + d] < split ? l.idx : r.idx).push_back(id);
+      next.push_back(std::move(l));
+      next.push_back(std::move(r));
+    }
+    boxes.swap(next);
+  }
+  for (int g = 0; g < nblocks; g++) {
+    memcpy(bounds_out + 6 * g, boxes[g].mn, 12);
+    memcpy(bounds_out + 6 * g + 3, boxes[g].mx, 12);
+    if (owner_out) for (int id : boxes[g].idx) owner_out[id] = g;
+  }
+  return 0;
+}

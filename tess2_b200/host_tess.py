@@ -22,7 +22,8 @@ class HostBlock(C.Structure):
     ]
 
 
-EXPORTS = ["tessb200_host_delaunay", "tessb200_host_tess", "tessb200_host_free_block", "tessb200_host_free", "tessb200_host_last_error"]
+EXPORTS = ["tessb200_host_delaunay", "tessb200_host_tess", "tessb200_host_free_block", "tessb200_host_free", "tessb200_host_last_error",
+           "tessb200_host_regular_blocks", "tessb200_host_kdtree_blocks"]
 
 
 def load():
@@ -37,6 +38,9 @@ def load():
                                            C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_int, C.c_float,
                                            C.c_int, C.POINTER(HostBlock)]
         lib.tessb200_host_free_block.argtypes = [C.POINTER(HostBlock)]
+        lib.tessb200_host_regular_blocks.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float)]
+        lib.tessb200_host_kdtree_blocks.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                                                    C.POINTER(C.c_float), C.POINTER(C.c_int)]
         lib.tessb200_host_free.argtypes = [C.c_void_p]
         lib.tessb200_host_last_error.restype = C.c_char_p
         _lib = lib
@@ -93,3 +97,31 @@ def tess(points, owner, bounds, domain_min, domain_max, margin0=0.0, threads=0, 
             margin=b.ghost_margin, rounds=b.rounds, seconds=b.seconds))
         lib.tessb200_host_free_block(C.byref(b))
     return out
+
+
+def _bounds_list(bb):
+    return [(bb[g, :3].copy(), bb[g, 3:].copy()) for g in range(len(bb))]
+
+
+def regular_blocks(domain_min, domain_max, nblocks):
+    """[(min[3], max[3])] of a regular decomposition, gid x-fastest."""
+    lib = load()
+    dmin = np.ascontiguousarray(domain_min, dtype=np.float32)
+    dmax = np.ascontiguousarray(domain_max, dtype=np.float32)
+    bb = np.zeros((nblocks, 6), np.float32)
+    if lib.tessb200_host_regular_blocks(_fp(dmin), _fp(dmax), nblocks, _fp(bb)):
+        raise RuntimeError(lib.tessb200_host_last_error().decode())
+    return _bounds_list(bb)
+
+
+def kdtree_blocks(points, domain_min, domain_max, nblocks):
+    """(bounds list, owner gid per particle) of a median kd-tree decomposition."""
+    lib = load()
+    p = np.ascontiguousarray(points, dtype=np.float32)
+    dmin = np.ascontiguousarray(domain_min, dtype=np.float32)
+    dmax = np.ascontiguousarray(domain_max, dtype=np.float32)
+    bb = np.zeros((nblocks, 6), np.float32)
+    owner = np.zeros(len(p), np.int32)
+    if lib.tessb200_host_kdtree_blocks(len(p), _fp(p), _fp(dmin), _fp(dmax), nblocks, _fp(bb), owner.ctypes.data_as(C.POINTER(C.c_int))):
+        raise RuntimeError(lib.tessb200_host_last_error().decode())
+    return _bounds_list(bb), owner

@@ -112,3 +112,19 @@ def test_dense_on_driver_blocks_agrees_with_qhull_blocks(port):
     close = np.abs(g1 - g2) <= 1e-5 * np.maximum(np.abs(g1), 1e-3 * scale)
     assert close.mean() > 0.999                      # all but tie points (a point within eps of a cell face)
     assert abs(float(g1.astype(np.float64).sum()) - float(g2.astype(np.float64).sum())) <= 1e-5 * float(g1.astype(np.float64).sum())
+
+
+def test_decompositions_match_the_python_harness():
+    dom = ([0, 0, 0], [31, 47, 15])
+    for nb in (1, 2, 8, 12, 64):
+        for (m1, x1), (m2, x2) in zip(decomp.regular_blocks(*dom, nb), host_tess.regular_blocks(*dom, nb)):
+            assert np.array_equal(m1, m2) and np.array_equal(x1, x2)
+    p = particles.clustered_particles(20000, *dom, seed=3)
+    for nb in (1, 2, 8, 32):
+        b1, o1 = decomp.kdtree_blocks(p, *dom, nb)
+        b2, o2 = host_tess.kdtree_blocks(p, *dom, nb)
+        assert np.array_equal(o1, o2)
+        for (m1, x1), (m2, x2) in zip(b1, b2):
+            assert np.array_equal(m1, m2) and np.array_equal(x1, x2)
+    with pytest.raises(RuntimeError):
+        host_tess.kdtree_blocks(p, *dom, 6)
