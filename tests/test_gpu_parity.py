@@ -185,6 +185,33 @@ def test_dense_on_native_tess_blocks(ctx, port):
         compare_dense(run_gpu(ctx, blocks, (40, 40, 40), alg=alg), port.dense(blocks, (40, 40, 40), alg=alg), f"native tess alg {alg}")
 
 
+@pytest.mark.parametrize("kd", [0, 1])
+def test_c_example_end_to_end(ctx, port, tmp_path, kd):
+    # examples/tess_dense.c: particles -> decomposition -> tess -> dense -> raw file through the two C ABIs only
+    import subprocess
+    from tess2_b200 import host_tess
+    from tess2_b200.harness import particles
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "tess_dense"
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), "-o", str(exe), os.path.join(root, "examples", "tess_dense.c"),
+                    "-L", os.path.join(root, "tess2_b200"), "-ltess_b200", "-ltess_b200_host", "-Wl,-rpath," + os.path.join(root, "tess2_b200")], check=True)
+    raw = tmp_path / "dense.raw"
+    out = subprocess.run([str(exe), "12", "8", "40", str(raw), "0", "0", str(kd)], check=True, capture_output=True, text=True).stdout
+    assert "total mass" in out
+    # the same pipeline from Python, checked against the oracle on the same blocks
+    dom = ([0, 0, 0], [23, 23, 23])
+    bounds = host_tess.regular_blocks(*dom, 8)
+    ps = [particles.gen_particles(g, mn, mx) for g, (mn, mx) in enumerate(bounds)]
+    p = np.concatenate(ps)
+    own = np.concatenate([np.full(len(q), g, np.int32) for g, q in enumerate(ps)])
+    if kd:
+        bounds, own = host_tess.kdtree_blocks(p, *dom, 8)
+    blocks = host_tess.tess(p, own, bounds, *dom)
+    o = port.dense(blocks, (40, 40, 40))
+    got = np.fromfile(raw, dtype=np.float32).reshape(40, 40, 40)
+    assert_same_bits(got, o["grid"], "C example dense.raw")
+
+
 def test_edge_cases(ctx):
     import tess2_b200
     # a block with particles but no tets, next to a normal block: nothing deposits from it
