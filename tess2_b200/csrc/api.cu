@@ -203,7 +203,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   CU(cudaMallocHost(&c->h_max, sizeof(float) * 1024));
   for (auto &ev : c->ev) CU(cudaEventCreate(&ev));
   CU(cudaFuncSetAttribute(k_cell_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM));
-  CU(cudaFuncSetAttribute(k_cell_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BFS_SMEM));
   CU(cudaFuncSetAttribute(k_cell_volumes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOL_SMEM));
   CU(cudaFuncSetAttribute(k_cell_nbrs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NBRS_SMEM));
   CU(cudaFuncSetAttribute(k_vertex_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
@@ -842,7 +842,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       for (int k = k0; k < k1; k++) gtets += c->blocks[k]->num_tets;
       TRY(c->pre_hdr.ensure(sizeof(CellHdr) * n_slots));
       TRY(c->cand.ensure(sizeof(int2) * n_slots * TOPO_CAND_CAP));
-      k_cell_bfs<<<gctas, TOPO_THREADS, TOPO_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to,
+      k_cell_bfs<<<gctas, TOPO_THREADS, BFS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to,
                                                         c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
       if (timed) CU(cudaEventRecord(c->ev[11], s));
       trace_mark(c, "bfs");

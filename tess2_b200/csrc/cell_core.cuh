@@ -553,6 +553,117 @@ TB_HD int walk_edge_link_rec(int s_c, int s_u, int ut, const WalkRec *walk, Visi
   return -1;
 }
 
+// ---- the same BFS on walk records ------------------------------------------------------------------
+// k_cell_bfs' version: one 32-byte WalkRec per popped tet (neighbours, circumcenter, slot
+// permutation) instead of the tet record and the circumcenter (48 bytes), and no vertex compares:
+// a queue entry carries, in the bits above the tet number, the slot of the site in that tet and
+// the slot facing the BFS parent, both derived from the popping tet's permutation word when the
+// entry is pushed.  That also retires the parent-index bytes of the workspace (272 instead of
+// 324 bytes per thread: one more CTA per SM).  Same tets in the same order, same candidates, same
+// box as star_bfs_cands (checked cell by cell in tests/emul).  Tet numbers must fit TB_STAR_TET_BITS.
+#define TB_STAR_TET_BITS 27
+#define TB_STAR_TET_MASK ((1 << TB_STAR_TET_BITS) - 1)
+
+template <class WS>
+TB_HD int vis_find_or_insert_tag(WS &ws, int key, int tag, int *count, int cap)
+{
+  unsigned h = ((unsigned)key * 0x9E3779B1u) >> 28;      // 16 buckets
+  for (int guard = 0; guard < TB_VIS_BUCKETS; guard++) {
+    const uint32_t w = ws.vis_word(h);
+    const unsigned i0 = w & 0xFFu, i1 = (w >> 8) & 0xFFu, i2 = (w >> 16) & 0xFFu, i3 = w >> 24;
+    const int e0 = ws.star(i0 == 0xFFu ? 0 : (int)i0) & TB_STAR_TET_MASK, e1 = ws.star(i1 == 0xFFu ? 0 : (int)i1) & TB_STAR_TET_MASK;
+    const int e2 = ws.star(i2 == 0xFFu ? 0 : (int)i2) & TB_STAR_TET_MASK, e3 = ws.star(i3 == 0xFFu ? 0 : (int)i3) & TB_STAR_TET_MASK;
+    const bool hit = ((i0 != 0xFFu) & (e0 == key)) | ((i1 != 0xFFu) & (e1 == key)) | ((i2 != 0xFFu) & (e2 == key)) | ((i3 != 0xFFu) & (e3 == key));
+    if (hit) return 0;
+    if (i3 == 0xFFu) {
+      if (*count >= cap) return -1;
+      const int b = i0 == 0xFFu ? 0 : (i1 == 0xFFu ? 1 : (i2 == 0xFFu ? 2 : 3));
+      ws.vis_word(h) = (w & ~(0xFFu << (8 * b))) | ((uint32_t)*count << (8 * b));
+      ws.star(*count) = key | (tag << TB_STAR_TET_BITS);
+      (*count)++;
+      return 1;
+    }
+    h = (h + 1u) & (TB_VIS_BUCKETS - 1u);
+  }
+  return -1;
+}
+
+// slots, in the neighbour across face s, of the site (at slot `is` here) and of the vertex that is not shared
+TB_HD int walk_child_tag(uint32_t perm, int s, int is)
+{
+  const uint32_t b = (perm >> (8 * s)) & 0xFFu;         // four 2-bit fields, the one for slot s itself is 0
+  const int is_n = (int)((b >> (2 * is)) & 3u);
+  const int back = 6 - (int)((b & 3u) + ((b >> 2) & 3u) + ((b >> 4) & 3u) + (b >> 6));
+  return is_n | (back << 2);
+}
+
+template <class WS, class Sink>
+TB_HD int star_bfs_rec(int site, int t0, const int4 *tets, const WalkRec *walk, WS &ws, int star_cap, int *n_star, float *cmin, float *cmax,
+                       Sink &sink)
+{
+  ws.hash_clear_vis();
+  int ns = 0, ncand = 0;
+  if (t0 > TB_STAR_TET_MASK) return CELL_OVERFLOW;
+  {
+    const int4 v = tets[2 * (size_t)t0];
+    const WalkRec r = walk[t0];
+    cmin[0] = fminf(cmin[0], r.cx); cmin[1] = fminf(cmin[1], r.cy); cmin[2] = fminf(cmin[2], r.cz);
+    cmax[0] = fmaxf(cmax[0], r.cx); cmax[1] = fmaxf(cmax[1], r.cy); cmax[2] = fmaxf(cmax[2], r.cz);
+    const int is = v.x == site ? 0 : (v.y == site ? 1 : (v.z == site ? 2 : (v.w == site ? 3 : -1)));
+    if (is < 0) return CELL_OVERFLOW;
+    vis_find_or_insert_tag(ws, t0, is, &ns, star_cap);
+    for (int q = 0; q < 3; q++) {
+      const int s = q + (q >= is ? 1 : 0);
+      sink(ncand++, tb_sel4(v.x, v.y, v.z, v.w, s), t0);
+      const int next = tb_sel4(r.nb[0], r.nb[1], r.nb[2], r.nb[3], s);
+      if (next < 0) return CELL_INCOMPLETE;
+      if (next > TB_STAR_TET_MASK) return CELL_OVERFLOW;
+      if (vis_find_or_insert_tag(ws, next, walk_child_tag(r.perm, s, is), &ns, star_cap) < 0) return CELL_OVERFLOW;
+    }
+  }
+  // software pipeline: the record of the next tet in the queue and the candidate vertex it will hand
+  // over (the vertex opposite its parent face) are loaded one visit ahead
+  WalkRec r_n;
+  r_n.nb[0] = r_n.nb[1] = r_n.nb[2] = r_n.nb[3] = 0; r_n.cx = r_n.cy = r_n.cz = 0.0f; r_n.perm = 0;
+  int u_n = 0;
+  bool have_n = false;
+  const int *verts = reinterpret_cast<const int *>(tets);
+  if (ns > 1) {
+    const int e1 = ws.star(1);
+    r_n = walk[e1 & TB_STAR_TET_MASK];
+    u_n = verts[8 * (size_t)(e1 & TB_STAR_TET_MASK) + ((e1 >> (TB_STAR_TET_BITS + 2)) & 3)];
+    have_n = true;
+  }
+  for (int head = 1; head < ns; head++) {
+    const int e = ws.star(head);
+    const int t = e & TB_STAR_TET_MASK, is = (e >> TB_STAR_TET_BITS) & 3, ip = (e >> (TB_STAR_TET_BITS + 2)) & 3;
+    const WalkRec r = have_n ? r_n : walk[t];
+    const int u = have_n ? u_n : verts[8 * (size_t)t + ip];
+    have_n = head + 1 < ns;
+    if (have_n) {
+      const int e1 = ws.star(head + 1);
+      r_n = walk[e1 & TB_STAR_TET_MASK];
+      u_n = verts[8 * (size_t)(e1 & TB_STAR_TET_MASK) + ((e1 >> (TB_STAR_TET_BITS + 2)) & 3)];
+    }
+    cmin[0] = fminf(cmin[0], r.cx); cmin[1] = fminf(cmin[1], r.cy); cmin[2] = fminf(cmin[2], r.cz);
+    cmax[0] = fmaxf(cmax[0], r.cx); cmax[1] = fmaxf(cmax[1], r.cy); cmax[2] = fmaxf(cmax[2], r.cz);
+    if (is == ip) return CELL_OVERFLOW;        // inconsistent adjacency: the general walk decides
+    // the vertex opposite the parent face is the only one that can be a new neighbour
+    sink(ncand++, u, t);
+    unsigned m = 0xFu & ~(1u << is) & ~(1u << ip);
+    const int s1 = tb_ffs(m) - 1;
+    m &= m - 1u;
+    const int s2 = tb_ffs(m) - 1;
+    const int n1 = tb_sel4(r.nb[0], r.nb[1], r.nb[2], r.nb[3], s1), n2 = tb_sel4(r.nb[0], r.nb[1], r.nb[2], r.nb[3], s2);
+    if (n1 < 0 || n2 < 0) return CELL_INCOMPLETE;
+    if ((n1 | n2) > TB_STAR_TET_MASK) return CELL_OVERFLOW;
+    if (vis_find_or_insert_tag(ws, n1, walk_child_tag(r.perm, s1, is), &ns, star_cap) < 0) return CELL_OVERFLOW;
+    if (vis_find_or_insert_tag(ws, n2, walk_child_tag(r.perm, s2, is), &ns, star_cap) < 0) return CELL_OVERFLOW;
+  }
+  *n_star = ns;
+  return CELL_OK;
+}
+
 // One Voronoi face for the dense stage (src/dense.cpp:682-735): circumcenters around the edge ->
 // Newell normal, first vertex, running bbox.
 struct FaceAccum

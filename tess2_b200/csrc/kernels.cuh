@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ 
 // Shared-memory workspaces of the fast topology kernels: word w of a thread lives at
 // base[w * STRIDE] (stride = threads per CTA, so a warp touching the same word index hits 32
 // distinct banks).
-//   StarWS (k_cell_bfs):  star[52] | parent_idx bytes[13 words] | vis buckets[16 words] = 81 words = 324 B
+//   StarRecWS (k_cell_bfs):    star[52] (tet | site slot | parent slot) | vis buckets[16 words]    = 68 words = 272 B
+//   StarWS (k_vertex_density): star[52] | parent_idx bytes[13 words] | vis buckets[16 words]       = 81 words = 324 B
 //   NbrWS  (k_cell_nbrs): nu[36] | nt[36] | nbr buckets[16 words]                      = 88 words = 352 B
 template <int STRIDE>
 struct StarWS
@@ -241,7 +242,21 @@ struct DynStridedWS
 constexpr int TOPO_THREADS = 128;
 constexpr int TOPO_STAR_CAP = 52;
 constexpr int TOPO_NBR_CAP = 36;
+template <int STRIDE>
+struct StarRecWS
+{
+  int *base;
+  static constexpr int VH = 52, WORDS = 68;
+  __device__ __forceinline__ int &star(int i) { return base[(size_t)i * STRIDE]; }
+  __device__ __forceinline__ uint32_t &vis_word(unsigned h) { return reinterpret_cast<uint32_t *>(base)[(size_t)(VH + (int)h) * STRIDE]; }
+  __device__ __forceinline__ void hash_clear_vis()
+  {
+#pragma unroll
+    for (int w = VH; w < WORDS; w++) base[(size_t)w * STRIDE] = -1;
+  }
+};
 constexpr size_t TOPO_SMEM = (size_t)StarWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
+constexpr size_t BFS_SMEM = (size_t)StarRecWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
 constexpr size_t NBRS_SMEM = (size_t)NbrWS<TOPO_THREADS>::WORDS * TOPO_THREADS * sizeof(int);
 constexpr int TOPO_CAND_CAP = TOPO_STAR_CAP + 2;   // candidates per cell: 3 at the root + 1 per further star tet
 constexpr int BIG_STAR_CAP = 4096;
@@ -395,14 +410,14 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__res
   const int slot_in_blk = (int)(blockIdx.x - blk.cta_start) * TOPO_THREADS + (int)threadIdx.x;
   const size_t slot = (size_t)blockIdx.x * TOPO_THREADS + threadIdx.x;
   const size_t n_slots = (size_t)gridDim.x * TOPO_THREADS;
-  StarWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
+  StarRecWS<TOPO_THREADS> ws{ws_s + threadIdx.x};
   int status = -1, n_star = 0, cell = 0;
   float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
   if (slot_in_blk < blk.num_orig && blk.tets != nullptr) {
     cell = (int)blk.order[slot_in_blk];
     const int t0 = blk.v2t[cell];
     CandSink sink{cand + slot, n_slots};
-    status = t0 < 0 ? CELL_NO_TET : star_bfs_cands(cell, t0, blk.tets, blk.cc, ws, TOPO_STAR_CAP, &n_star, cmin, cmax, sink);
+    status = t0 < 0 ? CELL_NO_TET : star_bfs_rec(cell, t0, blk.tets, blk.walk, ws, TOPO_STAR_CAP, &n_star, cmin, cmax, sink);
     // A star too large for this kernel usually belongs to a cell at the edge of the data whose Voronoi
     // vertices reach beyond the data bounds: the filter of src/dense.cpp:1385-1392 drops it whatever the
     // rest of the star holds (the box only grows; the hull flag says the cell is complete), so the part seen so far decides.

@@ -75,6 +75,14 @@ struct StarHostWS
   uint32_t &vis_word(unsigned h) { return vw[h]; }
   void hash_clear_vis() { memset(vw, 0xFF, sizeof(vw)); }
 };
+struct StarRecHostWS
+{
+  int s[52];
+  uint32_t vw[16];
+  int &star(int i) { return s[i]; }
+  uint32_t &vis_word(unsigned h) { return vw[h]; }
+  void hash_clear_vis() { memset(vw, 0xFF, sizeof(vw)); }
+};
 struct NbrHostWS
 {
   int u[36], t[36];
@@ -102,7 +110,7 @@ struct Topo
   bool use_fast = true;
   int nn = 0;
   float cmin[3], cmax[3];   // bbox from the star's circumcenters (k_cell_bfs), when cc is given
-  int run(int site, int t0, const int4 *tets, const float4 *cc = nullptr)
+  int run(int site, int t0, const int4 *tets, const float4 *cc = nullptr, const WalkRec *walk = nullptr)
   {
     int ns;
     use_fast = true;
@@ -114,6 +122,20 @@ struct Topo
       NbrHostWS nw;
       CandVec cands;
       st = star_bfs_cands(site, t0, tets, cc, sw, 52, &ns, cmin, cmax, cands);
+      if (walk) {
+        // k_cell_bfs runs the walk-record version: same status, same star in the same order, same candidates, same box
+        StarRecHostWS rw;
+        CandVec rc;
+        float rmin[3] = {INFINITY, INFINITY, INFINITY}, rmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+        int rns = 0;
+        const int rst = star_bfs_rec(site, t0, tets, walk, rw, 52, &rns, rmin, rmax, rc);
+        bool same = rst == st;
+        if (same && st == CELL_OK) {
+          same = rns == ns && rc.v == cands.v && !memcmp(rmin, cmin, 12) && !memcmp(rmax, cmax, 12);
+          for (int k = 0; same && k < ns; k++) same = (rw.s[k] & TB_STAR_TET_MASK) == sw.s[k];
+        }
+        if (!same) { fprintf(stderr, "emul: record BFS differs from vertex BFS at site %d (status %d/%d, ns %d/%d)\n", site, rst, st, rns, ns); abort(); }
+      }
       if (st == CELL_OK) {
         CandRead rd{&cands.v};
         nn = nbrs_from_cands(nw, ns + 2, 36, rd);
@@ -421,7 +443,7 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
     }
     for (int cell = 0; cell < b.num_orig_particles; cell++) {
       if (v2t[cell] < 0) continue;
-      int st = tp.run(cell, v2t[cell], (const int4 *)b.tets, cc.data());
+      int st = tp.run(cell, v2t[cell], (const int4 *)b.tets, cc.data(), walk.data());
       if (st != CELL_OK) continue;
       const int nn = tp.nn;
       float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
