@@ -753,8 +753,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   sc.boxes = c->d_boxes.as<BlockBox>(); sc.nblocks = nall; sc.kl = G.kl; sc.project = G.g.project;
 
   unsigned long long span_cap = 0;
-  auto ensure_spans = [&](unsigned long long cap, unsigned long long keep) -> int {
-    (void)keep;
+  auto ensure_spans = [&](unsigned long long cap) -> int {
     for (int i = 0; i < 2; i++) {
       TRY(c->keys[i].ensure(8 * (size_t)cap));
       TRY(c->data[i].ensure(8 * (size_t)cap));
@@ -787,9 +786,9 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.faces = c->face_list.as<FaceRef>(); to.cnt = cnt;
     to.cap_pairs = fast_pairs;
     to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
-    TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells), 0));
+    TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells)));
   } else {
-    TRY(ensure_spans(std::max<unsigned long long>(1ull << 16, 8ull * (unsigned long long)cells + 1024), 0));
+    TRY(ensure_spans(std::max<unsigned long long>(1ull << 16, 8ull * (unsigned long long)cells + 1024)));
   }
 
   CU(cudaEventRecord(c->ev[3], s));
@@ -922,7 +921,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   unsigned long long n_spans = c->h_cnt->n_spans;
   if (n_spans > span_cap) {
     if (!tess) return fail(TESSB200_ECAPACITY, "span buffer overflow in CIC");
-    TRY(ensure_spans(n_spans + n_spans / 16 + 1024, 0));
+    TRY(ensure_spans(n_spans + n_spans / 16 + 1024));
     Counters z = *c->h_cnt;
     z.n_spans = 0; z.n_deposit = 0; z.n_cic_fallback = 0;
     CU(cudaMemcpyAsync(c->d_cnt.p, &z, sizeof(Counters), cudaMemcpyHostToDevice, s));

@@ -212,6 +212,25 @@ def test_c_example_end_to_end(ctx, port, tmp_path, kd):
     assert_same_bits(got, o["grid"], "C example dense.raw")
 
 
+def test_many_small_blocks(ctx, port):
+    # 128 blocks through the one-call path: more groups than the per-block event rings hold (64), blocks
+    # with a handful of cells, most deposits crossing block faces
+    from tess2_b200 import host_tess
+    from tess2_b200.harness import particles
+    dom = ([0, 0, 0], [15, 15, 15])
+    p = particles.uniform_particles(16 ** 3, *dom, seed=21)
+    bounds = host_tess.regular_blocks(*dom, 128)
+    blocks = host_tess.tess(p, None, bounds, *dom)
+    assert len(blocks) == 128
+    o = port.dense(blocks, (32, 32, 32))
+    compare_dense(run_gpu(ctx, blocks, (32, 32, 32)), o, "128 blocks, one call")
+    ctx.upload(blocks)
+    params = ctx.make_params(0, 0, None, None, False, (0.0, 0.0, 1.0), 1.0, 1e-4, (32, 32, 32))
+    ctx.run(params)
+    res = ctx.download(params)
+    assert_same_bits(res.grid, o["grid"], "128 blocks, resident")
+
+
 def test_edge_cases(ctx):
     import tess2_b200
     # a block with particles but no tets, next to a normal block: nothing deposits from it
