@@ -346,6 +346,15 @@ def run_ours(args, rank, world, local_rank):
     stage_ms = {"k_circumcenters": stage["ms_circumcenters"], "k_cell_bfs": stage["ms_bfs"], "k_cell_nbrs": stage["ms_nbrs"],
                 "k_cell_faces": stage["ms_faces"], "k_cell_scan": stage["ms_scan"],
                 "sort (cub radix, 64-bit key + 64-bit payload)": stage["ms_sort"], "k_rows": stage["ms_deposit"]}
+    n_shared = int(st.num_shared_deposits)
+    if n_shared >= 0:
+        # 3-D runs: deposits that are alone on their grid point are written directly, only the shared ones are sorted
+        del stage_ms["sort (cub radix, 64-bit key + 64-bit payload)"], stage_ms["k_rows"]
+        del alg_bytes["sort (cub radix, 64-bit key + 64-bit payload)"], alg_bytes["k_rows"]
+        stage_ms["k_span_count + k_span_place"] = stage["ms_sort"]
+        alg_bytes["k_span_count + k_span_place"] = 2 * 16 * spans + 3 * 4 * G_local      # records read twice; count grid cleared + grid cleared and written
+        stage_ms["sort + k_rows of the shared grid points"] = stage["ms_deposit"]
+        alg_bytes["sort + k_rows of the shared grid points"] = 3 * 16 * n_shared
     stage_ms["nccl span exchange"] = stage["ms_exchange"]
     alg_bytes["nccl span exchange"] = 0
     # oversized stars / index boxes (k_cell_bfs_big, k_cell_scan_big and their faces), run once after the fast kernels
@@ -399,7 +408,7 @@ def run_ours(args, rank, world, local_rank):
                           "tess_plus_dense_seconds": (host_tess["seconds"] + e2e_ms * 1e-3) if host_tess.get("seconds") else None,
                           "native": native_tess,
                           "native_tess_plus_dense_seconds": (native_tess["seconds"] + e2e_ms * 1e-3) if native_tess else None},
-            "stats": {"cells": cells_local, "tets": T_local, "particles_with_ghosts": P_local, "grid_points": G_local, "spans": spans, "faces": F, "candidates": Cn,
+            "stats": {"shared_deposits": int(st.num_shared_deposits), "cells": cells_local, "tets": T_local, "particles_with_ghosts": P_local, "grid_points": G_local, "spans": spans, "faces": F, "candidates": Cn,
                       "deposit_cells": int(st.num_deposit_cells), "cic_fallback_cells": int(st.num_cic_fallback), "slow_cells": int(st.num_slow_cells),
                       "tot_mass": float(st.tot_mass)},
         }

@@ -121,6 +121,8 @@ typedef struct tessb200_dense_stats
   int64_t num_candidates;     /* candidate neighbours handed from k_cell_bfs to k_cell_nbrs */
   float ms_slow_path;         /* general BFS for oversized stars + per-CTA scan of oversized cells (after the fast kernels) */
   float reserved0;
+  int64_t num_shared_deposits; /* deposits that met another one on their grid point and went through the ordered path;
+                                  -1 when every record did (projection, or more shared deposits than the buffer holds) */
 } tessb200_dense_stats;
 
 typedef struct tessb200_ctx tessb200_ctx;

@@ -163,7 +163,7 @@ struct tessb200_ctx
   ncclComm_t comm = nullptr;
 #endif
   Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, pre_hdr, cand, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
-  Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2], x_small;
+  Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2], x_small, pt_count;
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
@@ -228,7 +228,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   free_blocks(c);
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->pre_hdr, &c->cand, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
-                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small};
+                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small, &c->pt_count};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -940,50 +940,99 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   CU(cudaEventRecord(c->ev[6], s));
 
   int cur = 0;
+  long long n_shared_stat = -1;     // deposits that met another one on their grid point (-1: the full-sort path ran)
 #ifdef TESSB200_WITH_NCCL
   if (c->nranks > 1) TRY(exchange_spans(c, G, cur, &n_spans));
 #endif
   CU(cudaEventRecord(c->ev[7], s));
 
-  // sort by (row, remote, cell, z)
-  if (n_spans) {
-    if (n_spans > 0x7fffffffull) return fail(TESSB200_ELIMIT, "%llu span records exceed the sorter's 2^31 limit", n_spans);
+  TRY(c->row_start.ensure(8 * (size_t)(G.nrows + 2)));
+  TRY(c->out.ensure(sizeof(float) * (size_t)std::max<long long>(4, G.out_floats)));
+  if (n_spans > 0x7fffffffull) return fail(TESSB200_ELIMIT, "%llu span records exceed the sorter's 2^31 limit", n_spans);
+  // sort by (row, remote, cell, z) the records in (keys, data)[cur]
+  auto sort_records = [&](unsigned long long n) -> int {
+    if (!n) return 0;
     size_t tmp_bytes = 0;
     cub::DoubleBuffer<uint64_t> dk(c->keys[cur].as<uint64_t>(), c->keys[cur ^ 1].as<uint64_t>());
     cub::DoubleBuffer<uint64_t> dv(c->data[cur].as<uint64_t>(), c->data[cur ^ 1].as<uint64_t>());
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n_spans, 0, G.key_bits, s));
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, G.key_bits, s));
     TRY(c->cub_tmp.ensure(tmp_bytes));
-    CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n_spans, 0, G.key_bits, s));
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp_bytes, dk, dv, (int)n, 0, G.key_bits, s));
     if (dk.Current() != c->keys[cur].as<uint64_t>()) cur ^= 1;
     if (dv.Current() != c->data[cur].as<uint64_t>()) return fail(TESSB200_ECUDA, "sorter returned mismatched buffers");
-  }
-  CU(cudaEventRecord(c->ev[8], s));
+    return 0;
+  };
+  // one row buffer per warp; long rows (up to 32767 points) leave room for fewer warps per CTA
+  int rw = ROWS_WARPS;
+  while (rw > 1 && sizeof(float) * (size_t)rw * (size_t)G.nx_max > 160 * 1024) rw--;
+  const size_t rows_smem = sizeof(float) * (size_t)rw * (size_t)G.nx_max;
+  if (rows_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+  auto copy_out_all = [&]() -> int {
+    for (int k = 0; k < nloc; k++) {
+      BlockRes *b = c->blocks[k];
+      CU(cudaEventRecord(c->blk_ev[k % 64], s));
+      CU(cudaStreamWaitEvent(c->copy_stream, c->blk_ev[k % 64], 0));
+      tessb200_block *ob = nullptr;
+      for (int j = 0; j < io.nblocks_out; j++) if (io.out_blocks[j].gid == b->gid) ob = &io.out_blocks[j];
+      TRY(copy_block_out(c, *p, b, ob, io.global_grid, c->copy_stream));
+    }
+    return 0;
+  };
 
-  // deposit: every grid point written exactly once
-  TRY(c->row_start.ensure(8 * (size_t)(G.nrows + 2)));
-  TRY(c->out.ensure(sizeof(float) * (size_t)std::max<long long>(4, G.out_floats)));
-  k_row_starts<<<cdiv((long long)n_spans + 1, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows,
-                                                                 c->row_start.as<unsigned long long>());
-  COUNT_LAUNCH(c, 1);
-  {
-    // one row buffer per warp; long rows (up to 32767 points) leave room for fewer warps per CTA
-    int rw = ROWS_WARPS;
-    while (rw > 1 && sizeof(float) * (size_t)rw * (size_t)G.nx_max > 160 * 1024) rw--;
-    size_t smem = sizeof(float) * (size_t)rw * (size_t)G.nx_max;
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // 3-D runs: only the deposits that meet on a grid point go through the sort (kernels.cuh, "K3b without the big sort")
+  bool placed = false;
+  if (!G.g.project && n_spans && G.out_floats) {
+    const unsigned long long shared_cap = span_cap;                 // the second half of the double buffer
+    TRY(c->pt_count.ensure(sizeof(unsigned int) * (size_t)G.out_floats));
+    CU(cudaMemsetAsync(c->pt_count.p, 0, sizeof(unsigned int) * (size_t)G.out_floats, s));
+    CU(cudaMemsetAsync(c->out.p, 0, sizeof(float) * (size_t)G.out_floats, s));
+    CU(cudaMemsetAsync(&cnt->n_shared, 0, sizeof(unsigned long long), s));
+    const unsigned grid = cdiv((long long)n_spans, 256);
+    k_span_count<<<grid, 256, 0, s>>>(c->keys[cur].as<uint64_t>(), c->data[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->d_rblocks.as<RowBlock>(),
+                                      (int)G.rblocks.size(), c->pt_count.as<unsigned int>());
+    k_span_place<<<grid, 256, 0, s>>>(c->keys[cur].as<uint64_t>(), c->data[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->d_rblocks.as<RowBlock>(),
+                                      (int)G.rblocks.size(), c->pt_count.as<unsigned int>(), G.g.div, c->out.as<float>(), c->keys[cur ^ 1].as<uint64_t>(),
+                                      c->data[cur ^ 1].as<uint64_t>(), shared_cap, &cnt->n_shared);
+    COUNT_LAUNCH(c, 2);
+    CU(cudaGetLastError());
+    TRY(read_counters(c));
+    const unsigned long long n_shared = c->h_cnt->n_shared;
+    if (n_shared <= shared_cap && n_shared <= 0x7fffffffull) {
+      placed = true;
+      CU(cudaEventRecord(c->ev[8], s));      // ms_sort (7 -> 8) is the count + place pass here; the sort of the few shared records is in ms_deposit
+      cur ^= 1;                               // the shared one-point records are the list now
+      TRY(sort_records(n_shared));
+      if (n_shared) {
+        k_row_starts<<<cdiv((long long)n_shared + 1, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n_shared, G.kl, G.row0, G.nrows, c->row_start.as<unsigned long long>());
+        k_rows<<<cdiv((long long)G.nrows, rw), rw * 32, rows_smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0, 0ull, G.nrows,
+                                                                      c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div, G.nx_max, c->out.as<float>(), 1);
+        COUNT_LAUNCH(c, 2);
+      }
+      n_shared_stat = (long long)n_shared;
+      if (io.pipelined) TRY(copy_out_all());
+    }
+    // else: more shared deposits than the buffer holds (a grid far coarser than the cells): the full sort below
+  }
+  if (!placed) {
+    TRY(sort_records(n_spans));
+    CU(cudaEventRecord(c->ev[8], s));
+    // deposit: every grid point written exactly once
+    k_row_starts<<<cdiv((long long)n_spans + 1, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows,
+                                                                   c->row_start.as<unsigned long long>());
+    COUNT_LAUNCH(c, 1);
     if (!io.pipelined) {
-      k_rows<<<cdiv((long long)G.nrows, rw), rw * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0, 0ull,
-                                                                                 G.nrows, c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div,
-                                                                                 G.nx_max, c->out.as<float>());
+      k_rows<<<cdiv((long long)G.nrows, rw), rw * 32, rows_smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0, 0ull,
+                                                                    G.nrows, c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div,
+                                                                    G.nx_max, c->out.as<float>(), 0);
       COUNT_LAUNCH(c, 1);
     } else {
       // block by block: the device-to-host copy of block k (copy stream) overlaps the deposit of block k+1
       for (int k = 0; k < nloc; k++) {
         BlockRes *b = c->blocks[k];
         if (b->nrows) {
-          k_rows<<<cdiv(b->nrows, rw), rw * 32, smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0,
-                                                                            (unsigned long long)(b->row_base - (long long)G.row0), (unsigned long long)b->nrows,
-                                                                            c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div, G.nx_max, c->out.as<float>());
+          k_rows<<<cdiv(b->nrows, rw), rw * 32, rows_smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0,
+                                                              (unsigned long long)(b->row_base - (long long)G.row0), (unsigned long long)b->nrows,
+                                                              c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div, G.nx_max, c->out.as<float>(), 0);
           COUNT_LAUNCH(c, 1);
         }
         CU(cudaEventRecord(c->blk_ev[k % 64], s));
@@ -1067,6 +1116,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     st->ms_faces = sub ? ms(13, 5) : 0;
     st->num_faces = (int64_t)c->h_cnt->plane_cursor * 2;
     st->num_candidates = (int64_t)c->h_cnt->n_cands;
+    st->num_shared_deposits = n_shared_stat;
   }
   return 0;
 }

@@ -61,6 +61,8 @@ struct Counters
   // progress marks kept on the device (k_advance): the cell kernels of a group work on what was
   // appended since the previous group, so the host never has to read a count between launches
   unsigned int pairs_done, small_done, ovf_done;
+  unsigned int pad0;
+  unsigned long long n_shared;                 // one-point records k_span_place handed to the sorted path
 };
 
 struct FaceRef;
@@ -1188,7 +1190,7 @@ constexpr int ROWS_SHORT_SPAN = 16;   // spans up to this length are applied one
 
 __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__restrict__ data, const unsigned long long *__restrict__ row_start,
                                                           unsigned long long row0, unsigned long long r_begin, unsigned long long nrows, const RowBlock *__restrict__ rblocks,
-                                                          int n_rblocks, float div, int nx_max, float *__restrict__ out)
+                                                          int n_rblocks, float div, int nx_max, float *__restrict__ out, int sparse)
 {
   // rows [r_begin, r_begin + nrows) of this GPU's row range (row ids row0 + r)
   extern __shared__ float rowbuf_all[];
@@ -1206,9 +1208,13 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__rest
   }
   RowBlock rb = rblocks[lo_b];
   int nx = rb.nx;
-  for (int x = lane; x < nx; x += 32) buf[x] = 0.0f;
-  __syncwarp();
   unsigned long long s0 = row_start[r], s1 = row_start[r + 1];
+  float *dst = out + rb.out_off + (row - rb.row_base) * (long long)nx;
+  // sparse: the row already holds the deposits that are alone on their grid point (k_span_place) and zeros
+  // where several meet; rows without a record stay as they are
+  if (sparse && s0 == s1) return;
+  for (int x = lane; x < nx; x += 32) buf[x] = sparse ? dst[x] : 0.0f;
+  __syncwarp();
   for (unsigned long long sb = s0; sb < s1; sb += 32) {
     unsigned long long mine = sb + lane < s1 ? data[sb + lane] : 0ull;
     // the quotient mass / div of the reference's accumulate step is computed once per record by
@@ -1260,8 +1266,86 @@ __global__ void __launch_bounds__(ROWS_WARPS * 32) k_rows(const uint64_t *__rest
       __syncwarp();
     }
   }
-  float *dst = out + rb.out_off + (row - rb.row_base) * (long long)nx;
   for (int x = lane; x < nx; x += 32) dst[x] = buf[x];
+}
+
+// ---- K3b without the big sort ------------------------------------------------------------------------
+// Only grid points that receive MORE THAN ONE deposit need the reference's accumulation order; a
+// point with a single deposit ends up as (float)(0 + m/div) whoever gets there.  So: count the
+// deposits per grid point (k_span_count), then write the single ones straight into the grid and
+// hand only the deposits on shared points, as one-point records with their original keys, to the
+// sorted path (k_span_place -> radix sort -> k_rows in its `sparse` form, which starts from the
+// row as it stands instead of zeros and skips rows without records).  3-D runs only: a projection
+// stacks every z onto the same point, there everything is shared and the full sort is the shorter way.
+__device__ __forceinline__ bool span_target(uint64_t key, uint64_t data, KeyLayout kl, unsigned long long row0, unsigned long long nrows,
+                                            const RowBlock *__restrict__ rblocks, int n_rblocks, long long &base, int &x0, int &x1)
+{
+  const unsigned long long row = key_row(kl, key);
+  if (row < row0 || row >= row0 + nrows) return false;        // left for another rank (sentinel key)
+  int lo_b = 0, hi_b = n_rblocks;
+  while (hi_b - lo_b > 1) {
+    const int mid = (lo_b + hi_b) >> 1;
+    if (rblocks[mid].row_base <= (long long)row) lo_b = mid; else hi_b = mid;
+  }
+  const RowBlock rb = rblocks[lo_b];
+  const unsigned lo32 = (unsigned)data;
+  x0 = (int)(lo32 & 0xffffu);
+  x1 = x0 + (int)((lo32 >> 16) & 0x7fffu);
+  if (x1 > rb.nx) x1 = rb.nx;
+  base = rb.out_off + ((long long)row - rb.row_base) * (long long)rb.nx;
+  return x1 > x0;
+}
+
+__global__ void k_span_count(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ data, unsigned long long n, KeyLayout kl,
+                             unsigned long long row0, unsigned long long nrows, const RowBlock *__restrict__ rblocks, int n_rblocks,
+                             unsigned int *__restrict__ count)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long base;
+  int x0, x1;
+  if (!span_target(keys[i], data[i], kl, row0, nrows, rblocks, n_rblocks, base, x0, x1)) return;
+  for (int x = x0; x < x1; x++) atomicAdd(&count[base + x], 1u);
+}
+
+__global__ void k_span_place(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ data, unsigned long long n, KeyLayout kl,
+                             unsigned long long row0, unsigned long long nrows, const RowBlock *__restrict__ rblocks, int n_rblocks,
+                             const unsigned int *__restrict__ count, float div, float *__restrict__ out, uint64_t *__restrict__ shared_keys,
+                             uint64_t *__restrict__ shared_data, unsigned long long shared_cap, unsigned long long *n_shared)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long base = 0;
+  int x0 = 0, x1 = 0;
+  uint64_t key = 0, d = 0;
+  bool live = false;
+  if (i < n) {
+    key = keys[i];
+    d = data[i];
+    live = span_target(key, d, kl, row0, nrows, rblocks, n_rblocks, base, x0, x1);
+  }
+  int mine = 0;
+  if (live) {
+    // double path: (float)((double)0 + (double)m / (double)div)  (src/dense.cpp:290,193); float path: 0 + m / div  (:539)
+    const float m = u2f((uint32_t)(d >> 32));
+    const float v = ((d >> 31) & 1u) ? fadd(0.0f, fdiv(m, div)) : (float)((double)0.0f + (double)m / (double)div);
+    for (int x = x0; x < x1; x++) {
+      if (count[base + x] == 1u) out[base + x] = v;
+      else mine++;
+    }
+  }
+  // deposits on shared points: one-point records, same key (row, remote, cell, z) as the span they come from
+  const unsigned long long at = warp_alloc<unsigned long long>(n_shared, (unsigned long long)mine);
+  if (mine) {
+    unsigned long long pos = at;
+    for (int x = x0; x < x1; x++) {
+      if (count[base + x] == 1u) continue;
+      if (pos < shared_cap) {
+        shared_keys[pos] = key;
+        shared_data[pos] = (d & 0xffffffff80000000ull) | (1ull << 16) | (uint64_t)(unsigned)x;
+      }
+      pos++;
+    }
+  }
 }
 
 // sum(value) in double and max(value) over a float array (dense_stats, src/dense.cpp:1298-1326)
