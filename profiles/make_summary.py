@@ -7,7 +7,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01_z"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01_zz"
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
@@ -57,18 +57,22 @@ L.append("| kernels launched in the 5 timed steps | %d |" % d["gpu_launches"])
 L.append("\n## Per kernel (CUDA events inside the library; algorithmic bytes: DESIGN.md 4; DRAM traffic from `ncu --set full`)\n")
 L.append("| kernel | ms/step | algorithmic GB/s | of measured HBM peak 6542.7 GB/s | DRAM traffic / launch | what bounds it (ncu, `%s_ncu_*.txt`) |\n|---|---:|---:|---:|---:|---|" % tag)
 why = {"k_circumcenters": "stream + gathers (4 particles, 4 neighbour records per tet); includes the Morton sort of the cell order",
-       "k_cell_bfs": "shared-memory and global latency at 18 warps/SM (324 B of workspace per thread), 16.5/32 lanes (per-cell trip counts differ)",
+       "k_cell_bfs": "latency of the dependent walk-record loads (long scoreboard 3.9 cycles per issue, L1 hit rate 30 %) at 22 warps/SM (272 B of workspace per thread), 17/32 lanes (per-cell trip counts differ)",
        "k_cell_nbrs": "global-load latency of the candidate stream",
        "k_cell_faces": "L2 sector throughput (one 32-B walk record per step)",
        "k_cell_scan": "fp32 issue (12.75 instructions per face x 32 points; 8 of them the reference's unfused fp32 operations)",
        "sort (cub radix, 64-bit key + 64-bit payload)": "library radix sort, 5 passes over 39 key bits",
        "k_rows": "per-row latency chain (72 records per row, one record per lane)",
+       "k_span_count + k_span_place": "L2 atomics / scattered 4-byte stores: 9.4 M records read twice, 17 M point updates (`k_span_count` 85 us, `k_span_place` 132 us, one host read-back)",
+       "sort + k_rows of the shared grid points": "launch-bound: 39 k one-point records (0.4 % of the deposits) through the 5-pass radix sort and the ordered row kernel",
        "slow path (oversized cells)": "latency: 854 cells with stars > 52 tets (one warp each) and the per-CTA scan of oversized index boxes"}
 for kname, v in st.items():
     if kname.startswith("nccl"):
         continue
     g = v["algorithmic_GBps"] or 0
     t = tr.get(kname)
+    if kname == "k_span_count + k_span_place":
+        t = tr.get("k_span_count", 0) + tr.get("k_span_place", 0)
     L.append("| `%s` | %.3f | %s | %s | %s | %s |" % (kname, v["ms"], ("%.0f" % g) if g else "-", ("%.3f" % (g / 6542.7)) if g else "-",
                                                     ("%.0f MB" % (t / 1e6)) if t else "-", why.get(kname, "")))
 w = d["roofline"]["whole_stage"]
@@ -90,11 +94,11 @@ if os.path.exists(c3):
     L.append("## Config 3 at full size on one GPU (`profiles/probe_clustered.py 256 8`)\n")
     L.append("256^3 = 16.8 M clustered (Gaussian-clump) particles, kd-tree 8 blocks, %.0f M tets, 512^3 grid: **%.1f ms → %.3g grid points/s, %.3g tets/s**; "
              "%d of %d cells deposit (%d of them through the CIC fallback), total mass %.2f (= depositing cells to %.1e).  Stage ms: cc %.1f, bfs %.1f, nbrs %.1f, "
-             "faces %.1f, scan %.1f, sort %.1f, rows %.1f.\n" % (c["num_tets"] / 1e6, c["ms_total_device"], c["grid_points_per_sec"], c["num_tets"] / (c["ms_total_device"] * 1e-3),
+             "faces %.1f, scan %.1f, sort %.1f, rows %.1f (measured with the full sort, before the deposit was split into single and shared grid points).\n" % (c["num_tets"] / 1e6, c["ms_total_device"], c["grid_points_per_sec"], c["num_tets"] / (c["ms_total_device"] * 1e-3),
                                                              c["num_deposit_cells"], c["num_cells"], c["num_cic_fallback"], c["tot_mass"],
                                                              abs(c["tot_mass"] - c["num_deposit_cells"]) / c["num_deposit_cells"],
                                                              c["ms_circumcenters"], c["ms_bfs"], c["ms_nbrs"], c["ms_faces"], c["ms_scan"], c["ms_sort"], c["ms_deposit"]))
-L.append("## Parity\n\n`pytest -m gpu` on a 2-GPU box: 46 passed (bit equality with the oracle everywhere, including 2-GPU runs, the drop-in\n"
+L.append("## Parity\n\n`pytest -m gpu` on a 2-GPU box: 47 passed (bit equality with the oracle everywhere, including 2-GPU runs, the drop-in\n"
          "C++ header test, blocks from the repo's own tess driver and the plain-C example); opt-in `TESSB200_BIG_TESTS=1`: 128^3 clustered\n"
          "particles, kd-tree 16 blocks, 256^3 grid, global grid bit-identical to the oracle.\n")
 open(os.path.join(P, "r01_summary.md"), "w").write("\n".join(L) + "\n")
