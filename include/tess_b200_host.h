@@ -8,6 +8,8 @@
 #ifndef TESS_B200_HOST_H
 #define TESS_B200_HOST_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -64,6 +66,45 @@ void tessb200_host_free_block(tessb200_host_block *b);
 int tessb200_host_regular_blocks(const float *domain_min, const float *domain_max, int nblocks, float *bounds_out);
 int tessb200_host_kdtree_blocks(int num_particles, const float *particles, const float *domain_min, const float *domain_max, int nblocks,
                                 float *bounds_out, int *owner_out);
+
+/* ---- the hand-off file between the stages ("del.out"), SURVEY 8(f) N3 ---------------------------------
+ * tess_save (src/tess.cpp:126-137) = diy::io::write_blocks + save_block_light (src/tess.cpp:198-221);
+ * examples/dense/main.cpp:158-161 = diy::io::read_blocks + load_block_light (src/tess.cpp:223-259).
+ * One record per block with every field load_block_light fills, in dblock_t's terms
+ * (include/tess/delaunay.h:38-63) plus DBlock's three boxes (include/tess/delaunay.hpp:18-23).
+ * The payload order is the reference's; the container (footer of {gid, offset, count}, trailing
+ * footer size) restates DIY's published block-file layout and is parity-unpinned, DIY not being
+ * vendored (tess2_b200/host/block_file.cpp has the grammar). */
+typedef struct tessb200_host_dblock {
+  int gid;
+  float bounds_min[3], bounds_max[3];   /* DBlock::bounds: local block extents */
+  float box_min[3], box_max[3];         /* DBlock::box: box of the last redistribution round */
+  float data_min[3], data_max[3];       /* DBlock::data_bounds: global data extents */
+  int num_orig_particles, num_particles;
+  float *particles;                     /* [3 * num_particles] */
+  int *rem_gids, *rem_lids;             /* [num_particles - num_orig_particles] owner block / index there of each ghost */
+  int num_grid_pts;
+  float *density;                       /* [num_grid_pts] (0 points straight after tess()) */
+  int complete;
+  int num_tets;
+  int *tets;                            /* [8 * num_tets] */
+  int *vert_to_tet;                     /* [num_particles] */
+} tessb200_host_dblock;
+
+enum {
+  TESSB200_DIY_BOUNDS_DYNAMIC = 0,      /* Bounds = {size_t 3, float[3]} x 2: DIY with run-time point dimension (`Bounds b {3}`) */
+  TESSB200_DIY_BOUNDS_STATIC4 = 1       /* Bounds = float[4] x 2: DIY with DIY_MAX_DIM = 4 points */
+};
+
+/* Writes the blocks in the order given; the footer lists them by gid.  NULL rem_gids / rem_lids are
+ * written as -1.  extra: opaque user bytes of tess_save's `extra` buffer (may be NULL / 0). */
+int tessb200_host_write_blocks(const char *path, int nblocks, const tessb200_host_dblock *blocks, int bounds_layout,
+                               const void *extra, size_t extra_size);
+/* Reads every block of the file, in gid order.  The link record in front of each payload is
+ * skipped whatever its class; both Bounds layouts are recognised (*bounds_layout, may be NULL,
+ * receives the one found).  Arrays are malloc'ed; release with tessb200_host_free_dblocks. */
+int tessb200_host_read_blocks(const char *path, int *nblocks, tessb200_host_dblock **blocks, int *bounds_layout);
+void tessb200_host_free_dblocks(int nblocks, tessb200_host_dblock *blocks);
 
 void tessb200_host_free(void *p);
 const char *tessb200_host_last_error(void);

@@ -126,8 +126,8 @@ class Checker:
         p.alg = alg
         p.num_given_bounds = 0
         if given_bounds is not None:
-            p.num_given_bounds = 3
-            for d in range(3):
+            p.num_given_bounds = len(given_bounds[0])     # 1..3 leading axes (src/dense.cpp:1725-1735)
+            for d in range(p.num_given_bounds):
                 p.given_mins[d] = float(given_bounds[0][d])
                 p.given_maxs[d] = float(given_bounds[1][d])
         p.project = 1 if project else 0

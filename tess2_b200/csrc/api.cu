@@ -373,7 +373,7 @@ static int make_geometry(tessb200_ctx *c, tessb200_dense_params *p, Geometry *G,
   G->out_floats = out_off;
   G->total_cells = cell_base;
   G->kl.cell_bits = ceil_log2(cell_base + 1);
-  G->kl.z_bits = p->project ? ceil_log2((unsigned long long)p->glo_num_idx[2] + 2) : 0;
+  key_z_range(G->boxes.data(), G->boxes.size(), p->project, &G->kl);
   G->key_bits = ceil_log2(G->total_rows + 1) + 1 + G->kl.cell_bits + G->kl.z_bits;
   if (G->key_bits > 64) return fail(TESSB200_ELIMIT, "sort key needs %d bits (> 64): grid rows x cells too large", G->key_bits);
   return 0;

@@ -994,10 +994,15 @@ struct DtfeTet
 // One x-run of deposits in one row of one block's density array.
 //   key  = (((row << 1 | remote) << cell_bits | cell) << z_bits) | zslot      (sorted ascending)
 //   data = x0 | len << 16 | float_path << 31 | (uint64)float_bits(value) << 32
+//   zslot = z - z_lo, projections only: z index of the deposit (orders one cell's deposits onto the same
+//   (x, y) as the reference's z-outer scan does).  z_lo = lowest z index any block's closed bounds hold;
+//   it is negative when a given z range is narrower than the data (such points still deposit: the
+//   projected index drops z, src/dense.cpp:1047-1090)
 struct KeyLayout
 {
-  int cell_bits, z_bits;
+  int cell_bits, z_bits, z_lo;
 };
+TB_HD uint32_t z_slot(const KeyLayout &kl, int project, int z) { return project ? (uint32_t)(z - kl.z_lo) : 0u; }
 TB_HD uint64_t make_key(const KeyLayout &kl, uint64_t row, int remote, uint32_t cell, uint32_t zslot)
 {
   return ((((row << 1) | (uint64_t)remote) << kl.cell_bits | cell) << kl.z_bits) | zslot;
@@ -1094,7 +1099,7 @@ TB_HD void emit_line(const BlockBox *boxes, int nblocks, int e, const KeyLayout 
       int b = lb < be.b_lo[0] + be.b_num[0] - 1 ? lb : be.b_lo[0] + be.b_num[0] - 1;
       if (a <= b) {
         uint64_t row = (uint64_t)(be.row_base + (project ? (long long)ly : (long long)lz * be.b_num[1] + ly));
-        emit(make_key(kl, row, 0, cell, project ? (uint32_t)z : 0u), make_data(a - be.b_lo[0], b - a + 1, float_path_local, value));
+        emit(make_key(kl, row, 0, cell, z_slot(kl, project, z)), make_data(a - be.b_lo[0], b - a + 1, float_path_local, value));
       }
     }
   }
@@ -1121,7 +1126,7 @@ TB_HD void emit_line(const BlockBox *boxes, int nblocks, int e, const KeyLayout 
     }
     for (int s = 0; s < 2; s++)
       if (pa[s] <= pb[s])
-        emit(make_key(kl, row, 1, cell, project ? (uint32_t)z : 0u), make_data(pa[s] - bj.b_lo[0], pb[s] - pa[s] + 1, 0, value));
+        emit(make_key(kl, row, 1, cell, z_slot(kl, project, z)), make_data(pa[s] - bj.b_lo[0], pb[s] - pa[s] + 1, 0, value));
   }
 }
 

@@ -47,22 +47,29 @@ inline void block_grid_params(const float *bmin, const float *bmax, const tessb2
 }
 
 // { idx : bmin <= idx2phys(idx) <= bmax } as an inclusive index interval: the integer form of the
-// closed-bounds test of src/dense.cpp:279-284 (idx2phys is monotone in idx)
+// closed-bounds test of src/dense.cpp:279-284 (idx2phys is monotone in idx).  Indices are kept within
+// two points of the grid -- a point further out has no array element to land in -- except along z when
+// projecting: the projected index drops z (src/dense.cpp:1047-1090), so a point of any z index deposits
+// as long as its position lies in the block (a given z range narrower than the data).
 inline void phys_box(const float *bmin, const float *bmax, const tessb200_dense_params *p, int *lo, int *hi)
 {
   for (int d = 0; d < 3; d++) {
     float step = p->grid_step_size[d], gmin = p->grid_phys_mins[d];
-    int n = p->glo_num_idx[d];
-    int a = phys2idx1(bmin[d], step, gmin) - 2;
-    if (a < -2) a = -2;
-    if (a > n + 2) a = n + 2;
-    while (a > -2 && idx2phys1(a - 1, step, gmin) >= bmin[d]) a--;
-    while (a <= n + 2 && idx2phys1(a, step, gmin) < bmin[d]) a++;
-    int b = phys2idx1(bmax[d], step, gmin) + 2;
-    if (b > n + 2) b = n + 2;
-    if (b < -2) b = -2;
-    while (b < n + 2 && idx2phys1(b + 1, step, gmin) <= bmax[d]) b++;
-    while (b >= -2 && idx2phys1(b, step, gmin) > bmax[d]) b--;
+    const bool free_z = p->project && d == 2;
+    const int lim_lo = free_z ? -(1 << 22) : -2, lim_hi = free_z ? (1 << 22) : p->glo_num_idx[d] + 2;
+    float ea = (bmin[d] - gmin) / step, eb = (bmax[d] - gmin) / step;      // estimates, clamped before the cast
+    ea = fminf(fmaxf(ea, (float)lim_lo), (float)lim_hi);
+    eb = fminf(fmaxf(eb, (float)lim_lo), (float)lim_hi);
+    int a = (int)ea - 2;
+    if (a < lim_lo) a = lim_lo;
+    if (a > lim_hi) a = lim_hi;
+    while (a > lim_lo && idx2phys1(a - 1, step, gmin) >= bmin[d]) a--;
+    while (a <= lim_hi && idx2phys1(a, step, gmin) < bmin[d]) a++;
+    int b = (int)eb + 2;
+    if (b > lim_hi) b = lim_hi;
+    if (b < lim_lo) b = lim_lo;
+    while (b < lim_hi && idx2phys1(b + 1, step, gmin) <= bmax[d]) b++;
+    while (b >= lim_lo && idx2phys1(b, step, gmin) > bmax[d]) b--;
     lo[d] = a;
     hi[d] = b;
   }
@@ -74,6 +81,24 @@ inline int ceil_log2(unsigned long long v)
   while (b < 64 && (1ull << b) < v) b++;
   return b;
 }
+
+// z slots of the sort key (projections): the span of z indices that any block's closed bounds hold
+inline void key_z_range(const BlockBox *boxes, size_t nblocks, int project, KeyLayout *kl)
+{
+  kl->z_bits = 0;
+  kl->z_lo = 0;
+  if (!project || nblocks == 0) return;
+  int zlo = boxes[0].p_lo[2], zhi = boxes[0].p_hi[2];
+  for (size_t i = 1; i < nblocks; i++) {
+    if (boxes[i].p_lo[2] < zlo) zlo = boxes[i].p_lo[2];
+    if (boxes[i].p_hi[2] > zhi) zhi = boxes[i].p_hi[2];
+  }
+  if (zhi < zlo) zhi = zlo;
+  kl->z_lo = zlo;
+  kl->z_bits = ceil_log2((unsigned long long)((long long)zhi - zlo) + 1);
+  if (kl->z_bits < 1) kl->z_bits = 1;
+}
+
 
 
 } // namespace tb

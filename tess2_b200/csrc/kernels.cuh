@@ -297,8 +297,10 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
       int hi = phys2idx1(cmax[d], g.step[d], g.gmin[d]);
       n3[d] = hi - lo[d] + 1;
     }
+    // a projection keeps cells of any z index (the projected index drops z; phys_box, host_geom.hpp)
+    const int z_floor = g.project ? -(1 << 22) : -1;
     if (n3[0] < 1 || n3[1] < 1 || n3[2] < 1 || n3[0] > 32767 || n3[1] > 32767 || n3[2] > 32767 ||
-        lo[0] < -1 || lo[1] < -1 || lo[2] < -1)
+        lo[0] < -1 || lo[1] < -1 || lo[2] < z_floor)
       status = CELL_BAD_MESH;
     npts = (long long)n3[0] * n3[1] * n3[2];
   }
@@ -441,8 +443,10 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__res
       int hi = phys2idx1(cmax[d], g.step[d], g.gmin[d]);
       n3[d] = hi - lo[d] + 1;
     }
+    // a projection keeps cells of any z index (the projected index drops z; phys_box, host_geom.hpp)
+    const int z_floor = g.project ? -(1 << 22) : -1;
     if (n3[0] < 1 || n3[1] < 1 || n3[2] < 1 || n3[0] > 32767 || n3[1] > 32767 || n3[2] > 32767 ||
-        lo[0] < -1 || lo[1] < -1 || lo[2] < -1)
+        lo[0] < -1 || lo[1] < -1 || lo[2] < z_floor)
       status = CELL_BAD_MESH;
   }
   CellHdr h;
@@ -722,7 +726,7 @@ struct LineEmitter
       const BlockBox &b = sc.boxes[e];
       int ly = y - b.b_lo[1], lz = z - b.b_lo[2];
       uint64_t row = (uint64_t)(b.row_base + (sc.project ? (long long)ly : (long long)lz * b.b_num[1] + ly));
-      emit(make_key(sc.kl, row, 0, cell, sc.project ? (uint32_t)z : 0u), make_data(xa - b.b_lo[0], xb - xa + 1, 0, value));
+      emit(make_key(sc.kl, row, 0, cell, z_slot(sc.kl, sc.project, z)), make_data(xa - b.b_lo[0], xb - xa + 1, 0, value));
     } else {
       emit_line(sc.boxes, sc.nblocks, e, sc.kl, sc.project, cell, xa, xb, y, z, 0, value, emit, cand, ncand);
     }

@@ -117,8 +117,8 @@ class Context:
         p.alg = int(alg_type)
         p.num_given_bounds = int(num_given_bounds)
         for d in range(3):
-            p.given_mins[d] = float(given_mins[d]) if given_mins is not None else 0.0
-            p.given_maxs[d] = float(given_maxs[d]) if given_maxs is not None else 0.0
+            p.given_mins[d] = float(given_mins[d]) if given_mins is not None and d < len(given_mins) else 0.0
+            p.given_maxs[d] = float(given_maxs[d]) if given_maxs is not None and d < len(given_maxs) else 0.0
             p.proj_plane[d] = float(proj_plane[d]) if proj_plane is not None else (1.0 if d == 2 else 0.0)
             p.glo_num_idx[d] = int(glo_num_idx[d])
         p.project = 1 if project else 0

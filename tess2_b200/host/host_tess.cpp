@@ -11,6 +11,7 @@
 static thread_local std::string g_err;
 
 extern "C" const char *tessb200_host_last_error(void) { return g_err.c_str(); }
+void tessb200_host_set_error(const std::string &s) { g_err = s; }   // for block_file.cpp
 
 extern "C" int tessb200_host_delaunay(int num_particles, const float *particles, int *num_tets, int **tets)
 {

@@ -22,8 +22,22 @@ class HostBlock(C.Structure):
     ]
 
 
+class HostDBlock(C.Structure):
+    """tessb200_host_dblock: one block of the hand-off file (the fields of load_block_light, src/tess.cpp:223-259)."""
+    _fields_ = [
+        ("gid", C.c_int), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3), ("box_min", C.c_float * 3), ("box_max", C.c_float * 3),
+        ("data_min", C.c_float * 3), ("data_max", C.c_float * 3), ("num_orig_particles", C.c_int), ("num_particles", C.c_int),
+        ("particles", C.POINTER(C.c_float)), ("rem_gids", C.POINTER(C.c_int)), ("rem_lids", C.POINTER(C.c_int)),
+        ("num_grid_pts", C.c_int), ("density", C.POINTER(C.c_float)), ("complete", C.c_int), ("num_tets", C.c_int),
+        ("tets", C.POINTER(C.c_int)), ("vert_to_tet", C.POINTER(C.c_int)),
+    ]
+
+
+BOUNDS_DYNAMIC, BOUNDS_STATIC4 = 0, 1
+
 EXPORTS = ["tessb200_host_delaunay", "tessb200_host_tess", "tessb200_host_free_block", "tessb200_host_free", "tessb200_host_last_error",
-           "tessb200_host_regular_blocks", "tessb200_host_kdtree_blocks"]
+           "tessb200_host_regular_blocks", "tessb200_host_kdtree_blocks",
+           "tessb200_host_write_blocks", "tessb200_host_read_blocks", "tessb200_host_free_dblocks"]
 
 
 def load():
@@ -42,6 +56,9 @@ def load():
         lib.tessb200_host_kdtree_blocks.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
                                                     C.POINTER(C.c_float), C.POINTER(C.c_int)]
         lib.tessb200_host_free.argtypes = [C.c_void_p]
+        lib.tessb200_host_write_blocks.argtypes = [C.c_char_p, C.c_int, C.POINTER(HostDBlock), C.c_int, C.c_void_p, C.c_size_t]
+        lib.tessb200_host_read_blocks.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.POINTER(HostDBlock)), C.POINTER(C.c_int)]
+        lib.tessb200_host_free_dblocks.argtypes = [C.c_int, C.POINTER(HostDBlock)]
         lib.tessb200_host_last_error.restype = C.c_char_p
         _lib = lib
     return _lib
@@ -125,3 +142,71 @@ def kdtree_blocks(points, domain_min, domain_max, nblocks):
     if lib.tessb200_host_kdtree_blocks(len(p), _fp(p), _fp(dmin), _fp(dmax), nblocks, _fp(bb), owner.ctypes.data_as(C.POINTER(C.c_int))):
         raise RuntimeError(lib.tessb200_host_last_error().decode())
     return _bounds_list(bb), owner
+
+
+def write_blocks(path, blocks, data_min, data_max, layout=BOUNDS_DYNAMIC, extra=b""):
+    """tess_save (src/tess.cpp:126-137): the blocks (dicts as tess() returns them) into a DIY block file.
+    Optional keys: box_min/box_max (default: the block bounds), rem_gids/rem_lids (default -1), density, complete."""
+    lib = load()
+    arr = (HostDBlock * max(len(blocks), 1))()
+    keep = []
+
+    def arr_of(a, dtype):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep.append(a)
+        return a
+
+    for d, b in zip(arr, blocks):
+        p = arr_of(b["particles"], np.float32).reshape(-1, 3)
+        t = arr_of(b["tets"], np.int32).reshape(-1, 8)
+        v = arr_of(b["vert_to_tet"], np.int32)
+        d.gid, d.num_orig_particles, d.num_particles, d.num_tets = int(b["gid"]), int(b["num_orig"]), len(p), len(t)
+        d.bounds_min[:] = [float(x) for x in b["bounds_min"]]
+        d.bounds_max[:] = [float(x) for x in b["bounds_max"]]
+        d.box_min[:] = [float(x) for x in b.get("box_min", b["bounds_min"])]
+        d.box_max[:] = [float(x) for x in b.get("box_max", b["bounds_max"])]
+        d.data_min[:] = [float(x) for x in data_min]
+        d.data_max[:] = [float(x) for x in data_max]
+        d.particles = _fp(p)
+        d.tets = t.ctypes.data_as(C.POINTER(C.c_int))
+        d.vert_to_tet = v.ctypes.data_as(C.POINTER(C.c_int))
+        for key in ("rem_gids", "rem_lids"):
+            if b.get(key) is not None:
+                setattr(d, key, arr_of(b[key], np.int32).ctypes.data_as(C.POINTER(C.c_int)))
+        if b.get("density") is not None:
+            g = arr_of(b["density"], np.float32).reshape(-1)
+            d.num_grid_pts, d.density = len(g), _fp(g)
+        d.complete = int(b.get("complete", 0))
+    rc = lib.tessb200_host_write_blocks(os.fsencode(path), len(blocks), arr, int(layout), extra if extra else None, len(extra))
+    if rc:
+        raise RuntimeError(lib.tessb200_host_last_error().decode())
+
+
+def read_blocks(path):
+    """tess_load (src/tess.cpp:139-152): (list of block dicts in gid order, data_min, data_max, bounds layout found)."""
+    lib = load()
+    n = C.c_int()
+    layout = C.c_int()
+    arr = C.POINTER(HostDBlock)()
+    rc = lib.tessb200_host_read_blocks(os.fsencode(path), C.byref(n), C.byref(arr), C.byref(layout))
+    if rc:
+        raise RuntimeError(lib.tessb200_host_last_error().decode())
+
+    def copy(ptr, shape, dtype):
+        return np.ctypeslib.as_array(ptr, shape).copy() if shape[0] else np.zeros(shape, dtype)
+
+    out = []
+    data_min = data_max = None
+    for i in range(n.value):
+        b = arr[i]
+        npart, ng = b.num_particles, b.num_particles - b.num_orig_particles
+        out.append(dict(
+            gid=b.gid, num_orig=b.num_orig_particles, particles=copy(b.particles, (npart, 3), np.float32),
+            tets=copy(b.tets, (b.num_tets, 8), np.int32), vert_to_tet=copy(b.vert_to_tet, (npart,), np.int32),
+            rem_gids=copy(b.rem_gids, (ng,), np.int32), rem_lids=copy(b.rem_lids, (ng,), np.int32),
+            density=copy(b.density, (b.num_grid_pts,), np.float32), complete=b.complete,
+            bounds_min=np.array(b.bounds_min, np.float32), bounds_max=np.array(b.bounds_max, np.float32),
+            box_min=np.array(b.box_min, np.float32), box_max=np.array(b.box_max, np.float32)))
+        data_min, data_max = np.array(b.data_min, np.float32), np.array(b.data_max, np.float32)
+    lib.tessb200_host_free_dblocks(n.value, arr)
+    return out, data_min, data_max, layout.value

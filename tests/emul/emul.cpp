@@ -384,7 +384,7 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
   if (rc) return rc;
   KeyLayout kl;
   kl.cell_bits = ceil_log2(cb + 1);
-  kl.z_bits = p.project ? ceil_log2((unsigned long long)p.glo_num_idx[2] + 2) : 0;
+  key_z_range(boxes.data(), boxes.size(), p.project, &kl);
 
   if (p.alg == TESSB200_DENSE_DTFE) {
     for (int bi = 0; bi < nblocks; bi++) {

@@ -50,3 +50,28 @@ def test_emul_dtfe_matches_port(port, emul, name, gs):
         covered += int((d1 > 0).sum())
     # most of the grid is covered by valid tets (not the non-cubic case, whose grid is mostly padding)
     assert covered > (0.0 if name == "aniso" else 0.6) * gs[0] * gs[1] * gs[2]
+
+
+# given grid bounds (the run scripts pass two, with a projection: DENSE_TEST, TESS_DENSE_TEST).  Bounds wider
+# than the data on x and y -- narrower ones make the reference itself write out of bounds (test_oracle.py) --
+# and a z range NARROWER than the data under projection: the projected index drops z, so those points deposit.
+GIVEN = [([-1.5], [16.5]), ([-1.5, -1.5], [16.5, 16.5]), ([-1.5, -1.5, -2.0], [16.5, 16.5, 17.0]), ([-1.5, -1.5, 2.5], [16.5, 16.5, 12.5])]
+
+
+@pytest.mark.parametrize("gb", GIVEN)
+def test_emul_given_bounds(port, emul, gb):
+    blocks = dataset("u16x8")
+    narrow_z = len(gb[0]) == 3 and gb[0][2] > 0
+    for proj in (False, True):
+        if narrow_z and not proj:
+            continue          # 3-D with a narrower z range: the reference writes out of bounds
+        for alg in (0, 1):
+            o1 = port.dense(blocks, (24, 24, 24), alg=alg, project=proj, given_bounds=gb)
+            o2 = emul.dense(blocks, (24, 24, 24), alg=alg, project=proj, given_bounds=gb)
+            assert o1["block_min_idx"] == o2["block_min_idx"] and o1["block_num_idx"] == o2["block_num_idx"]
+            for i, (d1, d2) in enumerate(zip(o1["block_density"], o2["block_density"])):
+                assert_same_bits(d1, d2, f"given {gb} alg{alg} proj{proj} block {i}")
+            if narrow_z:      # the points beyond the z range did deposit: about the mass of the run whose z range holds the data
+                wide = port.dense(blocks, (24, 24, 24), alg=alg, project=True, given_bounds=(gb[0][:2], gb[1][:2]))
+                tot = lambda o: sum(float(d.astype(np.float64).sum()) for d in o["block_density"])
+                assert abs(tot(o1) - tot(wide)) < 0.05 * tot(wide)
