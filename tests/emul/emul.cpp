@@ -154,8 +154,11 @@ struct Topo
       HashWS chk;
       int ns2, nn2;
       int st2 = star_and_neighbors_hashed(site, t0, tets, chk, 52, 36, &ns2, &nn2);
-      if (st2 != st || (st == CELL_OK && (ns2 != ns || nn2 != nn))) { fprintf(stderr, "emul: BFS variants disagree: st %d/%d ns %d/%d nn %d/%d\n", st, st2, ns, ns2, nn, nn2); abort(); }
-      if (st == CELL_OK)
+      // (a walk that overflows its workspace is redone by the general walk whatever the other variant said: an
+      // incomplete star can be reported as overflow by the variant that fills a bucket before it meets the hull)
+      const bool redo = st == CELL_OVERFLOW || st2 == CELL_OVERFLOW;
+      if (!redo && (st2 != st || (st == CELL_OK && (ns2 != ns || nn2 != nn)))) { fprintf(stderr, "emul: BFS variants disagree: st %d/%d ns %d/%d nn %d/%d\n", st, st2, ns, ns2, nn, nn2); abort(); }
+      if (st == CELL_OK && st2 == CELL_OK)
         for (int k = 0; k < nn; k++)
           if (chk.nu(k) != fast.nu(k) || chk.nt(k) != fast.nt(k)) { fprintf(stderr, "emul: BFS variants disagree on faces\n"); abort(); }
     } else {
@@ -379,7 +382,8 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
     long long npts = nrows * bx.b_num[0];
     for (int d = 0; d < 3; d++) { blocks[i].block_min_idx[d] = bx.b_lo[d]; blocks[i].block_num_idx[d] = bx.b_num[d]; }
     blocks[i].num_grid_pts = (int)npts;
-    if (npts > blocks[i].density_capacity) rc = -1;
+    if (bx.b_num[0] < 1 || bx.b_num[1] < 1 || bx.b_num[2] < 1) rc = -3;   // as api.cu: "block owns no grid points along axis"
+    else if (npts > blocks[i].density_capacity) rc = -1;
   }
   if (rc) return rc;
   KeyLayout kl;

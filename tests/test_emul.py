@@ -75,3 +75,10 @@ def test_emul_given_bounds(port, emul, gb):
                 wide = port.dense(blocks, (24, 24, 24), alg=alg, project=True, given_bounds=(gb[0][:2], gb[1][:2]))
                 tot = lambda o: sum(float(d.astype(np.float64).sum()) for d in o["block_density"])
                 assert abs(tot(o1) - tot(wide)) < 0.05 * tot(wide)
+
+
+def test_fuzz_reference_port_device_logic(reference, port, emul):
+    # a fixed slice of tests/fuzz_logic.py (run that script for longer sweeps)
+    import fuzz_logic
+    n, failures = fuzz_logic.run(seed=12345, cases=120, checkers=(reference, port, emul), log=lambda *a: None)
+    assert n == 120 and not failures, failures[:3]
