@@ -9,7 +9,7 @@ Random particle sets (uniform / clustered / jittered lattice, domains of extent 
 and projected, eps 1e-6..1e-2, 0-3 given bounds wider or narrower than the data.  Every case runs in a forked
 child: the reference has no bounds checks, and where a deposit falls outside its block's sub-grid (counted by
 the port: `out_of_range`) the reference's result is undefined and only port == device logic is asked for.
-Round 1: 10 000 cases over 5 seeds, no difference; it found the projection-with-narrow-z case (test_emul.py)."""
+Round 1: 12 000 cases over 5 seeds (300 s each), no difference; it found the projection-with-narrow-z case (test_emul.py)."""
 import os
 import sys
 import time
@@ -103,7 +103,9 @@ def run(seed, seconds=None, cases=None, checkers=None, log=print):
                     if d:
                         msg = f"reference vs port: {d}"
             except RuntimeError as e:
-                if "-3" not in str(e):          # a block without grid points: rejected by all three, not a failure
+                # -3: a block without grid points; -1: a block's index box exceeds the grid (narrow given bounds):
+                # rejected, not a failure
+                if not str(e).endswith(("-3", "-1")):
                     msg = f"exception: {e}"
             os.write(w, msg.encode())
             os._exit(0)
