@@ -99,7 +99,7 @@ class Delaunay3
   std::vector<float> sorted_;        // the points in insertion order
   std::vector<Tet> tets_;
   std::vector<int> free_;
-  std::vector<uint32_t> mark_;       // per tet: epoch * 2 + conflict bit of the current insertion
+  std::vector<uint32_t> mark_;       // per tet: epoch * 4 + (in cavity list) * 2 + conflict bit of the current insertion
   uint32_t epoch_ = 0;
   int last_ = 0;
   size_t skipped_ = 0;
@@ -107,9 +107,9 @@ class Delaunay3
   StaticFilter filter_;
   // scratch of one insertion
   std::vector<int> cavity_, stack_;
-  struct BFace { int t, i; };
+  struct BFace { int t, i, nt; };
   std::vector<BFace> boundary_;
-  struct EdgeSlot { uint64_t key; int tet, slot; uint32_t epoch; };
+  struct EdgeSlot { uint64_t key; int tetslot; uint32_t epoch; };   // tetslot = tet * 4 + slot, -1 once matched
   std::vector<EdgeSlot> edges_;
 
   const float *P(int i) const { return p_ + 3 * (size_t)i; }
@@ -245,11 +245,12 @@ class Delaunay3
         if (T.v[i] >= 0 && same_point(T.v[i], id)) { skipped_++; return; }
     }
     epoch_++;
+    if (epoch_ >= (1u << 30)) { std::fill(mark_.begin(), mark_.end(), 0u); epoch_ = 1; }
     auto state = [&](int t) -> int {          // 1 conflict, 0 no conflict (cached per insertion)
-      if ((mark_[t] >> 1) == epoch_) return (int)(mark_[t] & 1u);
+      if ((mark_[t] >> 2) == epoch_) return (int)(mark_[t] & 1u);
       const int c = conflict(t, p) > 0 ? 1 : 0;
       stat_conflict++;
-      mark_[t] = epoch_ << 1 | (uint32_t)c;
+      mark_[t] = epoch_ << 2 | (uint32_t)c;
       return c;
     };
     if (!state(t0)) {
@@ -269,53 +270,83 @@ class Delaunay3
     // conflict region
     cavity_.clear(); boundary_.clear(); stack_.clear();
     stack_.push_back(t0);
-    mark_[t0] |= 0;   // already marked conflict
     cavity_.push_back(t0);
-    // visited set = cavity membership via a second epoch bit would cost another array: reuse `n` scan with a small flag vector
-    in_cavity_flag(t0, true);
+    mark_[t0] |= 2u;          // listed (the bit dies with the epoch)
     while (!stack_.empty()) {
       const int t = stack_.back();
       stack_.pop_back();
+      for (int i = 0; i < 4; i++) {            // the four neighbours are about to be tested: start their loads together
+        __builtin_prefetch(&tets_[tets_[t].n[i]]);
+        __builtin_prefetch(&mark_[tets_[t].n[i]]);
+      }
       for (int i = 0; i < 4; i++) {
         const int u = tets_[t].n[i];
         if (state(u)) {
-          if (!in_cavity(u)) { in_cavity_flag(u, true); cavity_.push_back(u); stack_.push_back(u); }
+          if (!(mark_[u] & 2u)) { mark_[u] |= 2u; cavity_.push_back(u); stack_.push_back(u); }
         } else {
           BFace bf;
-          bf.t = t; bf.i = i;
+          bf.t = t; bf.i = i; bf.nt = -1;
           boundary_.push_back(bf);
         }
       }
     }
-    // new tets: boundary face + p
-    if (edges_.size() < 1024) edges_.assign(1024, EdgeSlot{0, 0, 0, 0});
-    while (edges_.size() < boundary_.size() * 8) edges_.assign(edges_.size() * 2, EdgeSlot{0, 0, 0, 0});
-    edge_epoch_++;
+    // new tets: boundary face + p.  Pass 1 creates them and leaves, in the cavity tet's neighbour slot of that
+    // face, the new tet's id (as ~id < 0); pass 2 links the new tets to each other by turning around each edge
+    // of the cavity boundary through the cavity tets until the next boundary face comes up.
     int first_new = -1;
-    for (const BFace &bf : boundary_) {
+    for (BFace &bf : boundary_) {
       const int nt = new_tet();
-      Tet N = tets_[bf.t];          // copy: tets_ may reallocate in new_tet (already done above)
+      Tet N = tets_[bf.t];
       const int outside = N.n[bf.i];
       N.v[bf.i] = id;
-      for (int j = 0; j < 4; j++) N.n[j] = -1;
+      N.n[0] = N.n[1] = N.n[2] = N.n[3] = -1;
       N.n[bf.i] = outside;
       tets_[nt] = N;
       mark_[nt] = 0;
       // the outside tet now faces the new one
       Tet &O = tets_[outside];
-      for (int j = 0; j < 4; j++) if (O.n[j] == bf.t && shares_face(O, j, N, bf.i)) O.n[j] = nt;
-      // faces of the new tet that contain p: one per other slot j, identified by the edge left when
-      // p and v[j] are removed
-      for (int j = 0; j < 4; j++) {
-        if (j == bf.i) continue;
-        int e[2], k = 0;
-        for (int m = 0; m < 4; m++) if (m != bf.i && m != j) e[k++] = N.v[m];
-        link_edge(e[0], e[1], nt, j);
+      const int hits = (O.n[0] == bf.t) + (O.n[1] == bf.t) + (O.n[2] == bf.t) + (O.n[3] == bf.t);
+      if (hits == 1) {
+        O.n[O.n[0] == bf.t ? 0 : (O.n[1] == bf.t ? 1 : (O.n[2] == bf.t ? 2 : 3))] = nt;
+      } else {
+        for (int j = 0; j < 4; j++) if (O.n[j] == bf.t && shares_face(O, j, N, bf.i)) O.n[j] = nt;
       }
+      tets_[bf.t].n[bf.i] = ~nt;
+      bf.nt = nt;
       if (first_new < 0) first_new = nt;
     }
+    for (const BFace &bf : boundary_) {
+      Tet &N = tets_[bf.nt];
+      for (int j = 0; j < 4; j++) {
+        if (j == bf.i || N.n[j] >= 0) continue;
+        // edge (a, b) = the boundary face minus v[j]; leave the cavity tet through the face opposite v[j]
+        int a = -2, b = -2;
+        for (int m = 0; m < 4; m++)
+          if (m != bf.i && m != j) { if (a == -2) a = N.v[m]; else b = N.v[m]; }
+        int cur = bf.t, exit = j;
+        for (int steps = 0;; steps++) {
+          const int nxt = tets_[cur].n[exit];
+          if (nxt < 0) break;                                     // (cur, exit) is a boundary face
+          if (steps > 100000) throw std::runtime_error("delaunay3: cavity boundary is not a manifold");
+          const Tet &X = tets_[nxt];
+          int s1 = -1, s2 = -1;
+          for (int m = 0; m < 4; m++)
+            if (X.v[m] != a && X.v[m] != b) { if (s1 < 0) s1 = m; else s2 = m; }
+          exit = X.n[s1] == cur ? s2 : s1;
+          cur = nxt;
+        }
+        const int other = ~tets_[cur].n[exit];
+        // in the new tet over (cur, exit) the face that holds p, a, b is opposite the vertex that is neither
+        // a nor b nor at slot `exit` (the new tet keeps the slots of the cavity tet it came from)
+        const Tet &C = tets_[cur];
+        int k = -1;
+        for (int m = 0; m < 4; m++) if (m != exit && C.v[m] != a && C.v[m] != b) k = m;
+        N.n[j] = other;
+        tets_[other].n[k] = bf.nt;
+      }
+    }
     stat_cavity += cavity_.size();
-    for (int t : cavity_) { in_cavity_flag(t, false); tets_[t].v[0] = -2; free_.push_back(t); }
+    for (int t : cavity_) { tets_[t].v[0] = -2; free_.push_back(t); }
     last_ = first_new;
     // walks start from a finite tet when possible
     if (!finite(tets_[last_])) {
@@ -324,14 +355,7 @@ class Delaunay3
   }
 
   // ---- small helpers -----------------------------------------------------------------------------
-  std::vector<char> cav_;
   uint32_t edge_epoch_ = 0;
-  bool in_cavity(int t) { return (size_t)t < cav_.size() && cav_[t]; }
-  void in_cavity_flag(int t, bool v)
-  {
-    if ((size_t)t >= cav_.size()) cav_.resize(std::max<size_t>(tets_.size(), (size_t)t + 1) * 2, 0);
-    cav_[t] = v ? 1 : 0;
-  }
   static bool shares_face(const Tet &A, int ia, const Tet &B, int ib)
   {
     // the face of A opposite slot ia equals the face of B opposite slot ib (as vertex sets)
@@ -351,11 +375,11 @@ class Delaunay3
     size_t h = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 20) & mask;
     for (;;) {
       EdgeSlot &s = edges_[h];
-      if (s.epoch != edge_epoch_) { s.key = key; s.tet = tet; s.slot = slot; s.epoch = edge_epoch_; return; }
-      if (s.key == key && s.tet >= 0) {
-        tets_[tet].n[slot] = s.tet;
-        tets_[s.tet].n[s.slot] = tet;
-        s.tet = -1;      // matched (an edge of the cavity boundary is shared by exactly two boundary faces)
+      if (s.epoch != edge_epoch_) { s.key = key; s.tetslot = tet * 4 + slot; s.epoch = edge_epoch_; return; }
+      if (s.key == key && s.tetslot >= 0) {
+        tets_[tet].n[slot] = s.tetslot >> 2;
+        tets_[s.tetslot >> 2].n[s.tetslot & 3] = tet;
+        s.tetslot = -1;  // matched (an edge of the cavity boundary is shared by exactly two boundary faces)
         return;
       }
       h = (h + 1) & mask;
