@@ -118,3 +118,27 @@ def assert_same_bits(a, b, what=""):
         with np.errstate(all="ignore"):
             rel = np.nanmax(np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(np.abs(a.astype(np.float64)), 1e-30))
         raise AssertionError(f"{what}: {nd} of {a.size} values differ (max rel {rel:.3g})")
+
+
+def write_grid_from(o, blocks, gs, project, path):
+    """tessb200_write_grid (host code of libtess_b200.so, no device needed) over per-block densities that an
+    oracle run produced."""
+    import ctypes as C
+    from tess2_b200 import lib as _l
+    arr = (_l.Block * len(blocks))()
+    keep = []
+    for i, d in enumerate(o["block_density"]):
+        d = np.ascontiguousarray(d, np.float32).reshape(-1)
+        keep.append(d)
+        arr[i].gid = int(blocks[i]["gid"])
+        arr[i].density = d.ctypes.data_as(_l.f32p)
+        arr[i].density_capacity = d.size
+        arr[i].num_grid_pts = d.size
+        for k in range(3):
+            arr[i].block_min_idx[k] = o["block_min_idx"][i][k]
+            arr[i].block_num_idx[k] = o["block_num_idx"][i][k]
+    prm = _l.DenseParams()
+    prm.project = 1 if project else 0
+    for k in range(3):
+        prm.glo_num_idx[k] = int(gs[k])
+    _l.check(_l.load().tessb200_write_grid(str(path).encode(), C.byref(prm), len(blocks), arr))

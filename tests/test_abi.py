@@ -96,3 +96,20 @@ def test_product_does_not_import_the_oracle():
                 if re.search(r"(from|import)\s+oracle|oracle/|libtess_oracle|libtess_ref|dense_oracle", s):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name,gs", [("u16x8", (32, 32, 32)), ("clump8", (48, 48, 48)), ("aniso", (40, 28, 17))])
+def test_write_grid_equals_the_reference_writer(reference, tmp_path, name, gs):
+    # WriteGrid / ProjectGrid (src/dense.cpp:751-1023) are host code on both sides: tessb200_write_grid over the block
+    # densities the unmodified reference left in its DBlocks must write the bytes the reference's own MPI-IO writer wrote
+    from conftest import dataset, write_grid_from, assert_same_bits
+    import numpy as np
+    blocks = dataset(name)
+    for alg in (0, 1):
+        for proj in (False, True):
+            f1, f2 = tmp_path / "ref.raw", tmp_path / "lib.raw"
+            o = reference.dense(blocks, gs, alg=alg, project=proj, outfile=str(f1))
+            write_grid_from(o, blocks, gs, proj, f2)
+            a, b = np.fromfile(f1, np.float32), np.fromfile(f2, np.float32)
+            assert a.size == (gs[0] * gs[1] if proj else gs[0] * gs[1] * gs[2])
+            assert_same_bits(a, b, f"{name} alg{alg} proj{proj} dense.raw")

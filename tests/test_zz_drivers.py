@@ -93,9 +93,16 @@ def test_drivers_end_to_end(drivers, tmp_path, port):
         assert_same_bits(a.reshape(32, 32, 32), o["grid"], f"dense.raw alg {alg} vs oracle")
     # DENSE_TEST's own argument shape: projection onto xy with two given bounds
     raw1, raw2 = tmp_path / "p1.raw", tmp_path / "p2.raw"
-    tail = ["24", "24", "24", "0.0", "0.0", "1.0", "1", "2", "2.5", "2.5", "12.5", "12.5"]
+    tail = ["24", "24", "24", "0.0", "0.0", "1.0", "1", "2", "-1.5", "-1.5", "16.5", "16.5"]
     subprocess.run([str(drivers / "dense"), str(f), str(raw1), "0"] + tail, check=True, capture_output=True)
     subprocess.run([str(drivers / "tess-dense"), "0", "8", "16", "16", "16", "0", "-1", "-1", "0", "0", str(raw2)] + tail, check=True, capture_output=True)
     a, b = np.fromfile(raw1, np.float32), np.fromfile(raw2, np.float32)
     assert a.size == 24 * 24 and np.isfinite(a).all() and a.sum() > 0
     assert_same_bits(a, b, "projected dense vs tess-dense")
+    # against the oracle: its per-block projected densities, assembled by the library's own WriteGrid (host code,
+    # itself checked against the reference's writer in test_abi.py)
+    from conftest import write_grid_from
+    o = port.dense(blocks, (24, 24, 24), alg=0, project=True, given_bounds=([-1.5, -1.5], [16.5, 16.5]))
+    raw3 = tmp_path / "p3.raw"
+    write_grid_from(o, blocks, (24, 24, 24), True, raw3)
+    assert_same_bits(a, np.fromfile(raw3, np.float32), "projected dense.raw vs oracle")
