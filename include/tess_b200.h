@@ -166,6 +166,16 @@ int tessb200_cell_volumes(tessb200_ctx *ctx, int num_sites, int num_particles, c
                           const int *tets, const int *vert_to_tet, float mass, int *complete, float *volume,
                           float *density);
 
+/* ---- input check (host code, no device needed) ----
+ * The kernels index `particles` with the tets' vertex ids and `tets` with their neighbour ids without range
+ * checks, as the reference does (src/tet.cpp, src/dense.cpp trust tess()).  A caller that does not trust its
+ * tessellation can ask first: every vertex id in [0, num_particles), every neighbour id in [-1, num_tets),
+ * every vert_to_tet entry -1 or a tet that holds the vertex, counts consistent; with `deep` != 0 also that
+ * tets[i] really is the tet across the face opposite verts[i] (shares the other three vertices and points
+ * back).  Returns 0, or TESSB200_EINVAL with the first finding in tessb200_last_error().  With the environment
+ * variable TESSB200_CHECK_INPUT=1 (2 = deep) tessb200_dense / tessb200_dense_upload run it on every block. */
+int tessb200_check_block(const tessb200_block *block, int deep);
+
 /* ---- output: replaces WriteGrid (src/dense.cpp:751-870) for one process ----
  * Writes the raw C-order float32 grid (x fastest, no header) that the reference's MPI-IO
  * subarray writes produce.  With project != 0 the z-stacked blocks are summed into the z=0

@@ -9,5 +9,5 @@ Only what the hot path needs lives here:
   harness/   host-side input staging: particle generators, block decomposition, SciPy-Qhull
 """
 from .dense import (DENSE_TESS, DENSE_CIC, DENSE_DTFE, Context, DenseResult, dense, WriteGrid, fill_vert_to_tet,  # noqa: F401
-                    fill_circumcenters, volume, complete, default_context)
+                    fill_circumcenters, volume, complete, default_context, check_blocks)
 from .lib import TessB200Error, LIB_PATH  # noqa: F401

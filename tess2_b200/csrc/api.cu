@@ -395,6 +395,9 @@ static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *block
     CU(cudaEventCreate(&e));               // timed: the TESSB200_TRACE timeline reads them
     c->h2d_ev.push_back(e);
   }
+  if (const char *chk = getenv("TESSB200_CHECK_INPUT"))
+    if (chk[0] == '1' || chk[0] == '2')
+      for (int i = 0; i < nblocks; i++) TRY(tessb200_check_block(&blocks[i], chk[0] == '2'));
   // reuse device buffers of a previous upload where possible
   std::vector<int> order(nblocks);
   for (int i = 0; i < nblocks; i++) order[i] = i;
@@ -1298,6 +1301,50 @@ extern "C" int tessb200_cell_volumes(tessb200_ctx *c, int num_sites, int num_par
     cleanup();
     if (e != cudaSuccess) return fail(TESSB200_ECUDA, "cell volumes: %s", cudaGetErrorString(e));
   }
+  return 0;
+}
+
+// ---- input check (host code) --------------------------------------------------------------------------
+extern "C" int tessb200_check_block(const tessb200_block *b, int deep)
+{
+  if (!b) return fail(TESSB200_EINVAL, "block is NULL");
+  if (b->num_particles < 0 || b->num_orig_particles < 0 || b->num_orig_particles > b->num_particles || b->num_tets < 0)
+    return fail(TESSB200_EINVAL, "block gid %d: inconsistent counts", b->gid);
+  if ((b->num_particles && !b->particles) || (b->num_tets && !b->tets)) return fail(TESSB200_EINVAL, "block gid %d: NULL input array", b->gid);
+  for (int d = 0; d < 3; d++)
+    if (!(b->bounds_min[d] <= b->bounds_max[d])) return fail(TESSB200_EINVAL, "block gid %d: bounds_min > bounds_max on axis %d", b->gid, d);
+  const int np = b->num_particles, nt = b->num_tets;
+  for (int t = 0; t < nt; t++) {
+    const int *v = b->tets + 8 * (size_t)t, *n = v + 4;
+    for (int i = 0; i < 4; i++) {
+      if (v[i] < 0 || v[i] >= np) return fail(TESSB200_EINVAL, "block gid %d: tet %d has vertex %d outside [0, %d)", b->gid, t, v[i], np);
+      if (n[i] < -1 || n[i] >= nt) return fail(TESSB200_EINVAL, "block gid %d: tet %d has neighbour %d outside [-1, %d)", b->gid, t, n[i], nt);
+    }
+    if (v[0] == v[1] || v[0] == v[2] || v[0] == v[3] || v[1] == v[2] || v[1] == v[3] || v[2] == v[3])
+      return fail(TESSB200_EINVAL, "block gid %d: tet %d repeats a vertex", b->gid, t);
+    if (!deep) continue;
+    for (int i = 0; i < 4; i++) {
+      if (n[i] < 0) continue;
+      const int *w = b->tets + 8 * (size_t)n[i], *m = w + 4;
+      int shared = 0, back = 0;
+      for (int j = 0; j < 4; j++) {
+        if (j != i && (v[j] == w[0] || v[j] == w[1] || v[j] == w[2] || v[j] == w[3])) shared++;
+        if (m[j] == t) back++;
+      }
+      if (shared != 3 || back != 1 || n[i] == t)
+        return fail(TESSB200_EINVAL, "block gid %d: tet %d slot %d: neighbour %d is not the tet across that face", b->gid, t, i, n[i]);
+    }
+  }
+  if (b->vert_to_tet)
+    for (int p = 0; p < np; p++) {
+      const int t = b->vert_to_tet[p];
+      if (t == -1) continue;
+      if (t < -1 || t >= nt) return fail(TESSB200_EINVAL, "block gid %d: vert_to_tet[%d] = %d outside [-1, %d)", b->gid, p, t, nt);
+      const int *v = b->tets + 8 * (size_t)t;
+      if (v[0] != p && v[1] != p && v[2] != p && v[3] != p) return fail(TESSB200_EINVAL, "block gid %d: vert_to_tet[%d] = %d, a tet that does not hold the vertex", b->gid, p, t);
+    }
+  for (size_t i = 0; i < 3 * (size_t)np; i++)
+    if (!std::isfinite(b->particles[i])) return fail(TESSB200_EINVAL, "block gid %d: particle %zu has a non-finite coordinate", b->gid, i / 3);
   return 0;
 }
 

@@ -259,6 +259,14 @@ def WriteGrid(outfile, result):
     _l.check(lib.tessb200_write_grid(str(outfile).encode(), C.byref(result.params), len(result.block_density), arr))
 
 
+def check_blocks(blocks, deep=False):
+    """tessb200_check_block on every block (host code, no device): raises TessB200Error with the first finding."""
+    lib = _l.load()
+    arr, keep = Context._marshal(None, blocks, False, None, False)
+    for i in range(len(blocks)):
+        _l.check(lib.tessb200_check_block(C.byref(arr[i]), 1 if deep else 0))
+
+
 def fill_vert_to_tet(num_particles, tets, ctx=None):
     return (ctx or default_context()).fill_vert_to_tet(num_particles, tets)
 

@@ -113,3 +113,45 @@ def test_write_grid_equals_the_reference_writer(reference, tmp_path, name, gs):
             a, b = np.fromfile(f1, np.float32), np.fromfile(f2, np.float32)
             assert a.size == (gs[0] * gs[1] if proj else gs[0] * gs[1] * gs[2])
             assert_same_bits(a, b, f"{name} alg{alg} proj{proj} dense.raw")
+
+
+def test_check_block_finds_malformed_input():
+    # tessb200_check_block is host code: the kernels trust their input (as the reference does), this is the opt-in guard
+    import numpy as np
+    import tess2_b200
+    from conftest import dataset
+    blocks = dataset("u16x8")
+    tess2_b200.check_blocks(blocks, deep=True)           # SciPy-Qhull blocks of the harness
+    from tess2_b200 import host_tess
+    p = np.random.default_rng(3).random((500, 3), dtype=np.float32)
+    native = host_tess.tess(p, None, host_tess.regular_blocks([0, 0, 0], [1, 1, 1], 2), [0, 0, 0], [1, 1, 1])
+    tess2_b200.check_blocks(native, deep=True)           # blocks of the repo's own tess()
+
+    def broken(**kw):
+        b = dict(blocks[0])
+        for k, f in kw.items():
+            a = np.array(b[k], copy=True)
+            f(a)
+            b[k] = a
+        return [b]
+
+    def set_(idx, v):
+        return lambda a: a.__setitem__(idx, v)
+
+    n, t = len(blocks[0]["particles"]), len(blocks[0]["tets"])
+    cases = {
+        "vertex": (broken(tets=set_((5, 2), n)), False),
+        "neighbour": (broken(tets=set_((5, 6), t)), False),
+        "neighbour ": (broken(tets=set_((5, 6), -2)), False),
+        "repeats": (broken(tets=set_((7, 1), int(blocks[0]["tets"][7, 0]))), False),
+        "vert_to_tet": (broken(vert_to_tet=set_(3, t + 4)), False),
+        "does not hold": (broken(vert_to_tet=set_(3, int(np.argmax((blocks[0]["tets"][:, :4] != 3).all(axis=1))))), False),
+        "non-finite": (broken(particles=set_((2, 1), np.nan)), False),
+        "not the tet across": (broken(tets=set_((5, 6), (int(blocks[0]["tets"][5, 6]) + 1) % t)), True),
+    }
+    for what, (blk, deep) in cases.items():
+        with pytest.raises(tess2_b200.TessB200Error, match=what.strip()):
+            tess2_b200.check_blocks(blk, deep=deep)
+    b = dict(blocks[0], num_orig=n + 1)
+    with pytest.raises(tess2_b200.TessB200Error, match="inconsistent counts"):
+        tess2_b200.check_blocks([b])
