@@ -297,10 +297,11 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
       int hi = phys2idx1(cmax[d], g.step[d], g.gmin[d]);
       n3[d] = hi - lo[d] + 1;
     }
-    // a projection keeps cells of any z index (the projected index drops z; phys_box, host_geom.hpp)
-    const int z_floor = g.project ? -(1 << 22) : -1;
+    // index boxes may start below the grid (given bounds narrower than the data): the span emitter keeps the points
+    // that have a grid element, and a projection keeps every z (phys_box, host_geom.hpp).  The floor only stops
+    // garbage (a NaN circumcenter casts to INT_MIN).
     if (n3[0] < 1 || n3[1] < 1 || n3[2] < 1 || n3[0] > 32767 || n3[1] > 32767 || n3[2] > 32767 ||
-        lo[0] < -1 || lo[1] < -1 || lo[2] < z_floor)
+        lo[0] < -(1 << 22) || lo[1] < -(1 << 22) || lo[2] < -(1 << 22))
       status = CELL_BAD_MESH;
     npts = (long long)n3[0] * n3[1] * n3[2];
   }
@@ -443,10 +444,11 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__res
       int hi = phys2idx1(cmax[d], g.step[d], g.gmin[d]);
       n3[d] = hi - lo[d] + 1;
     }
-    // a projection keeps cells of any z index (the projected index drops z; phys_box, host_geom.hpp)
-    const int z_floor = g.project ? -(1 << 22) : -1;
+    // index boxes may start below the grid (given bounds narrower than the data): the span emitter keeps the points
+    // that have a grid element, and a projection keeps every z (phys_box, host_geom.hpp).  The floor only stops
+    // garbage (a NaN circumcenter casts to INT_MIN).
     if (n3[0] < 1 || n3[1] < 1 || n3[2] < 1 || n3[0] > 32767 || n3[1] > 32767 || n3[2] > 32767 ||
-        lo[0] < -1 || lo[1] < -1 || lo[2] < z_floor)
+        lo[0] < -(1 << 22) || lo[1] < -(1 << 22) || lo[2] < -(1 << 22))
       status = CELL_BAD_MESH;
   }
   CellHdr h;
