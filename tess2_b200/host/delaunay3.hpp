@@ -41,9 +41,11 @@ class Delaunay3
   bool build(const float *pts, int n, uint32_t seed = 12345u)
   {
     n_ = n;
+    built_ = false;
     tets_.clear(); free_.clear(); mark_.clear();
     if (n < 4) return false;
-    p_ = pts;
+    p_ = src_ = pts;
+    seed_ = seed;
     insertion_order(order_, seed);
     // work on a copy of the points in insertion order (internal id = rank in the order): the vertices of
     // the tets around the point being inserted then sit close together in memory
@@ -68,6 +70,24 @@ class Delaunay3
       if (id == seed4[0] || id == seed4[1] || id == seed4[2] || id == seed4[3]) continue;
       insert(id);
     }
+    built_ = true;
+    return true;
+  }
+
+  // More points into the finished triangulation: pts is the caller's array grown to n points, its first points
+  // unchanged (those already inserted).  Same result as build(pts, n) for points in general position.
+  bool add(const float *pts, int n)
+  {
+    if (!built_) return build(pts, n, seed_);
+    const int first = n_;
+    if (n <= first) return true;
+    src_ = pts;
+    n_ = n;
+    insertion_order(order_, seed_, first);
+    sorted_.resize(3 * (size_t)n);
+    for (int i = first; i < n; i++) memcpy(&sorted_[3 * (size_t)i], pts + 3 * (size_t)order_[i], 12);
+    p_ = sorted_.data();
+    for (int id = first; id < n; id++) insert(id);
     return true;
   }
 
@@ -93,7 +113,11 @@ class Delaunay3
   size_t stat_walk = 0, stat_conflict = 0, stat_cavity = 0;
 
  private:
-  const float *p_ = nullptr;
+  const float *p_ = nullptr;         // the points in insertion order (sorted_) once build() has copied them
+  const float *src_ = nullptr;       // the caller's array
+  float all_lo_[3] = {0, 0, 0}, all_hi_[3] = {0, 0, 0};
+  uint32_t seed_ = 12345u;
+  bool built_ = false;
   int n_ = 0;
   std::vector<int> order_;           // internal id -> index in the caller's array
   std::vector<float> sorted_;        // the points in insertion order
@@ -128,14 +152,19 @@ class Delaunay3
 
   // Morton order inside rounds of doubling size (biased randomised insertion order): the walk from
   // the previous tet stays short and no input order can make the insertion quadratic
-  void insertion_order(std::vector<int> &order, uint32_t seed)
+  // The order covers the caller's points [first, n_): build() passes 0, add() the first new point.
+  void insertion_order(std::vector<int> &order, uint32_t seed, int first = 0)
   {
-    float lo[3] = {P(0)[0], P(0)[1], P(0)[2]}, hi[3] = {lo[0], lo[1], lo[2]};
-    for (int i = 1; i < n_; i++)
-      for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], P(i)[d]); hi[d] = std::max(hi[d], P(i)[d]); }
-    double inv[3], extent = 0.0;
+    const float *q = src_;
+    float lo[3] = {q[3 * (size_t)first], q[3 * (size_t)first + 1], q[3 * (size_t)first + 2]}, hi[3] = {lo[0], lo[1], lo[2]};
+    for (int i = first + 1; i < n_; i++)
+      for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], q[3 * (size_t)i + d]); hi[d] = std::max(hi[d], q[3 * (size_t)i + d]); }
+    double inv[3];
     for (int d = 0; d < 3; d++) inv[d] = hi[d] > lo[d] ? 2097151.0 / ((double)hi[d] - lo[d]) : 0.0;
-    for (int d = 0; d < 3; d++) extent = std::max(extent, (double)hi[d] - lo[d]);
+    // the static filter must hold for every pair of points seen so far
+    for (int d = 0; d < 3; d++) { all_lo_[d] = first ? std::min(all_lo_[d], lo[d]) : lo[d]; all_hi_[d] = first ? std::max(all_hi_[d], hi[d]) : hi[d]; }
+    double extent = 0.0;
+    for (int d = 0; d < 3; d++) extent = std::max(extent, (double)all_hi_[d] - all_lo_[d]);
     filter_.set_extent(extent);
     auto spread = [](uint64_t x) {
       x &= 0x1fffff;
@@ -146,20 +175,20 @@ class Delaunay3
       x = (x | x << 2) & 0x1249249249249249ull;
       return x;
     };
-    rng_.seed(seed);
-    std::vector<std::pair<uint64_t, int> > key(n_);
-    for (int i = 0; i < n_; i++) {
+    rng_.seed(seed + (uint32_t)first);
+    std::vector<std::pair<uint64_t, int> > key((size_t)(n_ - first));
+    for (int i = first; i < n_; i++) {
       uint64_t m = 0;
-      for (int d = 0; d < 3; d++) m |= spread((uint64_t)(((double)P(i)[d] - lo[d]) * inv[d])) << d;
+      for (int d = 0; d < 3; d++) m |= spread((uint64_t)(((double)q[3 * (size_t)i + d] - lo[d]) * inv[d])) << d;
       // round = number of trailing coin flips: the last round holds half the points, the one before a quarter, ...
       uint32_t r = rng_();
       int round = 0;
       while ((r & 1u) && round < 20) { r >>= 1; round++; }
-      key[i] = std::make_pair(((uint64_t)(20 - round) << 58) | (m >> 5), i);   // rarer rounds first, Morton order inside a round
+      key[i - first] = std::make_pair(((uint64_t)(20 - round) << 58) | (m >> 5), i);   // rarer rounds first, Morton order inside a round
     }
     std::sort(key.begin(), key.end());
     order.resize(n_);
-    for (int i = 0; i < n_; i++) order[i] = key[i].second;
+    for (int i = first; i < n_; i++) order[i] = key[i - first].second;
   }
 
   int new_tet()

@@ -83,28 +83,31 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     const double vol = (job.bmax[0] - job.bmin[0]) * (job.bmax[1] - job.bmin[1]) * (job.bmax[2] - job.bmin[2]);
     margin0 = 3.0 * std::cbrt(vol / std::max(n_orig, 1));
   }
-  double margin = margin0;
+  double margin = margin0, prev_margin = -1.0;
   std::vector<float> P;
-  std::vector<int> gids, tets;
+  std::vector<int> gids(job.mine.begin(), job.mine.end()), tets;
   int rounds = 0;
   double secs = 0.0;
+  tb_host::Delaunay3 dt;       // lives across the rounds: a wider margin only inserts the new ghosts
   for (;;) {
     rounds++;
-    gids.assign(job.mine.begin(), job.mine.end());
     for (int i = 0; i < n; i++) {
       if (owner[i] == job.gid) continue;
       const float *q = pts + 3 * (size_t)i;
-      bool in = true;
-      for (int d = 0; d < 3; d++) in = in && (double)q[d] >= job.bmin[d] - margin && (double)q[d] <= job.bmax[d] + margin;
-      if (in) gids.push_back(i);
+      bool in = true, before = prev_margin >= 0.0;
+      for (int d = 0; d < 3; d++) {
+        in = in && (double)q[d] >= job.bmin[d] - margin && (double)q[d] <= job.bmax[d] + margin;
+        before = before && (double)q[d] >= job.bmin[d] - prev_margin && (double)q[d] <= job.bmax[d] + prev_margin;
+      }
+      if (in && !before) gids.push_back(i);
     }
     const int np = (int)gids.size();
+    const size_t had = P.size() / 3;
     P.resize(3 * (size_t)np);
-    for (int i = 0; i < np; i++) memcpy(&P[3 * (size_t)i], pts + 3 * (size_t)gids[i], 12);
+    for (size_t i = had; i < (size_t)np; i++) memcpy(&P[3 * i], pts + 3 * (size_t)gids[i], 12);
     const auto t0 = std::chrono::steady_clock::now();
-    tb_host::Delaunay3 dt;
     tets.clear();
-    if (dt.build(P.data(), np)) dt.export_tets(tets);
+    if (dt.add(P.data(), np)) dt.export_tets(tets);
     secs += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const size_t nt = tets.size() / 8;
     bool covered = true;
@@ -141,10 +144,28 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     }
     if (grow) req = std::max(req, 2.0 * margin);
     if (req <= margin || margin >= max_growth * margin0) break;
+    prev_margin = margin;
     margin = std::min(req * 1.05, max_growth * margin0);
   }
   const int np = (int)gids.size();
   const size_t nt = tets.size() / 8;
+  if (rounds > 1) {
+    // ghosts in input order whatever round brought them in (the layout of a single-round run)
+    std::vector<int> ord(np), pos(np);
+    for (int i = 0; i < np; i++) ord[i] = i;
+    std::sort(ord.begin() + n_orig, ord.end(), [&](int a, int b) { return gids[a] < gids[b]; });
+    std::vector<float> P2(P.size());
+    std::vector<int> g2(np);
+    for (int i = 0; i < np; i++) {
+      pos[ord[i]] = i;
+      g2[i] = gids[ord[i]];
+      memcpy(&P2[3 * (size_t)i], &P[3 * (size_t)ord[i]], 12);
+    }
+    P.swap(P2);
+    gids.swap(g2);
+    for (size_t t = 0; t < nt; t++)
+      for (int j = 0; j < 4; j++) tets[8 * t + j] = pos[tets[8 * t + j]];
+  }
   out->gid = job.gid;
   for (int d = 0; d < 3; d++) { out->bounds_min[d] = (float)job.bmin[d]; out->bounds_max[d] = (float)job.bmax[d]; }
   out->num_orig_particles = n_orig;

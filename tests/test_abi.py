@@ -41,11 +41,13 @@ def test_host_library_exports_every_declared_symbol(tmp_path):
     src.write_text('''#include <stdio.h>
 #include <stddef.h>
 #include "tess_b200_host.h"
-int main(void) { printf("%zu %zu %zu\\n", sizeof(tessb200_host_block), offsetof(tessb200_host_block, particles), offsetof(tessb200_host_block, seconds)); return 0; }''')
+int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tessb200_host_block), offsetof(tessb200_host_block, particles), offsetof(tessb200_host_block, seconds),
+                        sizeof(tessb200_host_dblock), offsetof(tessb200_host_dblock, particles), offsetof(tessb200_host_dblock, vert_to_tet)); return 0; }''')
     exe = tmp_path / "szh"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    assert got == [C.sizeof(host_tess.HostBlock), host_tess.HostBlock.particles.offset, host_tess.HostBlock.seconds.offset]
+    assert got == [C.sizeof(host_tess.HostBlock), host_tess.HostBlock.particles.offset, host_tess.HostBlock.seconds.offset,
+                   C.sizeof(host_tess.HostDBlock), host_tess.HostDBlock.particles.offset, host_tess.HostDBlock.vert_to_tet.offset]
 
 
 def test_struct_layouts_match_the_header(tmp_path):

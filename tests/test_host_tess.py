@@ -128,3 +128,26 @@ def test_decompositions_match_the_python_harness():
             assert np.array_equal(m1, m2) and np.array_equal(x1, x2)
     with pytest.raises(RuntimeError):
         host_tess.kdtree_blocks(p, *dom, 6)
+
+
+def test_wider_rounds_insert_only_the_new_ghosts():
+    # a block whose first ghost margin is too narrow keeps its triangulation and inserts the additional ghosts; the
+    # result must be the block a single round at the final margin produces: same particles in the same order, same
+    # tets as a set (the Delaunay triangulation of points in general position is unique)
+    dom = ([0, 0, 0], [31, 31, 31])
+    p = particles.clustered_particles(30000, *dom, seed=77, n_clumps=6)
+    bounds, owner = host_tess.kdtree_blocks(p, *dom, 8)
+    multi = host_tess.tess(p, owner, bounds, *dom)
+    assert max(b["rounds"] for b in multi) >= 2
+    for b in multi:
+        if b["rounds"] < 2:
+            continue
+        one = host_tess.tess(p, owner, bounds, *dom, margin0=float(b["margin"]), max_rounds=1, gids=[b["gid"]])[0]
+        assert one["rounds"] == 1 and one["num_orig"] == b["num_orig"]
+        assert np.array_equal(one["global_ids"], b["global_ids"])
+        assert np.array_equal(one["particles"].view(np.uint32), b["particles"].view(np.uint32))
+        assert tet_set(one["tets"]) == tet_set(b["tets"])
+        check_adjacency(b["tets"], limit=1500)
+        v2t = b["vert_to_tet"]
+        used = v2t >= 0
+        assert (b["tets"][v2t[used], :4] == np.nonzero(used)[0][:, None]).any(axis=1).all()
