@@ -166,6 +166,12 @@ int tessb200_cell_volumes(tessb200_ctx *ctx, int num_sites, int num_particles, c
                           const int *tets, const int *vert_to_tet, float mass, int *complete, float *volume,
                           float *density);
 
+/* Per-site density of the first-order DTFE mode (NOT in the reference, see TESSB200_DENSE_DTFE): for every particle
+ * density[v] = 4 * mass / (sum of the volumes of the tets at v), -1 where the star is infinite or v is in no tet.
+ * vert_to_tet may be NULL. */
+int tessb200_dtfe_vertex_density(tessb200_ctx *ctx, int num_particles, const float *particles, int num_tets, const int *tets,
+                                 const int *vert_to_tet, float mass, float *density);
+
 /* ---- input check (host code, no device needed) ----
  * The kernels index `particles` with the tets' vertex ids and `tets` with their neighbour ids without range
  * checks, as the reference does (src/tet.cpp, src/dense.cpp trust tess()).  A caller that does not trust its

@@ -174,6 +174,15 @@ class Checker:
             n *= min(gs[d], int(frac * gs[d]) + 4)
         return n
 
+    def dtfe_vertex_density(self, num_verts, tets, particles, vert_to_tet, mass=1.0):
+        """port only: per-vertex density of the DTFE mode (oracle/dense_oracle.c, orc_dtfe_vertex_density)"""
+        tets = np.ascontiguousarray(tets, dtype=np.int32)
+        particles = np.ascontiguousarray(particles, dtype=np.float32)
+        v2t = np.ascontiguousarray(vert_to_tet, dtype=np.int32)
+        rho = np.empty(num_verts, dtype=np.float32)
+        self._f("dtfe_vertex_density")(C.c_int(num_verts), C.c_int(len(tets)), _ip(tets), _fp(particles), _ip(v2t), C.c_float(mass), _fp(rho))
+        return rho
+
     def cell_points(self, block, cell, data_mins, data_maxs, grid_phys_mins, step, mass=1.0, eps=1e-4, cap=1 << 16):
         arr = Block()
         pa = np.ascontiguousarray(block["particles"], dtype=np.float32)

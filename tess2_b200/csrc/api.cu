@@ -1304,6 +1304,46 @@ extern "C" int tessb200_cell_volumes(tessb200_ctx *c, int num_sites, int num_par
   return 0;
 }
 
+// Per-site density of the first-order DTFE mode (SURVEY 8(f) N4 "per-site DTFE density export"): what run_dtfe
+// computes for its blocks before rasterising, for one block's vertices.
+extern "C" int tessb200_dtfe_vertex_density(tessb200_ctx *c, int num_particles, const float *particles, int num_tets, const int *tets,
+                                            const int *vert_to_tet, float mass, float *density)
+{
+  if (!c || !particles || !density) return fail(TESSB200_EINVAL, "NULL argument");
+  CU(cudaSetDevice(c->device));
+  TmpBlock t;
+  TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, vert_to_tet));
+  if (num_particles == 0) return 0;
+  if (num_tets == 0) {
+    for (int i = 0; i < num_particles; i++) density[i] = -1.0f;
+    return 0;
+  }
+  TRY(prep_block_geometry(c, &t.b));
+  Buf d_rho, d_ovf, d_n, d_ws;
+  auto cleanup = [&]() { d_rho.release(); d_ovf.release(); d_n.release(); d_ws.release(); };
+  const uint32_t cap = (uint32_t)std::max(1024, num_particles / 64);
+  int rc = 0;
+  if ((rc = d_rho.ensure(4 * (size_t)num_particles)) || (rc = d_ovf.ensure(4 * (size_t)cap)) || (rc = d_n.ensure(4))) { cleanup(); return rc; }
+  cudaMemsetAsync(d_n.p, 0, 4, c->stream);
+  DevBlock db = dev_block(&t.b);
+  k_vertex_density<<<cdiv(num_particles, TOPO_THREADS), TOPO_THREADS, TOPO_SMEM, c->stream>>>(db, mass, d_rho.as<float>(), d_ovf.as<uint32_t>(),
+                                                                                              d_n.as<unsigned int>(), cap);
+  unsigned int n_ovf = 0;
+  cudaMemcpyAsync(&n_ovf, d_n.p, 4, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { cleanup(); return fail(TESSB200_ECUDA, "k_vertex_density: %s", cudaGetErrorString(e)); }
+  if (n_ovf > cap) { cleanup(); return fail(TESSB200_ELIMIT, "%u vertices exceed the fast star workspace", n_ovf); }
+  if (n_ovf) {
+    if ((rc = d_ws.ensure(sizeof(int) * (size_t)BIG_STAR_CAP * (size_t)n_ovf))) { cleanup(); return rc; }
+    k_vertex_density_big<<<cdiv((long long)n_ovf * 32, 128), 128, 0, c->stream>>>(db, mass, d_rho.as<float>(), d_ovf.as<uint32_t>(), (int)n_ovf, d_ws.as<int>());
+  }
+  cudaMemcpyAsync(density, d_rho.p, 4 * (size_t)num_particles, cudaMemcpyDeviceToHost, c->stream);
+  e = cudaStreamSynchronize(c->stream);
+  cleanup();
+  if (e != cudaSuccess) return fail(TESSB200_ECUDA, "vertex densities: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---- input check (host code) --------------------------------------------------------------------------
 extern "C" int tessb200_check_block(const tessb200_block *b, int deep)
 {

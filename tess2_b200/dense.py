@@ -232,6 +232,18 @@ class Context:
         return comp, vol, den
 
 
+    def dtfe_vertex_density(self, tets, particles, vert_to_tet=None, mass=1.0):
+        """Per-particle density of the first-order DTFE mode (not in the reference): 4 m / (volume of the star), -1 where
+        the star is infinite."""
+        tets = np.ascontiguousarray(tets, dtype=np.int32)
+        particles = np.ascontiguousarray(particles, dtype=np.float32)
+        v2t = None if vert_to_tet is None else np.ascontiguousarray(vert_to_tet, dtype=np.int32)
+        rho = np.empty(particles.shape[0], dtype=np.float32)
+        _l.check(self.lib.tessb200_dtfe_vertex_density(self.handle, particles.shape[0], _fp(particles), tets.shape[0], _ip(tets),
+                                                       _ip(v2t) if v2t is not None else None, float(mass), _fp(rho)))
+        return rho
+
+
 _default_ctx = {}
 
 

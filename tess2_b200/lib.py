@@ -18,7 +18,7 @@ EXPORTS = [
     "tessb200_dense", "tessb200_dense_upload", "tessb200_dense_run", "tessb200_dense_download",
     "tessb200_dense_geometry", "tessb200_dense_device_density",
     "tessb200_fill_vert_to_tet", "tessb200_circumcenters", "tessb200_cell_volumes",
-    "tessb200_write_grid", "tessb200_check_block",
+    "tessb200_write_grid", "tessb200_check_block", "tessb200_dtfe_vertex_density",
     "tessb200_comm_unique_id", "tessb200_comm_init", "tessb200_dense_set_layout",
 ]
 
@@ -99,6 +99,7 @@ def load():
     lib.tessb200_cell_volumes.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_int, i32p, i32p, C.c_float, i32p, f32p, f32p]
     lib.tessb200_write_grid.argtypes = [C.c_char_p, C.POINTER(DenseParams), C.c_int, C.POINTER(Block)]
     lib.tessb200_check_block.argtypes = [C.POINTER(Block), C.c_int]
+    lib.tessb200_dtfe_vertex_density.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int, i32p, i32p, C.c_float, f32p]
     lib.tessb200_comm_unique_id.argtypes = [C.c_void_p]
     lib.tessb200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.tessb200_dense_set_layout.argtypes = [C.c_void_p, C.c_int, i32p, f32p, i32p]

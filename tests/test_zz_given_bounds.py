@@ -63,3 +63,20 @@ def test_random_configurations_match_oracle(port):
     finally:
         ctx.close()
     assert compared >= 25
+
+
+@pytest.mark.parametrize("name", ["c1", "clump8", "tiny"])
+def test_dtfe_vertex_density_export(port, name):
+    # per-site density of the DTFE mode (not in the reference: compared with the repo's CPU statement)
+    import tess2_b200
+    ctx = tess2_b200.Context(0)
+    try:
+        for b in dataset(name)[:2]:
+            n = len(b["particles"])
+            want = port.dtfe_vertex_density(n, b["tets"], b["particles"], b["vert_to_tet"], mass=0.5)
+            got = ctx.dtfe_vertex_density(b["tets"], b["particles"], b["vert_to_tet"], mass=0.5)
+            assert_same_bits(got, want, f"{name} vertex densities")
+            assert_same_bits(ctx.dtfe_vertex_density(b["tets"], b["particles"], None, mass=0.5), want, f"{name} vertex densities, NULL vert_to_tet")
+            assert (want[want > 0] > 0).any() and (want == -1).any()       # hull vertices have no finite star
+    finally:
+        ctx.close()
