@@ -135,7 +135,7 @@ __attribute__((unused)) static tessb200_host_dblock *generate_and_tess(int tb, c
 #define GCHECK(x) do { int rc_ = (x); if (rc_) { fprintf(stderr, "%s failed (%d): %s\n", #x, rc_, tessb200_last_error()); exit(1); } } while (0)
 
 /* dense() + WriteGrid + dense_stats of the two density drivers (examples/dense/main.cpp:170-193) */
-static void dense_and_write(int alg, const grid_args *g, int nblocks, const tessb200_host_dblock *db, const char *outfile)
+__attribute__((unused)) static void dense_and_write(int alg, const grid_args *g, int nblocks, const tessb200_host_dblock *db, const char *outfile)
 {
   tessb200_ctx *ctx;
   GCHECK(tessb200_create(&ctx, 0));
