@@ -90,7 +90,7 @@ class Checker:
 
     # ---- the dense stage ---------------------------------------------------
     def dense(self, blocks, gsize, alg=0, mass=1.0, eps=1e-4, project=False, proj_plane=(0.0, 0.0, 1.0),
-              given_bounds=None, only_gid=-1, outfile=None, max_cells=-1):
+              given_bounds=None, only_gid=-1, outfile=None, max_cells=-1, first_cell=0):
         """blocks: list of dicts (gid, particles, num_orig, tets, bounds_min, bounds_max[, vert_to_tet]).
         Returns dict(grid=global [gz,gy,gx] (or [gy,gx] when projected... per-block arrays only),
         block_density=[...], block_min_idx, block_num_idx, params)."""
@@ -136,6 +136,8 @@ class Checker:
             p.glo_num_idx[d] = gs[d]
         p.mass = mass
         p.eps = eps
+        if first_cell:      # reference / port only: a window of cells [first_cell, max_cells) per block
+            self._f("set_cell_window")(C.c_int(first_cell))
         rc = self._f("dense")(C.byref(p), C.c_int(nb), arr, C.c_int(only_gid),
                               outfile.encode() if outfile else None, C.c_int(max_cells))
         if rc != 0:

@@ -135,6 +135,11 @@ static void fill_dblock(DBlock *b, const ref_block_t *rb, std::vector<int> &v2t_
 // skipped) -- used to time one block per OS process for the multi-core CPU baseline.
 // outfile != NULL: also run the reference's WriteGrid (dense.cpp:751-870).
 // max_cells >= 0: only the first max_cells cells of every (selected) block are visited.
+// ref_set_cell_window(first): the next ref_dense call also skips the cells below `first` (they are handed to the
+// reference with vert_to_tet = -1, which it skips at src/dense.cpp:251): with max_cells this gives a window of cells,
+// so that one block can be timed on several host cores at once.
+static int g_first_cell = 0;
+extern "C" void ref_set_cell_window(int first) { g_first_cell = first > 0 ? first : 0; }
 int ref_dense(ref_params_t *p, int nblocks, ref_block_t *blocks, int only_gid, const char *outfile, int max_cells)
 {
   diy::Master master;
@@ -155,6 +160,11 @@ int ref_dense(ref_params_t *p, int nblocks, ref_block_t *blocks, int only_gid, c
       b->num_orig_particles = 0;
     if (max_cells >= 0 && b->num_orig_particles > max_cells)
       b->num_orig_particles = max_cells; // bounded sample for the timed CPU baseline: cells [0, max_cells)
+    if (g_first_cell > 0 && b->num_orig_particles > 0) {
+      if (b->vert_to_tet != v2t[i].data()) v2t[i].assign(b->vert_to_tet, b->vert_to_tet + b->num_particles);   // the caller's array stays as it is
+      b->vert_to_tet = v2t[i].data();
+      for (int c = 0; c < g_first_cell && c < b->num_orig_particles; c++) v2t[i][c] = -1;
+    }
     for (int d = 0; d < 3; d++) {
       b->data_bounds.min[d] = dmin[d];
       b->data_bounds.max[d] = dmax[d];
@@ -217,6 +227,7 @@ int ref_dense(ref_params_t *p, int nblocks, ref_block_t *blocks, int only_gid, c
     delete[] dblocks[i]->density;
     delete dblocks[i];
   }
+  g_first_cell = 0;
   return rc;
 }
 

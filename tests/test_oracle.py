@@ -133,3 +133,23 @@ def test_port_given_bounds_match_reference(port, reference, gb):
             assert_same_bits(o1["step"], o2["step"], "step")
             for d1, d2 in zip(o1["block_density"], o2["block_density"]):
                 assert_same_bits(d1, d2, f"given {gb} alg{alg} proj{proj}")
+
+
+def test_cell_windows_partition_the_work(port, reference):
+    # bench.py's CPU legs cut a block's cells into windows so that every host core works: a window leaves the other
+    # cells to the reference with vert_to_tet = -1 (skipped at src/dense.cpp:251).  Port == reference on every window,
+    # and the windows add up to the whole run.
+    blocks = dataset("u16x8")
+    full = reference.dense(blocks, (32, 32, 32))["grid"].astype(np.float64)
+    acc = np.zeros_like(full)
+    for g in (0, 5):
+        for first in range(0, 512, 200):
+            o1 = reference.dense(blocks, (32, 32, 32), only_gid=g, first_cell=first, max_cells=first + 200)
+            o2 = port.dense(blocks, (32, 32, 32), only_gid=g, first_cell=first, max_cells=first + 200)
+            assert_same_bits(o1["grid"], o2["grid"], f"window {g}:{first}")
+    for g in range(8):
+        for first in range(0, 512, 200):
+            acc += reference.dense(blocks, (32, 32, 32), only_gid=g, first_cell=first, max_cells=first + 200)["grid"]
+    assert np.abs(acc - full).max() < 1e-5 * full.max()
+    # the caller's vert_to_tet is not touched
+    assert (blocks[0]["vert_to_tet"][:200] >= -1).all() and (blocks[0]["vert_to_tet"][:200] != -1).any()
