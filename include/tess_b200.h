@@ -83,7 +83,9 @@ typedef struct tessb200_block
 typedef struct tessb200_dense_params
 {
   int alg;                    /* TESSB200_DENSE_TESS / TESSB200_DENSE_CIC */
-  int num_given_bounds;       /* 0..3: leading axes whose grid extents are given */
+  int num_given_bounds;       /* 0..3: leading axes whose grid extents are given (src/dense.cpp:1725-1735).  Extents narrower than the
+                                 data: deposits without a grid element are dropped (the reference writes out of bounds there);
+                                 with project != 0 a given z range only sets the z sampling, every z index still deposits */
   float given_mins[3];
   float given_maxs[3];
   int project;                /* != 0: 2-D density, projection along z (the reference asserts xy only) */
