@@ -101,5 +101,13 @@ if os.path.exists(c3):
 L.append("## Parity\n\n`pytest -m gpu` on a 2-GPU box: 47 passed (bit equality with the oracle everywhere, including 2-GPU runs, the drop-in\n"
          "C++ header test, blocks from the repo's own tess driver and the plain-C example); opt-in `TESSB200_BIG_TESTS=1`: 128^3 clustered\n"
          "particles, kd-tree 16 blocks, 256^3 grid, global grid bit-identical to the oracle.\n")
+qc = os.path.join(P, "r01_quickcheck.txt")
+if os.path.exists(qc):
+    ok = [l.split()[1] for l in open(qc) if l.startswith("OK")]
+    bad = [l.split()[1] for l in open(qc) if l.startswith("FAIL")]
+    L.append("After the last capture (projection with a given z range narrower than the data, index boxes that start below the grid, the\n"
+             "reference drivers' command lines): `profiles/quick/run.sh` on a B200, the `dense` driver against the oracle's `dense.raw` byte for\n"
+             "byte -- %d cases identical (%s)%s.  The GPU tests written after that (`tests/test_zz_*.py`) have only run on the CPU side so far.\n"
+             % (len(ok), ", ".join(ok), "" if not bad else "; DIFFERENT: " + ", ".join(bad)))
 open(os.path.join(P, "r01_summary.md"), "w").write("\n".join(L) + "\n")
 print("\n".join(L))
