@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank for tess() (default cores / ranks)")
     ap.add_argument("--dry-run", action="store_true")
+    ap.add_argument("--limit-blocks", type=int, default=0, help="dry runs: tessellate only the first k of this rank's blocks")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -67,6 +68,8 @@ def main():
     t_gen = time.time() - t0
     owner = multi.assign_blocks(nb, world)
     my_gids = [g for g in range(nb) if owner[g] == rank]
+    if args.dry_run and args.limit_blocks > 0:
+        my_gids = my_gids[:args.limit_blocks]
     threads = args.threads or max(1, (os.cpu_count() or 1) // world)
     t0 = time.time()
     blocks = host_tess.tess(np.asarray(p), np.asarray(owner_of_particle), bounds, *dom, threads=threads, gids=my_gids)
