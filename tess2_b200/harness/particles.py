@@ -118,11 +118,13 @@ def _drop_duplicates(p, large=1 << 22):
     u = (p + np.float32(0.0)).view(np.uint32)            # -0.0 and 0.0 are the same point
     h = u[:, 0].astype(np.uint64) | (u[:, 1].astype(np.uint64) << np.uint64(32))
     h ^= u[:, 2].astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    hs = np.sort(h)                                      # the usual case ends here: no two rows share a hash
+    if not (hs[1:] == hs[:-1]).any():
+        return p
+    del hs
     order = np.argsort(h, kind="stable")
     hs = h[order]
     eq = hs[1:] == hs[:-1]
-    if not eq.any():
-        return p
     member = np.zeros(len(p), dtype=bool)
     member[1:] |= eq
     member[:-1] |= eq
