@@ -312,32 +312,43 @@ extern "C" int tessb200_host_kdtree_blocks(int num_particles, const float *parti
   for (int d = 0; d < 3; d++) { boxes[0].mn[d] = domain_min[d]; boxes[0].mx[d] = domain_max[d]; }
   boxes[0].idx.resize(num_particles);
   std::iota(boxes[0].idx.begin(), boxes[0].idx.end(), 0);
-  std::vector<float> x;
-  for (int level = 0; (int)boxes.size() < nblocks; level++) {
-    const int d = level % 3;
-    std::vector<Box> next;
-    next.reserve(boxes.size() * 2);
-    for (Box &b : boxes) {
-      float split;
-      const size_t n = b.idx.size();
-      if (n >= 2) {
-        x.resize(n);
-        for (size_t i = 0; i < n; i++) x[i] = particles[3 * (size_t)b.idx[i] + d];
-        const size_t m = n / 2;
-        std::nth_element(x.begin(), x.begin() + m, x.end());
-        const float hi = x[m], lo = *std::max_element(x.begin(), x.begin() + m);
-        split = (float)(((double)lo + (double)hi) * 0.5);
-        if (!(lo < split && split < hi)) split = hi;
-      } else {
-        split = (float)(((double)b.mn[d] + (double)b.mx[d]) * 0.5);
-      }
-      Box l, r;
-      memcpy(l.mn, b.mn, 12); memcpy(l.mx, b.mx, 12); memcpy(r.mn, b.mn, 12); memcpy(r.mx, b.mx, 12);
-      l.mx[d] = split; r.mn[d] = split;
-      for (int id : b.idx) (particles[3 * (size_t)id + d] < split ? l.idx : r.idx).push_back(id);
-      next.push_back(std::move(l));
-      next.push_back(std::move(r));
+  // the boxes of a level are independent: split them on host threads (the first levels have fewer boxes than cores)
+  auto split_box = [&](const Box &b, int d, Box &l, Box &r) {
+    float split;
+    const size_t n = b.idx.size();
+    if (n >= 2) {
+      std::vector<float> x(n);
+      for (size_t i = 0; i < n; i++) x[i] = particles[3 * (size_t)b.idx[i] + d];
+      const size_t m = n / 2;
+      std::nth_element(x.begin(), x.begin() + m, x.end());
+      const float hi = x[m], lo = *std::max_element(x.begin(), x.begin() + m);
+      split = (float)(((double)lo + (double)hi) * 0.5);
+      if (!(lo < split && split < hi)) split = hi;
+    } else {
+      split = (float)(((double)b.mn[d] + (double)b.mx[d]) * 0.5);
     }
+    memcpy(l.mn, b.mn, 12); memcpy(l.mx, b.mx, 12); memcpy(r.mn, b.mn, 12); memcpy(r.mx, b.mx, 12);
+    l.mx[d] = split; r.mn[d] = split;
+    l.idx.reserve(n / 2 + 1); r.idx.reserve(n / 2 + 1);
+    for (int id : b.idx) (particles[3 * (size_t)id + d] < split ? l.idx : r.idx).push_back(id);
+  };
+  const int hw = std::max(1, (int)std::thread::hardware_concurrency());
+  for (int level = 0; (int)boxes.size() < nblocks; level++) {
+    const int d = level % 3, nbox = (int)boxes.size();
+    std::vector<Box> next((size_t)nbox * 2);
+    std::atomic<int> cursor(0);
+    auto work = [&]() {
+      for (;;) {
+        const int k = cursor.fetch_add(1);
+        if (k >= nbox) return;
+        split_box(boxes[k], d, next[2 * (size_t)k], next[2 * (size_t)k + 1]);
+        std::vector<int>().swap(boxes[k].idx);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < std::min(hw, nbox); t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
     boxes.swap(next);
   }
   for (int g = 0; g < nblocks; g++) {
