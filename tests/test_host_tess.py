@@ -151,3 +151,48 @@ def test_wider_rounds_insert_only_the_new_ghosts():
         v2t = b["vert_to_tet"]
         used = v2t >= 0
         assert (b["tets"][v2t[used], :4] == np.nonzero(used)[0][:, None]).any(axis=1).all()
+
+
+def test_engine_is_exactly_delaunay_where_qhull_is_not():
+    # Coordinates far from the origin (float32 spacing 6e-5 at 1000 in a unit box): Qhull, working in double with
+    # tolerances, merges facets there and returns a different, smaller set of tets.  The engine's predicates are exact, so
+    # its result can be certified instead of compared: in rational arithmetic every tet is positively oriented, the
+    # neighbour relation is symmetric, every point is a vertex, and no vertex across a face lies inside the tet's
+    # circumsphere (local Delaunay property on every face => Delaunay).
+    from fractions import Fraction as F
+
+    def det3(a, b, c):
+        return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0])
+
+    def orient(a, b, c, d):
+        return det3(*[[p[i] - d[i] for i in range(3)] for p in (a, b, c)])
+
+    def insphere(a, b, c, d, e):
+        m = []
+        for p in (a, b, c, d):
+            v = [p[i] - e[i] for i in range(3)]
+            m.append(v + [v[0] * v[0] + v[1] * v[1] + v[2] * v[2]])
+        return sum((-1) ** j * m[0][j] * det3(*[[m[i][k] for k in range(4) if k != j] for i in range(1, 4)]) for j in range(4))
+
+    unit = [[F(0)] * 3, [F(1), F(0), F(0)], [F(0), F(1), F(0)], [F(0), F(0), F(1)]]
+    inside_sign = insphere(*unit, [F(1, 4)] * 3) * orient(*unit)        # sign of insphere * orient for a point inside
+    assert inside_sign != 0
+    for n, ext, off, seed in [(260, 1.0, 1000.0, 3), (300, 31.0, 31000.0, 4)]:
+        dom = ([off] * 3, [off + ext] * 3)
+        p = np.unique(particles.clustered_particles(n, *dom, seed=seed, n_clumps=3), axis=0)
+        t = host_tess.delaunay(p)
+        q = [[F(float(x)) for x in row] for row in p]
+        v, nb = t[:, :4], t[:, 4:]
+        assert len(np.unique(v)) == len(p)
+        for i in range(len(t)):
+            a, b, c, d = [q[k] for k in v[i]]
+            o = orient(a, b, c, d)
+            assert o > 0
+            for s in range(4):
+                u = nb[i, s]
+                if u < 0:
+                    continue
+                face = set(v[i].tolist()) - {v[i, s]}
+                opp = [x for x in v[u].tolist() if x not in face]
+                assert len(opp) == 1 and i in nb[u].tolist()
+                assert insphere(a, b, c, d, q[opp[0]]) * o * inside_sign <= 0, "a vertex inside a circumsphere"
