@@ -128,6 +128,8 @@ def cpu_jobs(blocks, max_cells, kind, cores):
     rank per block; when the box has more cores than blocks every block's sample is cut into windows of cells
     (cells are independent in the reference: src/dense.cpp:245-312), so that all host cores work."""
     parts = max(1, cores // max(1, len(blocks)))
+    smallest = min((min(b["num_orig"], max_cells) if max_cells >= 0 else b["num_orig"]) for b in blocks) if blocks else 0
+    parts = max(1, min(parts, smallest // 4096))      # a window below ~4096 cells measures process start-up, not dense()
     jobs = []
     for b in blocks:
         n = min(b["num_orig"], max_cells) if max_cells >= 0 else b["num_orig"]
