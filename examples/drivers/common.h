@@ -35,6 +35,7 @@ __attribute__((unused)) static int parse_grid_args(int argc, char **argv, int a,
   g->proj_plane[2] = 1.0f;
   if (argc < a + 6) return -1;
   for (int d = 0; d < 3; d++) g->gsize[d] = atoi(argv[a + d]);
+  if (g->gsize[0] < 2 || g->gsize[1] < 2 || g->gsize[2] < 2) return -1;
   a += 3;
   if (strcmp(argv[a], "!")) {
     if (argc < a + 5) return -1;
@@ -60,6 +61,7 @@ __attribute__((unused)) static int parse_grid_args(int argc, char **argv, int a,
  * jitter argument is unused there).  Returns tb blocks in dblock form, ready for tess_save or dense(). */
 __attribute__((unused)) static tessb200_host_dblock *generate_and_tess(int tb, const int *dsize, int wrap, int walls, float minvol, float maxvol, double *seconds)
 {
+  if (tb < 1 || dsize[0] < 2 || dsize[1] < 2 || dsize[2] < 2) { fprintf(stderr, "need tot_blocks >= 1 and a domain of at least 2 x 2 x 2\n"); exit(2); }
   if (wrap || walls) { fprintf(stderr, "wrap / walls are not supported by the single-process host driver\n"); exit(2); }
   if (minvol > 0.0f || maxvol > 0.0f) fprintf(stderr, "note: minvol / maxvol do not act on the tets handed to dense(); ignored\n");
   const float dmin[3] = {0, 0, 0}, dmax[3] = {dsize[0] - 1.0f, dsize[1] - 1.0f, dsize[2] - 1.0f};
