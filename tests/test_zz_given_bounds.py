@@ -33,8 +33,10 @@ def test_given_bounds_match_oracle(port, gb):
 def test_random_configurations_match_oracle(port):
     # tests/fuzz_logic.py's generator (distributions, offsets, 1-16 regular / kd-tree blocks, grids of 4-90 points,
     # both algorithms, 3-D / projected, eps, 0-3 given bounds wider or narrower than the data) through the CUDA path.
-    # Where the port reports deposits outside a block's sub-grid the reference is undefined: the run must still
-    # complete with finite values; everywhere else the bits must agree.
+    # The bits must agree with the port in every case: where the port reports deposits outside a block's sub-grid
+    # (the reference is undefined there; port and device logic both skip them) and where the reference's own
+    # arithmetic is non-finite (seed 2025 case 11: offset 1e4, CIC -- the 2*eps nudge vanishes in fp32, vol = 0,
+    # w = v0/vol, src/dense.cpp:1837-1841).  NaNs compare equal to NaNs (assert_same_bits).
     import tess2_b200
     import fuzz_logic
     rng = np.random.default_rng(2025)
@@ -54,9 +56,6 @@ def test_random_configurations_match_oracle(port):
             res = ctx.dense(args["alg"], 0 if gb is None else len(gb[0]), None if gb is None else gb[0], None if gb is None else gb[1],
                             args["project"], (0.0, 0.0, 1.0), args["mass"], args["eps"], gs, blocks)
             assert res.block_min_idx == o["block_min_idx"] and res.block_num_idx == o["block_num_idx"], desc
-            if o["out_of_range"]:
-                assert all(np.isfinite(d).all() for d in res.block_density), desc
-                continue
             for i, (d1, d2) in enumerate(zip(res.block_density, o["block_density"])):
                 assert_same_bits(d1, d2, f"case {case} block {i}: {desc}")
             compared += 1
