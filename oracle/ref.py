@@ -90,7 +90,7 @@ class Checker:
 
     # ---- the dense stage ---------------------------------------------------
     def dense(self, blocks, gsize, alg=0, mass=1.0, eps=1e-4, project=False, proj_plane=(0.0, 0.0, 1.0),
-              given_bounds=None, only_gid=-1, outfile=None, max_cells=-1, first_cell=0):
+              given_bounds=None, only_gid=-1, outfile=None, max_cells=-1, first_cell=0, assemble=True):
         """blocks: list of dicts (gid, particles, num_orig, tets, bounds_min, bounds_max[, vert_to_tet]).
         Returns dict(grid=global [gz,gy,gx] (or [gy,gx] when projected... per-block arrays only),
         block_density=[...], block_min_idx, block_num_idx, params)."""
@@ -161,7 +161,7 @@ class Checker:
         out["grid_phys_mins"] = np.array([p.grid_phys_mins[d] for d in range(3)], dtype=np.float32)
         out["data_mins"] = np.array([p.data_mins[d] for d in range(3)], dtype=np.float32)
         out["data_maxs"] = np.array([p.data_maxs[d] for d in range(3)], dtype=np.float32)
-        if not project:
+        if not project and assemble:
             out["grid"] = assemble_grid(gs, out["block_min_idx"], out["block_num_idx"], out["block_density"])
         return out
 

@@ -41,6 +41,15 @@ def broadcast_bytes(buf, src=0):
     return bytes(t.cpu().tolist())
 
 
+def set_layout(ctx, layout, owner):
+    """Install the decomposition (bounds and owner rank of every block) on this rank's Context."""
+    from . import lib as _l
+    lib = _l.load()
+    gids, b6, own = layout_arrays(layout, owner)
+    _l.check(lib.tessb200_dense_set_layout(ctx.handle, len(gids), gids.ctypes.data_as(_l.i32p), b6.ctypes.data_as(_l.f32p),
+                                           own.ctypes.data_as(_l.i32p)))
+
+
 def init_comm(ctx, layout, owner):
     """Join this rank's Context to the job-wide NCCL communicator and install the block layout."""
     import torch.distributed as dist
@@ -53,9 +62,7 @@ def init_comm(ctx, layout, owner):
     raw = broadcast_bytes(bytes(uid), src=0)
     uid = (C.c_ubyte * 128).from_buffer_copy(raw)
     _l.check(lib.tessb200_comm_init(ctx.handle, nranks, rank, uid))
-    gids, b6, own = layout_arrays(layout, owner)
-    _l.check(lib.tessb200_dense_set_layout(ctx.handle, len(gids), gids.ctypes.data_as(_l.i32p), b6.ctypes.data_as(_l.f32p),
-                                           own.ctypes.data_as(_l.i32p)))
+    set_layout(ctx, layout, owner)
     return rank, nranks
 
 
