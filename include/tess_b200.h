@@ -118,13 +118,15 @@ typedef struct tessb200_dense_stats
   float max_dense;            /* max over the final grid */
   float ms_upload, ms_circumcenters, ms_cells, ms_scan, ms_sort, ms_deposit, ms_exchange, ms_download;
   float ms_total_device;      /* inputs resident -> grid complete in device memory */
-  float ms_bfs, ms_nbrs, ms_faces; /* the three kernels inside ms_cells (resident runs only) */
+  float ms_bfs, ms_nbrs, ms_faces; /* the three kernels inside ms_cells (resident runs, TESSB200_FUSED=0 only) */
   int64_t num_faces;          /* Voronoi faces of the depositing cells (plane records) */
   int64_t num_candidates;     /* candidate neighbours handed from k_cell_bfs to k_cell_nbrs */
   float ms_slow_path;         /* general BFS for oversized stars + per-CTA scan of oversized cells (after the fast kernels) */
-  float reserved0;
+  float ms_fused;             /* k_cell_fused: star walk + faces + planes + inside bits of every cell the fast path holds */
   int64_t num_shared_deposits; /* deposits that met another one on their grid point and went through the ordered path;
                                   -1 when every record did (projection, or more shared deposits than the buffer holds) */
+  float ms_emit;              /* k_cell_emit: scan-line walk over the inside bits + span records */
+  float reserved1;
 } tessb200_dense_stats;
 
 typedef struct tessb200_ctx tessb200_ctx;

@@ -41,16 +41,16 @@ int main(int argc, char **argv)
     GCHECK(tessb200_dense_run(ctx, &p, &st));
     acc.ms_circumcenters += st.ms_circumcenters; acc.ms_bfs += st.ms_bfs; acc.ms_nbrs += st.ms_nbrs; acc.ms_faces += st.ms_faces;
     acc.ms_scan += st.ms_scan; acc.ms_sort += st.ms_sort; acc.ms_deposit += st.ms_deposit; acc.ms_slow_path += st.ms_slow_path;
-    acc.ms_total_device += st.ms_total_device;
+    acc.ms_total_device += st.ms_total_device; acc.ms_fused += st.ms_fused; acc.ms_emit += st.ms_emit;
   }
   const double k = 1.0 / (steps > 0 ? steps : 1), ms = acc.ms_total_device * k;
   const double g = project ? (double)gsize * gsize : (double)gsize * gsize * gsize;
   printf("{\"side\": %d, \"blocks\": %d, \"gsize\": %d, \"alg\": %d, \"project\": %d, \"steps\": %d, \"tess_s\": %.3f, \"tets\": %lld, \"cells\": %lld, "
          "\"deposit_cells\": %lld, \"spans\": %lld, \"shared_deposits\": %lld, \"slow_cells\": %lld, \"launches\": %lld, \"tot_mass\": %.6f, "
-         "\"ms\": {\"cc\": %.3f, \"bfs\": %.3f, \"nbrs\": %.3f, \"faces\": %.3f, \"scan\": %.3f, \"sort\": %.3f, \"deposit\": %.3f, \"slow\": %.3f, \"total\": %.3f}, "
+         "\"ms\": {\"fused\": %.3f, \"emit\": %.3f, \"cc\": %.3f, \"bfs\": %.3f, \"nbrs\": %.3f, \"faces\": %.3f, \"scan\": %.3f, \"sort\": %.3f, \"deposit\": %.3f, \"slow\": %.3f, \"total\": %.3f}, "
          "\"grid_points_per_sec\": %.4e}\n",
          side, tb, gsize, alg, project, steps, tess_s, (long long)st.num_tets, (long long)st.num_cells, (long long)st.num_deposit_cells, (long long)st.num_spans,
-         (long long)st.num_shared_deposits, (long long)st.num_slow_cells, (long long)st.num_kernel_launches, st.tot_mass, acc.ms_circumcenters * k, acc.ms_bfs * k,
+         (long long)st.num_shared_deposits, (long long)st.num_slow_cells, (long long)st.num_kernel_launches, st.tot_mass, acc.ms_fused * k, acc.ms_emit * k, acc.ms_circumcenters * k, acc.ms_bfs * k,
          acc.ms_nbrs * k, acc.ms_faces * k, acc.ms_scan * k, acc.ms_sort * k, acc.ms_deposit * k, acc.ms_slow_path * k, ms, ms > 0 ? g / (ms * 1e-3) : 0.0);
   tessb200_destroy(ctx);
   free(blk);

@@ -15,6 +15,7 @@
 #include <vector>
 #include "../../include/tess_b200.h"
 #include "kernels.cuh"
+#include "fused.cuh"
 #include "host_geom.hpp"
 #ifdef TESSB200_WITH_NCCL
 #include <nccl.h>
@@ -164,6 +165,9 @@ struct tessb200_ctx
 #endif
   Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, pre_hdr, cand, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
   Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2], x_small, pt_count;
+  Buf fz_hdr, fz_bits, fz_pool;     // k_cell_fused -> k_cell_emit: headers, in-line inside bits, pool for the larger index boxes
+  bool fused = false;               // TESSB200_FUSED=1 selects the one-kernel-per-cell path (fused.cuh; A/B measurements)
+  int fz_ctas = 0;
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
@@ -207,6 +211,16 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   CU(cudaFuncSetAttribute(k_cell_volumes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOL_SMEM));
   CU(cudaFuncSetAttribute(k_cell_nbrs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NBRS_SMEM));
   CU(cudaFuncSetAttribute(k_vertex_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TOPO_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
+  CU(cudaFuncSetAttribute(k_cell_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM));
+  {
+    const char *f = getenv("TESSB200_FUSED");
+    c->fused = f && f[0] == '1';        // opt-in: measured slower than the four-kernel path (profiles/r02/fused_a_*)
+    int per_sm = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cell_fused, FZ_THREADS, FZ_SMEM));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    c->fz_ctas = std::max(1, per_sm) * std::max(1, sms);
+  }
   *out = c;
   return 0;
 }
@@ -228,7 +242,8 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   free_blocks(c);
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->pre_hdr, &c->cand, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
-                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small, &c->pt_count};
+                 &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small, &c->pt_count,
+                 &c->fz_hdr, &c->fz_bits, &c->fz_pool};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -464,16 +479,17 @@ static DevBlock dev_block(const BlockRes *b)
   d.cell_base = b->cell_base;
   d.order = nullptr;
   d.cta_start = 0;
-  d.pad_ = 0;
+  d.slot_start = 0;
   return d;
 }
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
-static int prep_block_geometry(tessb200_ctx *c, BlockRes *b, bool want_walk = false)
+static int prep_block_geometry(tessb200_ctx *c, BlockRes *b, bool want_walk = false, bool want_hull = false)
 {
   if (want_walk && b->num_tets) TRY(b->walk.ensure(sizeof(WalkRec) * (size_t)b->num_tets));
-  if (want_walk) {
+  want_hull = want_hull || want_walk;
+  if (want_hull) {
     TRY(b->hull.ensure((size_t)std::max(1, b->num_particles)));
     CU(cudaMemsetAsync(b->hull.p, 0, (size_t)std::max(1, b->num_particles), c->stream));
   }
@@ -485,7 +501,7 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b, bool want_walk = fa
   }
   if (b->num_tets) {
     k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, (float4 *)b->cc.p,
-                                                                want_walk ? (WalkRec *)b->walk.p : nullptr, want_walk ? (unsigned char *)b->hull.p : nullptr);
+                                                                want_walk ? (WalkRec *)b->walk.p : nullptr, want_hull ? (unsigned char *)b->hull.p : nullptr);
     COUNT_LAUNCH(c, 1);
   }
   CU(cudaGetLastError());
@@ -711,6 +727,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   for (BlockRes *b : c->blocks) { cells += b->num_orig; tets += b->num_tets; }
   c->launches = 0;
   const bool tess = p->alg == TESSB200_DENSE_TESS;
+  const bool fused = tess && c->fused;
 
   CU(cudaEventRecord(c->ev[2], s));
   // groups of local blocks (indices into c->blocks)
@@ -729,17 +746,20 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   {
     long long order_off = 0;
     for (size_t gi = 0; gi < groups.size(); gi++) {
-      uint32_t ctas = 0;
+      uint32_t ctas = 0, slots = 0;
       for (int k = groups[gi].first; k < groups[gi].second; k++) {
         BlockRes *b = c->blocks[k];
         DevBlock &d = hblocks[first_local_all + k];
-        if (tess && b->num_tets) TRY(b->walk.ensure(sizeof(WalkRec) * (size_t)b->num_tets));
+        if (tess && !fused && b->num_tets) TRY(b->walk.ensure(sizeof(WalkRec) * (size_t)b->num_tets));
         if (tess) TRY(b->hull.ensure((size_t)std::max(1, b->num_particles)));
         d = dev_block(b);
+        if (fused) d.walk = nullptr;              // no walk records: the general kernels circulate on tet records + circumcenters
         d.order = c->order[1].as<uint32_t>() + order_off;
         order_off += b->num_orig;
         d.cta_start = ctas;
         ctas += cdiv(b->num_orig, TOPO_THREADS);
+        d.slot_start = slots;
+        slots += (uint32_t)b->num_orig;
       }
     }
   }
@@ -773,10 +793,12 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   uint32_t fast_pairs = 0;
   const int slow_warps = 148 * 4 * 4;          // persistent warps of the general star walk (four 4-warp CTAs per SM)
   if (tess) {
-    cap_ovf = (uint32_t)std::max<long long>(1024, cells / 64);
+    cap_ovf = fused ? (uint32_t)std::max<long long>(1024, cells) : (uint32_t)std::max<long long>(1024, cells / 64);
     // plane pool / face list: sum of faces <= 4 T, in pairs of faces
     if ((unsigned long long)2 * tets + (unsigned long long)cells + 64 >= 0xffffffffull) return fail(TESSB200_ELIMIT, "plane pool exceeds 2^32 face pairs");
     fast_pairs = (uint32_t)((unsigned long long)2 * tets + (unsigned long long)cells + 64);
+    // fused path: the pool holds only the cells the fast kernel hands to the general ones
+    if (fused) fast_pairs = (uint32_t)std::max<unsigned long long>(1ull << 20, (unsigned long long)fast_pairs / 4);
     TRY(c->plane_pool.ensure(48 * (size_t)fast_pairs));
     TRY(c->face_list.ensure(32 * (size_t)fast_pairs));
     TRY(c->hdr_small.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
@@ -790,6 +812,11 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     to.cap_pairs = fast_pairs;
     to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
     TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells)));
+    if (fused) {
+      TRY(c->fz_hdr.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
+      TRY(c->fz_bits.ensure(4 * (size_t)FZ_INLINE_WORDS * (size_t)std::max<long long>(1, cells)));
+      TRY(c->fz_pool.ensure(4 * (size_t)std::max<long long>(1 << 20, 8 * cells)));
+    }
   } else {
     TRY(ensure_spans(std::max<unsigned long long>(1ull << 16, 8ull * (unsigned long long)cells + 1024)));
   }
@@ -829,7 +856,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     }
     // K0 / K1 / processing order
     trace_mark(c, "group");
-    for (int k = k0; k < k1; k++) TRY(prep_block_geometry(c, c->blocks[k], true));
+    for (int k = k0; k < k1; k++) TRY(prep_block_geometry(c, c->blocks[k], !fused, true));
     trace_mark(c, "cc");
     if (!order_ready) TRY(prep_cell_order(c, k0, k1, cell_off));
     trace_mark(c, "order");
@@ -842,6 +869,30 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       const size_t n_slots = (size_t)gctas * TOPO_THREADS;
       long long gtets = 0;
       for (int k = k0; k < k1; k++) gtets += c->blocks[k]->num_tets;
+      if (fused) {
+        // one kernel per cell: star walk, faces, planes and inside bits stay in shared memory (fused.cuh); the scan-line
+        // walk + span records follow with one lane per cell.  Cells the fast path cannot hold land in the overflow list.
+        const long long goff = cell_off - gcells;
+        FusedOut fo;
+        fo.hdr = c->fz_hdr.as<CellHdr>() + goff;
+        fo.bits_inline = c->fz_bits.as<uint32_t>() + (size_t)goff * FZ_INLINE_WORDS;
+        fo.bits_pool = c->fz_pool.as<uint32_t>();
+        fo.pool_words = c->fz_pool.cap / 4;
+        fo.pool_cursor = &cnt->pool_cursor;
+        fo.overflow = c->overflow.as<uint2>();
+        fo.cap_overflow = cap_ovf;
+        fo.cnt = cnt;
+        const unsigned pairs = cdiv(gcells, FZ_CPW);
+        k_cell_fused<<<std::min<unsigned>(cdiv(pairs, FZ_WARPS), (unsigned)c->fz_ctas), FZ_THREADS, FZ_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0,
+                                                                                                            first_local_all + k1, (uint32_t)gcells, G.g, fo);
+        if (timed) CU(cudaEventRecord(c->ev[11], s));
+        trace_mark(c, "fused");
+        SpanOut so2{c->keys[0].as<uint64_t>(), c->data[0].as<uint64_t>(), span_cap, cnt};
+        k_cell_emit<<<cdiv(gcells, EMIT_WARPS * 32), EMIT_THREADS, EMIT_SMEM, s>>>(fo.hdr, (uint32_t)gcells, fo.bits_inline, fo.bits_pool, c->d_blocks.as<DevBlock>(),
+                                                                              sc, G.g, so2);
+        if (timed) CU(cudaEventRecord(c->ev[12], s));
+        trace_mark(c, "emit");
+      } else {
       TRY(c->pre_hdr.ensure(sizeof(CellHdr) * n_slots));
       TRY(c->cand.ensure(sizeof(int2) * n_slots * TOPO_CAND_CAP));
       k_cell_bfs<<<gctas, TOPO_THREADS, BFS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), first_local_all + k0, first_local_all + k1, G.g, to,
@@ -851,6 +902,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       k_cell_nbrs<<<gctas, TOPO_THREADS, NBRS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), to, c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
       if (timed) CU(cudaEventRecord(c->ev[12], s));
       trace_mark(c, "nbrs");
+      }
       // stars that did not fit the fast workspace: general BFS, persistent warps, the list range is read on
       // the device; it appends to the same lists, so the faces and scan launches below cover its cells too
       k_cell_bfs_big<<<slow_warps / 4, 128, 0, s>>>(c->d_blocks.as<DevBlock>(), G.g, to, c->overflow.as<uint2>(), c->ws_big.as<int>());
@@ -1114,10 +1166,12 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     st->ms_total_device = ms(2, 9);
     st->ms_download = io.pipelined ? ms(9, 14) : 0;
     const bool sub = one && tess && cells > 0;
-    st->ms_bfs = sub ? ms(4, 11) : 0;
-    st->ms_nbrs = sub ? ms(11, 12) : 0;
+    st->ms_bfs = sub && !fused ? ms(4, 11) : 0;
+    st->ms_nbrs = sub && !fused ? ms(11, 12) : 0;
     st->ms_faces = sub ? ms(13, 5) : 0;
-    st->num_faces = (int64_t)c->h_cnt->plane_cursor * 2;
+    st->ms_fused = sub && fused ? ms(4, 11) : 0;
+    st->ms_emit = sub && fused ? ms(11, 12) : 0;
+    st->num_faces = (int64_t)c->h_cnt->plane_cursor * 2 + (int64_t)c->h_cnt->n_faces_fused;
     st->num_candidates = (int64_t)c->h_cnt->n_cands;
     st->num_shared_deposits = n_shared_stat;
   }

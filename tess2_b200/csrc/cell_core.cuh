@@ -280,6 +280,16 @@ TB_HD int star_and_neighbors_hashed(int site, int t0, const int4 *tets, WS &ws, 
   return CELL_OK;
 }
 
+// hint: bring a line the walk will need a few visits from now into L1 / L2 (no register, no dependency)
+TB_HD void tb_prefetch(const void *p)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 TB_HD int tb_clz(uint32_t x)
 {
 #if defined(__CUDA_ARCH__)
@@ -604,6 +614,7 @@ TB_HD int star_bfs_rec(int site, int t0, const int4 *tets, const WalkRec *walk, 
   ws.hash_clear_vis();
   int ns = 0, ncand = 0;
   if (t0 > TB_STAR_TET_MASK) return CELL_OVERFLOW;
+  const int *verts_pf = reinterpret_cast<const int *>(tets);
   {
     const int4 v = tets[2 * (size_t)t0];
     const WalkRec r = walk[t0];
@@ -618,7 +629,10 @@ TB_HD int star_bfs_rec(int site, int t0, const int4 *tets, const WalkRec *walk, 
       const int next = tb_sel4(r.nb[0], r.nb[1], r.nb[2], r.nb[3], s);
       if (next < 0) return CELL_INCOMPLETE;
       if (next > TB_STAR_TET_MASK) return CELL_OVERFLOW;
-      if (vis_find_or_insert_tag(ws, next, walk_child_tag(r.perm, s, is), &ns, star_cap) < 0) return CELL_OVERFLOW;
+      const int tag = walk_child_tag(r.perm, s, is);
+      const int ins = vis_find_or_insert_tag(ws, next, tag, &ns, star_cap);
+      if (ins < 0) return CELL_OVERFLOW;
+      if (ins > 0) { tb_prefetch(&walk[next]); tb_prefetch(&verts_pf[8 * (size_t)next + ((tag >> 2) & 3)]); }
     }
   }
   // software pipeline: the record of the next tet in the queue and the candidate vertex it will hand
@@ -657,8 +671,13 @@ TB_HD int star_bfs_rec(int site, int t0, const int4 *tets, const WalkRec *walk, 
     const int n1 = tb_sel4(r.nb[0], r.nb[1], r.nb[2], r.nb[3], s1), n2 = tb_sel4(r.nb[0], r.nb[1], r.nb[2], r.nb[3], s2);
     if (n1 < 0 || n2 < 0) return CELL_INCOMPLETE;
     if ((n1 | n2) > TB_STAR_TET_MASK) return CELL_OVERFLOW;
-    if (vis_find_or_insert_tag(ws, n1, walk_child_tag(r.perm, s1, is), &ns, star_cap) < 0) return CELL_OVERFLOW;
-    if (vis_find_or_insert_tag(ws, n2, walk_child_tag(r.perm, s2, is), &ns, star_cap) < 0) return CELL_OVERFLOW;
+    const int tag1 = walk_child_tag(r.perm, s1, is), tag2 = walk_child_tag(r.perm, s2, is);
+    const int ins1 = vis_find_or_insert_tag(ws, n1, tag1, &ns, star_cap);
+    if (ins1 < 0) return CELL_OVERFLOW;
+    if (ins1 > 0) { tb_prefetch(&walk[n1]); tb_prefetch(&verts[8 * (size_t)n1 + ((tag1 >> 2) & 3)]); }
+    const int ins2 = vis_find_or_insert_tag(ws, n2, tag2, &ns, star_cap);
+    if (ins2 < 0) return CELL_OVERFLOW;
+    if (ins2 > 0) { tb_prefetch(&walk[n2]); tb_prefetch(&verts[8 * (size_t)n2 + ((tag2 >> 2) & 3)]); }
   }
   *n_star = ns;
   return CELL_OK;

@@ -35,8 +35,8 @@ struct DevBlock
   int num_orig, num_particles, num_tets;
   uint32_t cell_base;      // global number of this block's cell 0 (blocks in ascending gid order)
   const uint32_t *order;   // cells of the block in Morton order of their sites (processing order only)
-  uint32_t cta_start;      // first CTA of this block in the all-blocks BFS launch
-  uint32_t pad_;
+  uint32_t cta_start;      // first CTA of this block in the all-blocks BFS launch (k_cell_bfs)
+  uint32_t slot_start;     // first cell slot of this block in its group (k_cell_fused: slots are dense over the group's blocks)
 };
 
 // One accepted cell handed from k_cell_topo to the scan kernels (32 bytes)
@@ -63,6 +63,8 @@ struct Counters
   unsigned int pairs_done, small_done, ovf_done;
   unsigned int pad0;
   unsigned long long n_shared;                 // one-point records k_span_place handed to the sorted path
+  unsigned long long n_faces_fused;            // Voronoi faces (padded to pairs) of the cells k_cell_fused accepted
+  unsigned long long pool_cursor;              // words of the inside-bit pool handed out by k_cell_fused
 };
 
 struct FaceRef;
@@ -173,23 +175,24 @@ __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ 
   float det;
   circumcenter(a, b, c, d, o, &det);
   cc[t] = make_float4(o[0], o[1], o[2], fdiv(fabsf(det), 6.0f));   // w = tet volume (used by the DTFE mode)
+  if (!walk && !hull) return;
+  const int4 nb = __ldg(&tets[2 * (size_t)t + 1]);
+  const int vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {nb.x, nb.y, nb.z, nb.w};
   if (walk) {
-    const int4 nb = __ldg(&tets[2 * (size_t)t + 1]);
-    const int vv[4] = {v.x, v.y, v.z, v.w}, nn[4] = {nb.x, nb.y, nb.z, nb.w};
     WalkRec r;
     r.nb[0] = nb.x; r.nb[1] = nb.y; r.nb[2] = nb.z; r.nb[3] = nb.w;
     r.cx = o[0]; r.cy = o[1]; r.cz = o[2];
     r.perm = walk_perm(vv, nn, tets);
     walk[t] = r;
-    if (hull && (nb.x | nb.y | nb.z | nb.w) < 0) {
-      // a face without a neighbour: its three vertices have infinite Voronoi cells.  complete()
-      // finds exactly these by walking the star; the flag answers it before the walk starts.
+  }
+  if (hull && (nb.x | nb.y | nb.z | nb.w) < 0) {
+    // a face without a neighbour: its three vertices have infinite Voronoi cells.  complete()
+    // finds exactly these by walking the star; the flag answers it before the walk starts.
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (nn[i] < 0)
-          for (int j = 0; j < 4; j++)
-            if (j != i) hull[vv[j]] = 1;
-    }
+    for (int i = 0; i < 4; i++)
+      if (nn[i] < 0)
+        for (int j = 0; j < 4; j++)
+          if (j != i) hull[vv[j]] = 1;
   }
 }
 
@@ -627,11 +630,16 @@ __device__ __forceinline__ void cell_face(const FaceRef *__restrict__ faces, siz
   const float site[3] = {b.particles[3 * (size_t)r.site], b.particles[3 * (size_t)r.site + 1], b.particles[3 * (size_t)r.site + 2]};
   FaceAccum fa;
   fa.cmin = nullptr; fa.cmax = nullptr;
-  // slots of the site and of u in the first tet; from there on the walk follows slot permutations
-  const int4 v0 = b.tets[2 * (size_t)r.ut];
-  const int s_c = v0.x == r.site ? 0 : (v0.y == r.site ? 1 : (v0.z == r.site ? 2 : 3));
-  const int s_u = v0.x == r.u ? 0 : (v0.y == r.u ? 1 : (v0.z == r.u ? 2 : 3));
-  const int n = walk_edge_link_rec(s_c, s_u, r.ut, b.walk, fa);
+  int n;
+  if (b.walk) {
+    // slots of the site and of u in the first tet; from there on the walk follows slot permutations
+    const int4 v0 = b.tets[2 * (size_t)r.ut];
+    const int s_c = v0.x == r.site ? 0 : (v0.y == r.site ? 1 : (v0.z == r.site ? 2 : 3));
+    const int s_u = v0.x == r.u ? 0 : (v0.y == r.u ? 1 : (v0.z == r.u ? 2 : 3));
+    n = walk_edge_link_rec(s_c, s_u, r.ut, b.walk, fa);
+  } else {
+    n = walk_edge_link(r.site, r.u, r.ut, b.tets, b.cc, fa);      // no walk records (fused path): tet records + circumcenters
+  }
   float2 *dst = reinterpret_cast<float2 *>(plane_pool + f * 6);
   if (n < 0) {
     // the link did not close (malformed mesh): a NaN plane is never significant in PtInCell

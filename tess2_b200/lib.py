@@ -65,7 +65,8 @@ class DenseStats(C.Structure):
         ("ms_exchange", C.c_float), ("ms_download", C.c_float), ("ms_total_device", C.c_float),
         ("ms_bfs", C.c_float), ("ms_nbrs", C.c_float), ("ms_faces", C.c_float),
         ("num_faces", C.c_int64), ("num_candidates", C.c_int64),
-        ("ms_slow_path", C.c_float), ("reserved0", C.c_float), ("num_shared_deposits", C.c_int64),
+        ("ms_slow_path", C.c_float), ("ms_fused", C.c_float), ("num_shared_deposits", C.c_int64),
+        ("ms_emit", C.c_float), ("reserved1", C.c_float),
     ]
 
     def as_dict(self):
