@@ -126,7 +126,7 @@ typedef struct tessb200_dense_stats
   int64_t num_shared_deposits; /* deposits that met another one on their grid point and went through the ordered path;
                                   -1 when every record did (projection, or more shared deposits than the buffer holds) */
   float ms_emit;              /* k_cell_emit: scan-line walk over the inside bits + span records */
-  float reserved1;
+  float ms_direct;            /* k_cell_direct (cells with small index boxes: faces + planes + inside test + scan per thread); inside ms_scan */
 } tessb200_dense_stats;
 
 typedef struct tessb200_ctx tessb200_ctx;

@@ -166,12 +166,14 @@ struct tessb200_ctx
   Buf d_blocks, d_boxes, d_rblocks, d_cnt, plane_pool, face_list, pre_hdr, cand, hdr_small, hdr_big, big_bitoff, overflow, ws_big, bits_big;
   Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2], x_small, pt_count;
   Buf fz_hdr, fz_bits, fz_pool;     // k_cell_fused -> k_cell_emit: headers, in-line inside bits, pool for the larger index boxes
+  Buf hdr_dir[3];                   // cells of the small-box classes (k_cell_direct)
+  bool direct = true;               // TESSB200_DIRECT=0: every cell through k_cell_faces + k_cell_scan (A/B measurements)
   bool fused = false;               // TESSB200_FUSED=1 selects the one-kernel-per-cell path (fused.cuh; A/B measurements)
   int fz_ctas = 0;
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
-  cudaEvent_t ev[16];
+  cudaEvent_t ev[20];
   bool ran = false;
   long long launches = 0;           // kernels launched by the current run
   tessb200_dense_params last_params;
@@ -215,7 +217,9 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   CU(cudaFuncSetAttribute(k_cell_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EMIT_SMEM));
   {
     const char *f = getenv("TESSB200_FUSED");
-    c->fused = f && f[0] == '1';        // opt-in: measured slower than the four-kernel path (profiles/r02/fused_a_*)
+    c->fused = f && f[0] == '1';
+    const char *d = getenv("TESSB200_DIRECT");
+    c->direct = !(d && d[0] == '0');        // opt-in: measured slower than the four-kernel path (profiles/r02/fused_a_*)
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cell_fused, FZ_THREADS, FZ_SMEM));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -243,7 +247,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->pre_hdr, &c->cand, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
                  &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small, &c->pt_count,
-                 &c->fz_hdr, &c->fz_bits, &c->fz_pool};
+                 &c->fz_hdr, &c->fz_bits, &c->fz_pool, &c->hdr_dir[0], &c->hdr_dir[1], &c->hdr_dir[2]};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -811,6 +815,13 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     to.overflow = c->overflow.as<uint2>(); to.plane_pool = c->plane_pool.as<float>(); to.faces = c->face_list.as<FaceRef>(); to.cnt = cnt;
     to.cap_pairs = fast_pairs;
     to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
+    if (c->direct) {
+      for (int q = 0; q < 3; q++) {
+        TRY(c->hdr_dir[q].ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
+        to.dir[q] = c->hdr_dir[q].as<CellHdr>();
+      }
+      to.cap_dir = (uint32_t)cells;
+    }
     TRY(ensure_spans(std::max<unsigned long long>(1ull << 20, 6ull * (unsigned long long)cells)));
     if (fused) {
       TRY(c->fz_hdr.ensure(sizeof(CellHdr) * (size_t)std::max<long long>(1, cells)));
@@ -937,10 +948,27 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       k_cell_scan<<<cdiv(gcells, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(c->hdr_small.as<CellHdr>(), 0, c->plane_pool.as<float>(),
                                                                               c->d_blocks.as<DevBlock>(), sc, G.g, so, &cnt->small_done,
                                                                               &cnt->n_small, to.cap_small);
+      if (timed) CU(cudaEventRecord(c->ev[16], s));
+      if (to.cap_dir) {
+        // small index boxes: one thread per cell, planes applied to the whole box as they are produced (no plane storage)
+        const unsigned up = cdiv(gcells, DIRECT_THREADS);
+        const bool exact = !io.pipelined;      // resident runs read the counters before the faces launch
+        const unsigned g2 = exact ? cdiv(c->h_cnt->n_dir[0], DIRECT_THREADS) : up, g3 = exact ? cdiv(c->h_cnt->n_dir[1], DIRECT_THREADS) : up,
+                       g4 = exact ? cdiv(c->h_cnt->n_dir[2], DIRECT_THREADS) : up;
+        if (g2) k_cell_direct<2><<<g2, DIRECT_THREADS, 0, s>>>(to.dir[0], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
+                                                                       &cnt->dir_done[0], &cnt->n_dir[0], to.cap_dir, 0u);
+        if (g3) k_cell_direct<3><<<g3, DIRECT_THREADS, 0, s>>>(to.dir[1], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
+                                                                       &cnt->dir_done[1], &cnt->n_dir[1], to.cap_dir, 0u);
+        if (g4) k_cell_direct<4><<<g4, DIRECT_THREADS, 0, s>>>(to.dir[2], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
+                                                                       &cnt->dir_done[2], &cnt->n_dir[2], to.cap_dir, 0u);
+        COUNT_LAUNCH(c, (g2 ? 1 : 0) + (g3 ? 1 : 0) + (g4 ? 1 : 0));
+      }
+      if (timed) CU(cudaEventRecord(c->ev[17], s));
       k_advance<<<1, 1, 0, s>>>(cnt, to.cap_small);
       COUNT_LAUNCH(c, 6);
     } else {
-      if (timed) { CU(cudaEventRecord(c->ev[11], s)); CU(cudaEventRecord(c->ev[12], s)); CU(cudaEventRecord(c->ev[13], s)); CU(cudaEventRecord(c->ev[5], s)); }
+      if (timed) { CU(cudaEventRecord(c->ev[11], s)); CU(cudaEventRecord(c->ev[12], s)); CU(cudaEventRecord(c->ev[13], s)); CU(cudaEventRecord(c->ev[5], s));
+                   CU(cudaEventRecord(c->ev[16], s)); CU(cudaEventRecord(c->ev[17], s)); }
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->grp_ev[gi % 64], s));
@@ -986,6 +1014,12 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       k_cell_scan<<<cdiv(done_small, SCAN_WARPS * 32), SCAN_THREADS, SCAN_SMEM, s>>>(to.small, done_small, c->plane_pool.as<float>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
                                                                                   nullptr, nullptr, 0);
     if (done_big) TRY(scan_big_list(so));
+    if (to.cap_dir) {
+      const unsigned n2 = std::min(z.n_dir[0], to.cap_dir), n3 = std::min(z.n_dir[1], to.cap_dir), n4 = std::min(z.n_dir[2], to.cap_dir);
+      if (n2) k_cell_direct<2><<<cdiv(n2, DIRECT_THREADS), DIRECT_THREADS, 0, s>>>(to.dir[0], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so, nullptr, nullptr, 0u, n2);
+      if (n3) k_cell_direct<3><<<cdiv(n3, DIRECT_THREADS), DIRECT_THREADS, 0, s>>>(to.dir[1], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so, nullptr, nullptr, 0u, n3);
+      if (n4) k_cell_direct<4><<<cdiv(n4, DIRECT_THREADS), DIRECT_THREADS, 0, s>>>(to.dir[2], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so, nullptr, nullptr, 0u, n4);
+    }
     COUNT_LAUNCH(c, 2);
     CU(cudaGetLastError());
     TRY(read_counters(c));
@@ -1159,6 +1193,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     st->ms_circumcenters = one ? ms(3, 4) : 0;
     st->ms_cells = one ? ms(4, 5) : 0;
     st->ms_scan = one ? ms(5, 15) : ms(3, 15);    // pipelined: all cell stages together (they overlap the copies)
+    st->ms_direct = one && tess && cells > 0 ? ms(16, 17) : 0;   // part of ms_scan
     st->ms_slow_path = ms(15, 6) + (one && tess && cells > 0 ? ms(12, 13) : 0);   // oversized stars (general BFS) + oversized index boxes (per-CTA scan)
     st->ms_exchange = ms(6, 7);
     st->ms_sort = ms(7, 8);

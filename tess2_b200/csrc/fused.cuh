@@ -501,8 +501,9 @@ __global__ void __launch_bounds__(FZ_THREADS) k_cell_fused(const DevBlock *__res
 
 // ---- the scan-line walk + span emission of one cell per lane (phase 3 of k_cell_scan) -----------------------------------
 // h: this lane's header (any lane may be idle: in_sub == false); bits_w / lines_w: the warp's shared-memory slices;
-// p_off: bit offset of the lane's cell in bits_w.
-__device__ __forceinline__ void scan_emit_lane(const CellHdr &h, bool in_sub, int p_off, const uint32_t *bits_w, uint32_t *lines_w, int lane,
+// row(j, k) / inside(i, j, k): the inside bits of the lane's cell.
+template <class Row, class Inside>
+__device__ __forceinline__ void scan_emit_lane(const CellHdr &h, bool in_sub, Row row, Inside inside, uint32_t *lines_w, int lane,
                                                const ScanCtx &sc, const GridGeom &g, const DevBlock *__restrict__ blocks, const SpanOut &out)
 {
   const int e = (int)(h.blk_nf >> 16);
@@ -510,8 +511,6 @@ __device__ __forceinline__ void scan_emit_lane(const CellHdr &h, bool in_sub, in
   bool local_box = false, bitpath = false;
   float site[3] = {0, 0, 0};
   const int nx = (int)h.n3[0], ny = (int)h.n3[1], nz = (int)h.n3[2];
-  BitsInside inside{bits_w, (uint32_t)p_off, nx, ny};
-  RowBits row{bits_w, (uint32_t)p_off, nx, ny};
   if (in_sub) {
     int lo[3] = {h.lo[0], h.lo[1], h.lo[2]}, n3[3] = {nx, ny, nz};
     local_box = box_is_local(sc.boxes[e], lo, n3, sc.project);
@@ -581,6 +580,161 @@ __device__ __forceinline__ void scan_emit_lane(const CellHdr &h, bool in_sub, in
   __syncwarp();
 }
 
+
+// ---- k_cell_direct: one THREAD per cell for the small index boxes ---------------------------------------------------------
+// A cell whose index box holds at most M points along every axis (M = 2, 3, 4: two thirds of the cells of a clustered
+// set at two grid points per particle spacing) needs no plane storage at all: the thread walks its Voronoi faces one
+// after the other (fill_edge_link + NewellNormal, src/tet.cpp:389-409, src/dense.cpp:682-735) and applies every plane to
+// all M^3 points of the box at once -- the two "significant" flags of PtInCell (src/dense.cpp:1172-1203) are two 64-bit
+// masks with compile-time bit positions, the distance is the axis-separable form fadd(fadd(A[i], B[j]), C[k]) -- then
+// runs the scan-line state machine on the mask and writes its span records.  No shared memory besides the kept scan
+// lines, no plane pool, no inside-bit buffer: replaces k_cell_faces + k_cell_scan for these cells.
+template <int M>
+struct RegRow
+{
+  unsigned long long bits;
+  __device__ __forceinline__ uint32_t operator()(int j, int k) const { return (uint32_t)(bits >> ((k * M + j) * M)); }
+};
+template <int M>
+struct RegInside
+{
+  unsigned long long bits;
+  __device__ __forceinline__ bool operator()(int i, int j, int k) const { return (bits >> ((k * M + j) * M + i)) & 1ull; }
+};
+
+constexpr int DIRECT_THREADS = 128;
+template <int M>
+struct DirectSmem
+{
+  static constexpr int W = (M * M * M + 31) / 32;   // words of one cell's flags
+  CellHdr hdr[DIRECT_THREADS];
+  int off[DIRECT_THREADS + 1];                      // exclusive prefix of the cells' face counts
+  int warp_tot[DIRECT_THREADS / 32];
+  uint32_t pos[DIRECT_THREADS][W], neg[DIRECT_THREADS][W];
+  uint32_t lines[DIRECT_THREADS / 32][SCAN_LINE_CAP * 32];
+};
+
+// One CTA = 128 cells of one class.  Step 2 runs one thread per FACE over all faces of the CTA's cells (the lanes of a
+// warp then differ only in the length of their edge links), the flags of a cell are OR-ed into shared memory; step 3 is
+// one thread per cell.  (A first version with one thread per cell for everything ran at 8 of 32 active lanes: the cells
+// of a warp differ in face count AND link length; profiles/r02/direct_a_ncu.txt.)
+template <int M>
+__global__ void __launch_bounds__(DIRECT_THREADS) k_cell_direct(const CellHdr *__restrict__ hdrs, const FaceRef *__restrict__ faces,
+                                                               const DevBlock *__restrict__ blocks, ScanCtx sc, const __grid_constant__ GridGeom g,
+                                                               SpanOut out, const unsigned int *range_lo, const unsigned int *range_hi, uint32_t range_cap,
+                                                               uint32_t n_fixed)
+{
+  static_assert(M * M * M <= 64, "the inside flags of a cell live in one 64-bit mask");
+  __shared__ DirectSmem<M> S;
+  constexpr int W = DirectSmem<M>::W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t lo_i = 0, hi_i = n_fixed;
+  if (range_hi) {
+    lo_i = range_lo ? *range_lo : 0u;
+    hi_i = *range_hi < range_cap ? *range_hi : range_cap;
+  }
+  const uint32_t c0 = lo_i + blockIdx.x * DIRECT_THREADS;
+  if (c0 >= hi_i) return;                            // the whole CTA leaves together
+  const uint32_t idx = c0 + (uint32_t)tid;
+  const bool valid = idx < hi_i;
+  CellHdr h;
+  h.cell = 0; h.blk_nf = 0; h.lo[0] = h.lo[1] = h.lo[2] = 0; h.n3[0] = h.n3[1] = h.n3[2] = 1; h.pad = 0; h.plane_off = 0;
+  if (valid) h = hdrs[idx];
+  // ---- 1: headers and the prefix of the face counts ----
+  S.hdr[tid] = h;
+#pragma unroll
+  for (int w = 0; w < W; w++) { S.pos[tid][w] = 0u; S.neg[tid][w] = 0u; }
+  const int nf_mine = valid ? (int)(h.blk_nf & 0xffffu) : 0;
+  const int incl = warp_incl_scan(nf_mine);
+  if (lane == 31) S.warp_tot[warp] = incl;
+  __syncthreads();
+  int wbase = 0;
+#pragma unroll
+  for (int w = 0; w < DIRECT_THREADS / 32; w++) wbase += w < warp ? S.warp_tot[w] : 0;
+  S.off[tid] = wbase + incl - nf_mine;
+  if (tid == DIRECT_THREADS - 1) S.off[DIRECT_THREADS] = wbase + incl;
+  __syncthreads();
+  // ---- 2: one thread per Voronoi face ----
+  const int ftot = S.off[DIRECT_THREADS];
+  const float neg_eps = -g.eps;
+  for (int q0 = 0; q0 < ftot; q0 += DIRECT_THREADS) {
+    const int q = q0 + tid;
+    const bool fact = q < ftot;
+    int c = 0, n = -1;
+    float site[3] = {0.0f, 0.0f, 0.0f};
+    FaceAccum fa;
+    fa.cmin = nullptr; fa.cmax = nullptr;
+    if (fact) {
+#pragma unroll
+      for (int step = DIRECT_THREADS / 2; step >= 1; step >>= 1)
+        if (S.off[c + step] <= q) c += step;           // the last cell whose first face is at or before q
+      const int f = q - S.off[c];
+      const DevBlock &b = blocks[(int)(S.hdr[c].blk_nf >> 16)];
+      const FaceRef r = faces[(size_t)S.hdr[c].plane_off * 2 + f];
+      site[0] = b.particles[3 * (size_t)r.site]; site[1] = b.particles[3 * (size_t)r.site + 1]; site[2] = b.particles[3 * (size_t)r.site + 2];
+      if (b.walk) {
+        const int4 v0 = b.tets[2 * (size_t)r.ut];
+        const int s_c = v0.x == r.site ? 0 : (v0.y == r.site ? 1 : (v0.z == r.site ? 2 : 3));
+        const int s_u = v0.x == r.u ? 0 : (v0.y == r.u ? 1 : (v0.z == r.u ? 2 : 3));
+        n = walk_edge_link_rec(s_c, s_u, r.ut, b.walk, fa);
+      } else {
+        n = walk_edge_link(r.site, r.u, r.ut, b.tets, b.cc, fa);
+      }
+      if (n < 0) atomicAdd(&out.cnt->n_bad, 1ull);     // the link did not close: a NaN plane, never significant
+    }
+    // the links of a warp's faces differ in length: meet again before the (uniform) rest of the face
+    __syncwarp();
+    if (!fact || n < 0) continue;
+    const CellHdr &hc = S.hdr[c];
+    newell_term(fa.nrm, fa.prev, fa.v0);
+    newell_finish(fa.nrm, fa.v0, site);
+    // probe positions: cell_min_grid_pos + i * step (src/dense.cpp:1404,1530-1532); per-axis products of this plane
+    const float bx = idx2phys1(hc.lo[0], g.step[0], g.gmin[0]), by = idx2phys1(hc.lo[1], g.step[1], g.gmin[1]), bz = idx2phys1(hc.lo[2], g.step[2], g.gmin[2]);
+    float A[M], B[M], C[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+      A[i] = fmul(fa.nrm[0], fsub(fadd(bx, fmul((float)i, g.step[0])), fa.v0[0]));
+      B[i] = fmul(fa.nrm[1], fsub(fadd(by, fmul((float)i, g.step[1])), fa.v0[1]));
+      C[i] = fmul(fa.nrm[2], fsub(fadd(bz, fmul((float)i, g.step[2])), fa.v0[2]));
+    }
+    unsigned long long pos = 0ull, neg = 0ull;
+#pragma unroll
+    for (int j = 0; j < M; j++)
+#pragma unroll
+      for (int i = 0; i < M; i++) {
+        const float ab = fadd(A[i], B[j]);
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+          const float dist = fadd(ab, C[k]);
+          const unsigned long long bit = 1ull << ((k * M + j) * M + i);
+          if (dist > g.eps) pos |= bit;
+          if (dist < neg_eps) neg |= bit;
+        }
+      }
+    if ((uint32_t)pos) atomicOr(&S.pos[c][0], (uint32_t)pos);
+    if ((uint32_t)neg) atomicOr(&S.neg[c][0], (uint32_t)neg);
+    if (W > 1) {
+      if ((uint32_t)(pos >> 32)) atomicOr(&S.pos[c][W - 1], (uint32_t)(pos >> 32));
+      if ((uint32_t)(neg >> 32)) atomicOr(&S.neg[c][W - 1], (uint32_t)(neg >> 32));
+    }
+  }
+  __syncthreads();
+  // ---- 3: one thread per cell: the points the box really has, the scan-line walk, the span records ----
+  unsigned long long pos = S.pos[tid][0], neg = S.neg[tid][0];
+  if (W > 1) { pos |= (unsigned long long)S.pos[tid][W - 1] << 32; neg |= (unsigned long long)S.neg[tid][W - 1] << 32; }
+  unsigned long long vm = 0ull;
+  {
+    const unsigned long long rowm = (1ull << h.n3[0]) - 1ull;
+#pragma unroll
+    for (int k = 0; k < M; k++)
+#pragma unroll
+      for (int j = 0; j < M; j++)
+        if (k < (int)h.n3[2] && j < (int)h.n3[1]) vm |= rowm << ((k * M + j) * M);
+  }
+  const unsigned long long bits = ~(pos & neg) & vm;
+  scan_emit_lane(h, valid, RegRow<M>{bits}, RegInside<M>{bits}, S.lines[warp], lane, sc, g, blocks, out);
+}
+
 constexpr int EMIT_WARPS = 8;
 constexpr int EMIT_THREADS = EMIT_WARPS * 32;
 constexpr int EMIT_WARP_BYTES = (SCAN_BIT_WORDS + 4) * 4 + SCAN_LINE_CAP * 32 * 4;
@@ -620,7 +774,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_cell_emit(const CellHdr *__res
       for (int w = 0; w < nw; w++) bits_w[(p_off >> 5) + w] = src[w];
     }
     __syncwarp();
-    scan_emit_lane(h, in_sub, p_off, bits_w, lines_w, lane, sc, g, blocks, out);
+    scan_emit_lane(h, in_sub, RowBits{bits_w, (uint32_t)p_off, (int)h.n3[0], (int)h.n3[1]}, BitsInside{bits_w, (uint32_t)p_off, (int)h.n3[0], (int)h.n3[1]},
+                   lines_w, lane, sc, g, blocks, out);
     c0 = c1;
   }
 }

@@ -65,6 +65,7 @@ struct Counters
   unsigned long long n_shared;                 // one-point records k_span_place handed to the sorted path
   unsigned long long n_faces_fused;            // Voronoi faces (padded to pairs) of the cells k_cell_fused accepted
   unsigned long long pool_cursor;              // words of the inside-bit pool handed out by k_cell_fused
+  unsigned int n_dir[3], dir_done[3];          // cells of the three small-box classes handed to k_cell_direct (lengths, progress marks)
 };
 
 struct FaceRef;
@@ -77,7 +78,17 @@ struct TopoOut
   struct FaceRef *faces;   // face list, parallel to the plane pool
   Counters *cnt;
   uint32_t cap_small, cap_big, cap_overflow, cap_pairs;
+  CellHdr *dir[3];         // cells whose index box is at most 2 / 3 / 4 points along every axis: k_cell_direct
+  uint32_t cap_dir;        // 0: no direct classes
 };
+
+// class of an accepted cell for k_cell_direct: 0, 1, 2 for index boxes of at most 2, 3, 4 points per axis, else -1
+__device__ __forceinline__ int direct_class(const int *n3)
+{
+  const int mx = n3[0] > n3[1] ? (n3[0] > n3[2] ? n3[0] : n3[2]) : (n3[1] > n3[2] ? n3[1] : n3[2]);
+  return mx <= 2 ? 0 : (mx <= 3 ? 1 : (mx <= 4 ? 2 : -1));
+}
+constexpr int FACE_DIRECT = 0x40000000;   // FaceRef::blk flag: the cell goes through k_cell_direct, k_cell_faces skips the face
 
 struct SpanOut
 {
@@ -314,11 +325,12 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
   const uint32_t poff = warp_alloc<unsigned int>(&out.cnt->plane_cursor, want);
   // a pool that is too small drops the cell; the host sees the cursor past the capacity and reports it
   ok = ok && poff + want <= out.cap_pairs;
+  const int cls = ok && out.cap_dir ? direct_class(n3) : -1;
   if (ok) {
     FaceRef *fr = out.faces + (size_t)poff * 2;
     for (int k = 0; k < n_nbr; k++) {
       FaceRef r;
-      r.site = cell; r.u = ws.nu(k); r.ut = ws.nt(k); r.blk = blk_id;
+      r.site = cell; r.u = ws.nu(k); r.ut = ws.nt(k); r.blk = blk_id | (cls >= 0 ? FACE_DIRECT : 0);
       fr[k] = r;
     }
     if (n_nbr & 1) {
@@ -327,8 +339,8 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
       fr[n_nbr] = r;
     }
   }
-  const bool small = ok && n_nbr <= SCAN_FACE_CAP && npts <= SCAN_PTS_CAP;
-  const bool big = ok && !small;
+  const bool small = ok && cls < 0 && n_nbr <= SCAN_FACE_CAP && npts <= SCAN_PTS_CAP;
+  const bool big = ok && cls < 0 && !small;
   CellHdr h;
   h.cell = blk.cell_base + (uint32_t)cell;
   h.blk_nf = ((uint32_t)blk_id << 16) | (uint32_t)n_nbr;
@@ -344,6 +356,13 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
   if (big && b_slot < out.cap_big) {
     out.big[b_slot] = h;
     out.big_bit_off[b_slot] = boff;
+  }
+  if (out.cap_dir) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint32_t d_slot = warp_append<unsigned int>(&out.cnt->n_dir[c], cls == c);
+      if (cls == c && d_slot < out.cap_dir) out.dir[c][d_slot] = h;
+    }
   }
   warp_count(&out.cnt->n_no_tet, status == CELL_NO_TET);
   warp_count(&out.cnt->n_incomplete, status == CELL_INCOMPLETE);
@@ -501,11 +520,13 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_nbrs(const DevBlock *__re
   const uint32_t want = ok ? (uint32_t)((nn + 1) >> 1) : 0u;
   const uint32_t poff = warp_alloc<unsigned int>(&out.cnt->plane_cursor, want);
   ok = ok && poff + want <= out.cap_pairs;
+  const int n3i[3] = {(int)h.n3[0], (int)h.n3[1], (int)h.n3[2]};
+  const int cls = ok && out.cap_dir ? direct_class(n3i) : -1;
   if (ok) {
     FaceRef *fr = out.faces + (size_t)poff * 2;
     for (int k = 0; k < nn; k++) {
       FaceRef r;
-      r.site = (int)cell_local; r.u = ws.nu(k); r.ut = ws.nt(k); r.blk = blk_id;
+      r.site = (int)cell_local; r.u = ws.nu(k); r.ut = ws.nt(k); r.blk = blk_id | (cls >= 0 ? FACE_DIRECT : 0);
       fr[k] = r;
     }
     if (nn & 1) {
@@ -515,8 +536,8 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_nbrs(const DevBlock *__re
     }
   }
   const long long npts = (long long)h.n3[0] * h.n3[1] * h.n3[2];
-  const bool small = ok && nn <= SCAN_FACE_CAP && npts <= SCAN_PTS_CAP;
-  const bool big = ok && !small;
+  const bool small = ok && cls < 0 && nn <= SCAN_FACE_CAP && npts <= SCAN_PTS_CAP;
+  const bool big = ok && cls < 0 && !small;
   h.blk_nf = ((uint32_t)blk_id << 16) | (uint32_t)(ok ? nn : 0);
   h.plane_off = poff;
   uint32_t s_slot = warp_append<unsigned int>(&out.cnt->n_small, small);
@@ -527,6 +548,13 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_nbrs(const DevBlock *__re
   if (big && b_slot < out.cap_big) {
     out.big[b_slot] = h;
     out.big_bit_off[b_slot] = boff;
+  }
+  if (out.cap_dir) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint32_t d_slot = warp_append<unsigned int>(&out.cnt->n_dir[c], cls == c);
+      if (cls == c && d_slot < out.cap_dir) out.dir[c][d_slot] = h;
+    }
   }
 }
 
@@ -621,25 +649,34 @@ __global__ void __launch_bounds__(128) k_cell_bfs_big(const DevBlock *__restrict
 // K3a part 1b: one thread per Voronoi face: walk the tets around the Delaunay edge in the
 // reference's order, Newell normal, orientation, plane = (normal, first vertex) -> plane pool.
 // Tiny per-thread state and no shared memory: full occupancy hides the dependent gathers.
-__device__ __forceinline__ void cell_face(const FaceRef *__restrict__ faces, size_t f, const DevBlock *__restrict__ blocks,
+// `act`: this thread has a face (every lane of the warp calls: the links of a warp's faces differ in length, and the
+// lanes meet again -- __syncwarp -- before the uniform rest of the face: normalisation with one sqrt and three divisions)
+__device__ __forceinline__ void cell_face(const FaceRef *__restrict__ faces, size_t f, bool act, const DevBlock *__restrict__ blocks,
                                           float *__restrict__ plane_pool, Counters *cnt)
 {
-  const FaceRef r = faces[f];
-  if (r.u < 0) return;
-  const DevBlock &b = blocks[r.blk];
-  const float site[3] = {b.particles[3 * (size_t)r.site], b.particles[3 * (size_t)r.site + 1], b.particles[3 * (size_t)r.site + 2]};
+  FaceRef r;
+  r.site = 0; r.u = -1; r.ut = 0; r.blk = 0;
+  if (act) r = faces[f];
+  act = act && r.u >= 0 && !(r.blk & FACE_DIRECT);      // padding slot, or a cell that computes its own planes (k_cell_direct)
   FaceAccum fa;
   fa.cmin = nullptr; fa.cmax = nullptr;
-  int n;
-  if (b.walk) {
-    // slots of the site and of u in the first tet; from there on the walk follows slot permutations
-    const int4 v0 = b.tets[2 * (size_t)r.ut];
-    const int s_c = v0.x == r.site ? 0 : (v0.y == r.site ? 1 : (v0.z == r.site ? 2 : 3));
-    const int s_u = v0.x == r.u ? 0 : (v0.y == r.u ? 1 : (v0.z == r.u ? 2 : 3));
-    n = walk_edge_link_rec(s_c, s_u, r.ut, b.walk, fa);
-  } else {
-    n = walk_edge_link(r.site, r.u, r.ut, b.tets, b.cc, fa);      // no walk records (fused path): tet records + circumcenters
+  int n = -1;
+  float site[3] = {0.0f, 0.0f, 0.0f};
+  if (act) {
+    const DevBlock &b = blocks[r.blk];
+    site[0] = b.particles[3 * (size_t)r.site]; site[1] = b.particles[3 * (size_t)r.site + 1]; site[2] = b.particles[3 * (size_t)r.site + 2];
+    if (b.walk) {
+      // slots of the site and of u in the first tet; from there on the walk follows slot permutations
+      const int4 v0 = b.tets[2 * (size_t)r.ut];
+      const int s_c = v0.x == r.site ? 0 : (v0.y == r.site ? 1 : (v0.z == r.site ? 2 : 3));
+      const int s_u = v0.x == r.u ? 0 : (v0.y == r.u ? 1 : (v0.z == r.u ? 2 : 3));
+      n = walk_edge_link_rec(s_c, s_u, r.ut, b.walk, fa);
+    } else {
+      n = walk_edge_link(r.site, r.u, r.ut, b.tets, b.cc, fa);      // no walk records (fused path): tet records + circumcenters
+    }
   }
+  __syncwarp();
+  if (!act) return;
   float2 *dst = reinterpret_cast<float2 *>(plane_pool + f * 6);
   if (n < 0) {
     // the link did not close (malformed mesh): a NaN plane is never significant in PtInCell
@@ -659,8 +696,7 @@ __global__ void __launch_bounds__(256) k_cell_faces(const FaceRef *__restrict__ 
                                                      float *__restrict__ plane_pool, Counters *cnt)
 {
   const size_t f = f_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= f_end) return;
-  cell_face(faces, f, blocks, plane_pool, cnt);
+  cell_face(faces, f, f < f_end, blocks, plane_pool, cnt);
 }
 
 // The same over a range kept on the device, in pairs of faces: [*range_lo, min(*range_hi, cap)).  Persistent
@@ -670,8 +706,9 @@ __global__ void __launch_bounds__(256, 6) k_cell_faces_dev(const FaceRef *__rest
 {
   const uint32_t hi = *range_hi < range_cap ? *range_hi : range_cap;
   const size_t f_end = (size_t)hi * 2;
-  for (size_t f = (size_t)*range_lo * 2 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < f_end; f += (size_t)gridDim.x * blockDim.x)
-    cell_face(faces, f, blocks, plane_pool, cnt);
+  // every lane of a warp makes the same number of trips (cell_face synchronises the warp)
+  for (size_t f0 = (size_t)*range_lo * 2 + (size_t)blockIdx.x * blockDim.x; f0 < f_end; f0 += (size_t)gridDim.x * blockDim.x)
+    cell_face(faces, f0 + threadIdx.x, f0 + threadIdx.x < f_end, blocks, plane_pool, cnt);
 }
 
 // ---- span emission shared by the scan kernels and k_cic --------------------------------------------
@@ -1172,6 +1209,7 @@ __global__ void k_advance(Counters *cnt, uint32_t cap_small)
   cnt->pairs_done = cnt->plane_cursor;
   cnt->small_done = cnt->n_small < cap_small ? cnt->n_small : cap_small;
   cnt->ovf_done = cnt->n_overflow;
+  for (int c = 0; c < 3; c++) cnt->dir_done[c] = cnt->n_dir[c];
 }
 
 // ---- K3b: deposit.  Spans sorted by (row, remote, cell, z); one warp owns one row -----------------

@@ -66,7 +66,7 @@ class DenseStats(C.Structure):
         ("ms_bfs", C.c_float), ("ms_nbrs", C.c_float), ("ms_faces", C.c_float),
         ("num_faces", C.c_int64), ("num_candidates", C.c_int64),
         ("ms_slow_path", C.c_float), ("ms_fused", C.c_float), ("num_shared_deposits", C.c_int64),
-        ("ms_emit", C.c_float), ("reserved1", C.c_float),
+        ("ms_emit", C.c_float), ("ms_direct", C.c_float),
     ]
 
     def as_dict(self):
