@@ -7,6 +7,8 @@
 // point runs in the kernels of kernels.cuh.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -130,7 +132,7 @@ struct BlockRes
   int num_orig = 0, num_particles = 0, num_tets = 0;
   float bmin[3], bmax[3];
   bool have_v2t = false;
-  Buf particles, tets, v2t, cc, rho, walk, hull;
+  Buf particles, tets, v2t, cc, rho, walk, hull, p4;
   // geometry of the last run
   int mn[3], num[3];
   long long npts = 0, nrows = 0, row_base = 0, out_off = 0;
@@ -167,6 +169,9 @@ struct tessb200_ctx
   Buf keys[2], data[2], cub_tmp, row_start, out, stat_sum, stat_max, recv_keys, recv_data, mkeys[2], order[2], x_small, pt_count;
   Buf fz_hdr, fz_bits, fz_pool;     // k_cell_fused -> k_cell_emit: headers, in-line inside bits, pool for the larger index boxes
   Buf hdr_dir[3];                   // cells of the small-box classes (k_cell_direct)
+  Buf pt_off, pt_fill, big_points;  // shared grid points: segment offsets, fill cursors, the points with many deposits
+  bool segments = false;            // TESSB200_SEGMENTS=1: shared deposits through per-point segments instead of the radix sort + k_rows
+                                    // (faster on uniform input, slower where clumps put hundreds of deposits on one point: profiles/r02)
   bool direct = true;               // TESSB200_DIRECT=0: every cell through k_cell_faces + k_cell_scan (A/B measurements)
   bool fused = false;               // TESSB200_FUSED=1 selects the one-kernel-per-cell path (fused.cuh; A/B measurements)
   int fz_ctas = 0;
@@ -219,7 +224,10 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
     const char *f = getenv("TESSB200_FUSED");
     c->fused = f && f[0] == '1';
     const char *d = getenv("TESSB200_DIRECT");
-    c->direct = !(d && d[0] == '0');        // opt-in: measured slower than the four-kernel path (profiles/r02/fused_a_*)
+    c->direct = !(d && d[0] == '0');
+    const char *sg = getenv("TESSB200_SEGMENTS");
+    c->segments = sg && sg[0] == '1';
+    CU(cudaFuncSetAttribute(k_point_apply_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POINT_BIG_SMEM));        // opt-in: measured slower than the four-kernel path (profiles/r02/fused_a_*)
     int per_sm = 0, sms = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cell_fused, FZ_THREADS, FZ_SMEM));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -232,7 +240,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
 static void free_blocks(tessb200_ctx *c)
 {
   for (BlockRes *b : c->blocks) {
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release(); b->hull.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release(); b->hull.release(); b->p4.release();
     delete b;
   }
   c->blocks.clear();
@@ -247,7 +255,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->pre_hdr, &c->cand, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
                  &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small, &c->pt_count,
-                 &c->fz_hdr, &c->fz_bits, &c->fz_pool, &c->hdr_dir[0], &c->hdr_dir[1], &c->hdr_dir[2]};
+                 &c->fz_hdr, &c->fz_bits, &c->fz_pool, &c->hdr_dir[0], &c->hdr_dir[1], &c->hdr_dir[2], &c->pt_off, &c->pt_fill, &c->big_points};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -425,7 +433,7 @@ static int upload_impl(tessb200_ctx *c, int nblocks, const tessb200_block *block
     if (blocks[order[i]].gid == blocks[order[i - 1]].gid) return fail(TESSB200_EINVAL, "duplicate gid %d", blocks[order[i]].gid);
   while ((int)c->blocks.size() > nblocks) {
     BlockRes *b = c->blocks.back();
-    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release(); b->hull.release();
+    b->particles.release(); b->tets.release(); b->v2t.release(); b->cc.release(); b->rho.release(); b->walk.release(); b->hull.release(); b->p4.release();
     delete b;
     c->blocks.pop_back();
   }
@@ -504,7 +512,15 @@ static int prep_block_geometry(tessb200_ctx *c, BlockRes *b, bool want_walk = fa
     if (b->num_tets) { k_vert_to_tet<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (int *)b->v2t.p); COUNT_LAUNCH(c, 1); }
   }
   if (b->num_tets) {
-    k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, (float4 *)b->cc.p,
+    // 16-byte particle records for the gathers (the packed xyz array stays what every other kernel reads)
+    const float4 *p4 = nullptr;
+    if (b->num_particles && b->num_tets >= 4096) {
+      TRY(b->p4.ensure(sizeof(float4) * (size_t)b->num_particles));
+      k_pack_particles<<<cdiv(b->num_particles, 256), 256, 0, c->stream>>>((const float *)b->particles.p, b->num_particles, b->p4.as<float4>());
+      COUNT_LAUNCH(c, 1);
+      p4 = b->p4.as<float4>();
+    }
+    k_circumcenters<<<cdiv(b->num_tets, 256), 256, 0, c->stream>>>((const int4 *)b->tets.p, b->num_tets, (const float *)b->particles.p, p4, (float4 *)b->cc.p,
                                                                 want_walk ? (WalkRec *)b->walk.p : nullptr, want_hull ? (unsigned char *)b->hull.p : nullptr);
     COUNT_LAUNCH(c, 1);
   }
@@ -1068,9 +1084,54 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     return 0;
   };
 
-  // 3-D runs: only the deposits that meet on a grid point go through the sort (kernels.cuh, "K3b without the big sort")
+  // 3-D runs: only the deposits that meet on a grid point need the reference's order (kernels.cuh, "K3b without the big sort")
   bool placed = false;
-  if (!G.g.project && n_spans && G.out_floats) {
+  if (!G.g.project && n_spans && G.out_floats && c->segments && G.kl.cell_bits <= 31 && G.out_floats < 0xffffffffll) {
+    // every shared point gets a segment of 8-byte records (offsets = scan of the counts); a point's few records are
+    // sorted where they are applied: no global sort, no host read-back before the deposit
+    const unsigned long long seg_cap = span_cap;                    // the second half of the double buffer
+    const size_t npts = (size_t)G.out_floats;
+    const unsigned int big_cap = (unsigned int)std::min<unsigned long long>(0x7fffffffull, std::max<unsigned long long>(1ull << 16, span_cap / 8));
+    TRY(c->pt_count.ensure(4 * npts));
+    TRY(c->pt_off.ensure(4 * npts));
+    TRY(c->pt_fill.ensure(4 * npts));
+    TRY(c->big_points.ensure(4 * (size_t)big_cap));
+    CU(cudaMemsetAsync(c->pt_count.p, 0, 4 * npts, s));
+    CU(cudaMemsetAsync(c->pt_fill.p, 0, 4 * npts, s));
+    CU(cudaMemsetAsync(c->out.p, 0, sizeof(float) * npts, s));
+    CU(cudaMemsetAsync(&cnt->n_shared, 0, sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(&cnt->n_big_points, 0, 2 * sizeof(unsigned int), s));      // n_big_points, dep_flags
+    const unsigned grid = cdiv((long long)n_spans, 256);
+    k_span_count<<<grid, 256, 0, s>>>(c->keys[cur].as<uint64_t>(), c->data[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->d_rblocks.as<RowBlock>(),
+                                      (int)G.rblocks.size(), c->pt_count.as<unsigned int>());
+    {
+      auto it = thrust::make_transform_iterator((const unsigned int *)c->pt_count.as<unsigned int>(), SharedCount());
+      size_t tmp = 0;
+      CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, c->pt_off.as<unsigned int>(), (int)npts, s));
+      TRY(c->cub_tmp.ensure(tmp));
+      CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, it, c->pt_off.as<unsigned int>(), (int)npts, s));
+    }
+    k_span_place2<<<grid, 256, 0, s>>>(c->keys[cur].as<uint64_t>(), c->data[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->d_rblocks.as<RowBlock>(),
+                                       (int)G.rblocks.size(), c->pt_count.as<unsigned int>(), c->pt_off.as<unsigned int>(), c->pt_fill.as<unsigned int>(), G.g.div,
+                                       c->out.as<float>(), c->keys[cur ^ 1].as<uint64_t>(), seg_cap, cnt);
+    CU(cudaEventRecord(c->ev[8], s));      // ms_sort (7 -> 8): count + scan + place; ms_deposit: the ordered accumulation on the shared points
+    k_point_apply<<<cdiv((long long)npts, 256), 256, 0, s>>>(c->pt_count.as<unsigned int>(), c->pt_off.as<unsigned int>(), c->keys[cur ^ 1].as<uint64_t>(), seg_cap,
+                                                            (unsigned long long)npts, G.g.div, p->alg == TESSB200_DENSE_CIC ? 1 : 0, c->out.as<float>(),
+                                                            c->big_points.as<unsigned int>(), big_cap, cnt);
+    k_point_apply_big<<<148 * 8, POINT_BIG_WARPS * 32, POINT_BIG_SMEM, s>>>(c->pt_count.as<unsigned int>(), c->pt_off.as<unsigned int>(), c->keys[cur ^ 1].as<uint64_t>(),
+                                                                          seg_cap, G.g.div, p->alg == TESSB200_DENSE_CIC ? 1 : 0, c->out.as<float>(),
+                                                                          c->big_points.as<unsigned int>(), big_cap, cnt);
+    COUNT_LAUNCH(c, 4);
+    CU(cudaGetLastError());
+    TRY(read_counters(c));
+    if (!c->h_cnt->dep_flags && c->h_cnt->n_big_points <= big_cap) {
+      placed = true;
+      n_shared_stat = (long long)c->h_cnt->n_shared;
+      if (io.pipelined) TRY(copy_out_all());
+    }
+    // else: more shared deposits than the buffer holds (a grid far coarser than the cells): the full sort below
+  } else if (!G.g.project && n_spans && G.out_floats) {
+    // round 1's form of the same idea: the shared deposits as one-point records through the radix sort and k_rows
     const unsigned long long shared_cap = span_cap;                 // the second half of the double buffer
     TRY(c->pt_count.ensure(sizeof(unsigned int) * (size_t)G.out_floats));
     CU(cudaMemsetAsync(c->pt_count.p, 0, sizeof(unsigned int) * (size_t)G.out_floats, s));
@@ -1301,7 +1362,7 @@ extern "C" int tessb200_dense(tessb200_ctx *c, tessb200_dense_params *p, int nbl
 struct TmpBlock
 {
   BlockRes b;
-  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.rho.release(); b.walk.release(); b.hull.release(); }
+  ~TmpBlock() { b.particles.release(); b.tets.release(); b.v2t.release(); b.cc.release(); b.rho.release(); b.walk.release(); b.hull.release(); b.p4.release(); }
 };
 
 static int upload_tmp(tessb200_ctx *c, TmpBlock &t, int num_particles, const float *particles, int num_tets, const int *tets, const int *v2t)
@@ -1344,7 +1405,7 @@ extern "C" int tessb200_circumcenters(tessb200_ctx *c, int num_particles, const 
   TmpBlock t;
   TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, nullptr));
   if (num_tets) {
-    k_circumcenters<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (const float *)t.b.particles.p, (float4 *)t.b.cc.p, nullptr, nullptr);
+    k_circumcenters<<<cdiv(num_tets, 256), 256, 0, c->stream>>>((const int4 *)t.b.tets.p, num_tets, (const float *)t.b.particles.p, nullptr, (float4 *)t.b.cc.p, nullptr, nullptr);
     CU(cudaGetLastError());
     // float4 -> packed xyz on the way out (the reference's std::vector<float> layout, volume.cpp:8)
     CU(cudaMemcpy2DAsync(out, 12, t.b.cc.p, 16, 12, (size_t)num_tets, cudaMemcpyDeviceToHost, c->stream));

@@ -66,6 +66,8 @@ struct Counters
   unsigned long long n_faces_fused;            // Voronoi faces (padded to pairs) of the cells k_cell_fused accepted
   unsigned long long pool_cursor;              // words of the inside-bit pool handed out by k_cell_fused
   unsigned int n_dir[3], dir_done[3];          // cells of the three small-box classes handed to k_cell_direct (lengths, progress marks)
+  unsigned int n_big_points;                   // grid points with more than POINT_SMALL deposits (k_point_apply -> k_point_apply_big)
+  unsigned int dep_flags;                      // 1: the segment buffer was too small for the shared deposits (the run falls back to the sorted path)
 };
 
 struct FaceRef;
@@ -166,22 +168,36 @@ __global__ void k_vert_to_tet(const int4 *__restrict__ tets, int num_tets, int *
   atomicMax(&v2t[v.w], t);
 }
 
+// xyz -> one 16-byte record per particle: K1 gathers four particles per tet, and a 16-byte gather is one sector
+// where three 4-byte gathers at a 12-byte stride are up to two
+__global__ void k_pack_particles(const float *__restrict__ particles, int n, float4 *__restrict__ p4)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p4[i] = make_float4(particles[3 * (size_t)i], particles[3 * (size_t)i + 1], particles[3 * (size_t)i + 2], 0.0f);
+}
+
 // ---- K1: circumcenters, one thread per tet ---------------------------------------------------------
 // reads 16 B of the tet record (verts only) + 4 gathered particles, writes one float4 (x, y, z, volume)
 __global__ void __launch_bounds__(256) k_circumcenters(const int4 *__restrict__ tets, int num_tets,
-                                                        const float *__restrict__ particles, float4 *__restrict__ cc, WalkRec *__restrict__ walk,
-                                                        unsigned char *__restrict__ hull)
+                                                        const float *__restrict__ particles, const float4 *__restrict__ p4, float4 *__restrict__ cc,
+                                                        WalkRec *__restrict__ walk, unsigned char *__restrict__ hull)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_tets) return;
   int4 v = __ldg(&tets[2 * (size_t)t]);
   float a[3], b[3], c[3], d[3], o[3];
+  if (p4) {
+    const float4 pa = __ldg(&p4[v.x]), pb = __ldg(&p4[v.y]), pc = __ldg(&p4[v.z]), pd = __ldg(&p4[v.w]);
+    a[0] = pa.x; a[1] = pa.y; a[2] = pa.z; b[0] = pb.x; b[1] = pb.y; b[2] = pb.z;
+    c[0] = pc.x; c[1] = pc.y; c[2] = pc.z; d[0] = pd.x; d[1] = pd.y; d[2] = pd.z;
+  } else {
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    a[i] = __ldg(&particles[3 * (size_t)v.x + i]);
-    b[i] = __ldg(&particles[3 * (size_t)v.y + i]);
-    c[i] = __ldg(&particles[3 * (size_t)v.z + i]);
-    d[i] = __ldg(&particles[3 * (size_t)v.w + i]);
+    for (int i = 0; i < 3; i++) {
+      a[i] = __ldg(&particles[3 * (size_t)v.x + i]);
+      b[i] = __ldg(&particles[3 * (size_t)v.y + i]);
+      c[i] = __ldg(&particles[3 * (size_t)v.z + i]);
+      d[i] = __ldg(&particles[3 * (size_t)v.w + i]);
+    }
   }
   float det;
   circumcenter(a, b, c, d, o, &det);
@@ -1396,6 +1412,185 @@ __global__ void k_span_place(const uint64_t *__restrict__ keys, const uint64_t *
         shared_data[pos] = (d & 0xffffffff80000000ull) | (1ull << 16) | (uint64_t)(unsigned)x;
       }
       pos++;
+    }
+  }
+}
+
+
+// ---- K3b, shared grid points without a global sort ------------------------------------------------------
+// Grid points that receive more than one deposit need the reference's accumulation order: the owner block's own cells in
+// cell order, then received points by source gid (cell numbers ascend with the gid; src/dense.cpp:286-296,187-199).
+// Instead of sorting every shared deposit by (row, remote, cell), each shared POINT gets a segment: offsets = exclusive
+// scan of the per-point counts (k_span_count), k_span_place2 drops each shared deposit into its point's segment as one
+// 8-byte record  (remote << 31 | cell) << 32 | value  -- so ascending records ARE the reference's order -- and
+// k_point_apply sorts the few records of a point in registers and accumulates them.  Points with many deposits (the
+// centres of clumps: hundreds) go to k_point_apply_big, one warp per point, bitonic sort in shared memory.
+struct SharedCount
+{
+  __host__ __device__ __forceinline__ unsigned int operator()(const unsigned int &c) const { return c > 1u ? c : 0u; }
+};
+
+constexpr int POINT_SMALL = 8;        // records sorted in registers by one thread
+constexpr int POINT_WARP_CAP = 2048;  // records sorted in shared memory by one warp
+constexpr int POINT_BIG_WARPS = 2;
+constexpr size_t POINT_BIG_SMEM = (size_t)POINT_BIG_WARPS * POINT_WARP_CAP * 8;
+
+__global__ void k_span_place2(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ data, unsigned long long n, KeyLayout kl,
+                              unsigned long long row0, unsigned long long nrows, const RowBlock *__restrict__ rblocks, int n_rblocks,
+                              const unsigned int *__restrict__ count, const unsigned int *__restrict__ seg_off, unsigned int *__restrict__ fill, float div,
+                              float *__restrict__ out, uint64_t *__restrict__ seg, unsigned long long seg_cap, Counters *cnt)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t key = 0, d = 0;
+  long long base = 0;
+  int x0 = 0, x1 = 0;
+  bool live = false;
+  if (i < n) {
+    key = keys[i];
+    d = data[i];
+    live = span_target(key, d, kl, row0, nrows, rblocks, n_rblocks, base, x0, x1);
+  }
+  unsigned long long mine = 0;
+  if (live) {
+    // double path: (float)((double)0 + (double)m / (double)div)  (src/dense.cpp:290,193); float path: 0 + m / div  (:539)
+    const float m = u2f((uint32_t)(d >> 32));
+    const float v = ((d >> 31) & 1u) ? fadd(0.0f, fdiv(m, div)) : (float)((double)0.0f + (double)m / (double)div);
+    const uint32_t cell = (uint32_t)(key >> kl.z_bits) & (kl.cell_bits >= 32 ? 0xffffffffu : ((1u << kl.cell_bits) - 1u));
+    const uint32_t remote = (uint32_t)(key >> (kl.z_bits + kl.cell_bits)) & 1u;
+    const uint64_t rec = ((uint64_t)((remote << 31) | cell) << 32) | (uint64_t)f2u(m);
+    for (int x = x0; x < x1; x++) {
+      const long long gp = base + x;
+      if (count[gp] == 1u) out[gp] = v;
+      else {
+        const unsigned long long p = (unsigned long long)seg_off[gp] + atomicAdd(&fill[gp], 1u);
+        if (p < seg_cap) seg[p] = rec;
+        else cnt->dep_flags = 1u;
+        mine++;
+      }
+    }
+  }
+  // deposits that met another one on their grid point (statistics)
+  const unsigned long long tot = warp_incl_scan_ull(mine);
+  if (lane_id() == 31 && tot) atomicAdd(&cnt->n_shared, tot);
+}
+
+__device__ __forceinline__ void cswap64(uint64_t &a, uint64_t &b)
+{
+  const uint64_t lo = a < b ? a : b, hi = a < b ? b : a;
+  a = lo; b = hi;
+}
+
+// one thread per grid point of this rank's output
+__global__ void __launch_bounds__(256) k_point_apply(const unsigned int *__restrict__ count, const unsigned int *__restrict__ seg_off,
+                                                     const uint64_t *__restrict__ seg, unsigned long long seg_cap, unsigned long long npoints, float div,
+                                                     int alg_cic, float *__restrict__ out, unsigned int *__restrict__ big_list, unsigned int big_cap, Counters *cnt)
+{
+  const unsigned long long gp = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned int n = gp < npoints ? count[gp] : 0u;
+  const bool big = n > (unsigned)POINT_SMALL;
+  const unsigned int slot = warp_append<unsigned int>(&cnt->n_big_points, big);
+  if (big && slot < big_cap) big_list[slot] = (unsigned int)gp;
+  if (n < 2u || big) return;
+  const unsigned long long off = seg_off[gp];
+  if (off + n > seg_cap) return;                       // flagged by k_span_place2: the run is redone through the sorted path
+  uint64_t r[POINT_SMALL];
+#pragma unroll
+  for (int i = 0; i < POINT_SMALL; i++) r[i] = (unsigned)i < n ? seg[off + i] : ~0ull;
+  // Batcher's odd-even merge sort for 8 keys (19 compare-exchanges)
+  cswap64(r[0], r[1]); cswap64(r[2], r[3]); cswap64(r[4], r[5]); cswap64(r[6], r[7]);
+  cswap64(r[0], r[2]); cswap64(r[1], r[3]); cswap64(r[4], r[6]); cswap64(r[5], r[7]);
+  cswap64(r[1], r[2]); cswap64(r[5], r[6]);
+  cswap64(r[0], r[4]); cswap64(r[1], r[5]); cswap64(r[2], r[6]); cswap64(r[3], r[7]);
+  cswap64(r[2], r[4]); cswap64(r[3], r[5]);
+  cswap64(r[1], r[2]); cswap64(r[3], r[4]); cswap64(r[5], r[6]);
+  float cur = 0.0f;
+#pragma unroll
+  for (int i = 0; i < POINT_SMALL; i++)
+    if ((unsigned)i < n) {
+      const int remote = (int)(r[i] >> 63);
+      cur = accumulate(cur, u2f((uint32_t)r[i]), div, alg_cic && !remote);
+    }
+  out[gp] = cur;
+}
+
+// one warp per grid point with many deposits (persistent warps over the list k_point_apply wrote)
+__global__ void __launch_bounds__(POINT_BIG_WARPS * 32) k_point_apply_big(const unsigned int *__restrict__ count, const unsigned int *__restrict__ seg_off,
+                                                                          const uint64_t *__restrict__ seg, unsigned long long seg_cap, float div, int alg_cic,
+                                                                          float *__restrict__ out, const unsigned int *__restrict__ big_list, unsigned int big_cap,
+                                                                          const Counters *cnt)
+{
+  extern __shared__ __align__(16) uint64_t pbig_s[];
+  const int lane = (int)lane_id(), warp = threadIdx.x >> 5;
+  uint64_t *s = pbig_s + (size_t)warp * POINT_WARP_CAP;
+  const unsigned int n_list = cnt->n_big_points < big_cap ? cnt->n_big_points : big_cap;
+  const unsigned int n_warps = gridDim.x * POINT_BIG_WARPS;
+  for (unsigned int li = blockIdx.x * POINT_BIG_WARPS + warp; li < n_list; li += n_warps) {
+    const unsigned int gp = big_list[li];
+    const int n = (int)count[gp];
+    const unsigned long long off = seg_off[gp];
+    if (off + (unsigned long long)n > seg_cap) continue;
+    float cur = 0.0f;
+    if (n <= POINT_WARP_CAP) {
+      int P = 16;
+      while (P < n) P <<= 1;
+      for (int i = lane; i < P; i += 32) s[i] = i < n ? seg[off + i] : ~0ull;
+      __syncwarp();
+      for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < P; i += 32) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const uint64_t a = s[i], b = s[ixj];
+              const bool asc = (i & k) == 0;
+              if ((a > b) == asc) { s[i] = b; s[ixj] = a; }
+            }
+          }
+          __syncwarp();
+        }
+      // the quotients m / div off the serial chain (every lane its records), then one lane adds in order
+      int n_local = 0;
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        bool loc = false;
+        if (i < n) {
+          const uint64_t r = s[i];
+          loc = !(r >> 63);
+          const float m = u2f((uint32_t)r);
+          const double q = (alg_cic && loc) ? (double)fdiv(m, div) : (double)m / (double)div;
+          s[i] = (uint64_t)__double_as_longlong(q);
+        }
+        n_local += __popc(__ballot_sync(0xffffffffu, loc));
+      }
+      __syncwarp();
+      if (lane == 0) {
+        for (int i = 0; i < n; i++) {
+          const double q = __longlong_as_double((long long)s[i]);
+          cur = (alg_cic && i < n_local) ? fadd(cur, (float)q) : (float)((double)cur + q);
+        }
+        out[gp] = cur;
+      }
+      __syncwarp();
+    } else {
+      // more records than the warp's slice holds: take them in ascending order, one minimum search per record
+      uint64_t last = 0ull;
+      bool first = true;
+      for (int done = 0; done < n; done++) {
+        uint64_t best = ~0ull;
+        for (int i = lane; i < n; i += 32) {
+          const uint64_t r = seg[off + i];
+          if ((first || r > last) && r < best) best = r;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const uint64_t o = __shfl_xor_sync(0xffffffffu, best, d);
+          best = o < best ? o : best;
+        }
+        const int remote = (int)(best >> 63);
+        cur = accumulate(cur, u2f((uint32_t)best), div, alg_cic && !remote);
+        last = best;
+        first = false;
+      }
+      if (lane == 0) out[gp] = cur;
     }
   }
 }
