@@ -124,7 +124,8 @@ def clustered_blocks(spec, d, p, owner, bounds, gids, threads):
         if os.path.exists(meta):
             try:
                 m = json.load(open(meta))
-                b = dict(gid=g, num_orig=m["num_orig"], bounds_min=bounds[g][0], bounds_max=bounds[g][1], rounds=m["rounds"], seconds=m["seconds"], cached=True)
+                b = dict(gid=g, num_orig=m["num_orig"], bounds_min=bounds[g][0], bounds_max=bounds[g][1], rounds=m["rounds"], seconds=m["seconds"],
+                         settled=m.get("settled", True), cached=True)
                 for k in keys:
                     b[k] = np.load(os.path.join(d, f"blk{g}_{k}.npy"))
                 blocks[g] = b
@@ -145,7 +146,7 @@ def clustered_blocks(spec, d, p, owner, bounds, gids, threads):
                     for k in keys:
                         np.save(os.path.join(d, f"blk{b['gid']}_{k}.npy"), b[k])
                     tmp = os.path.join(d, f"blk{b['gid']}.json.tmp{os.getpid()}")
-                    json.dump(dict(num_orig=int(b["num_orig"]), rounds=int(b["rounds"]), seconds=float(b["seconds"])), open(tmp, "w"))
+                    json.dump(dict(num_orig=int(b["num_orig"]), rounds=int(b["rounds"]), seconds=float(b["seconds"]), settled=bool(b["settled"])), open(tmp, "w"))
                     os.replace(tmp, os.path.join(d, f"blk{b['gid']}.json"))
                 except OSError as e:
                     log(f"block cache not written ({e})")
@@ -181,7 +182,7 @@ def build_workload(cfg, n_ranks, rank, scale=1, gids=None, threads=None):
     layout = [(g, bounds[g][0], bounds[g][1]) for g in range(nb)]
     host = dict(engine="tess2_b200/host (C++ incremental Delaunay, exact predicates)", generate_seconds=gen_s, tess_seconds=tess_s,
                 blocks_tessellated_now=n_made, blocks_from_cache=len(mine) - n_made, threads=thr,
-                max_ghost_rounds=int(max([b["rounds"] for b in blocks], default=0)))
+                max_ghost_rounds=int(max([b["rounds"] for b in blocks], default=0)), all_blocks_settled=bool(all(b.get("settled", True) for b in blocks)))
     # ng = 0: DataBounds comes from the layout (every block's bounds), so the grid is the same at every N
     return dict(blocks=blocks, layout=layout, owner=owner, dmin=dmin, dmax=dmax, gsize=(spec["g"],) * 3, ng=0, scaling="strong", host=host,
                 particles_total=int(len(p)))
@@ -598,6 +599,19 @@ def run_ours(args, rank, world, local_rank):
         ms = multi.max_over_ranks(ms / reps)
         other[names[alg]] = {"ms_per_step": ms, "grid_points_per_sec": G_total / (ms * 1e-3), "tot_mass": multi.sum_over_ranks(float(so.tot_mass)),
                              "max_dense": multi.max_over_ranks(float(so.max_dense))}
+    # ---- K2 (per-site Voronoi volume + zero-order density, volume() of src/volume.cpp:13-54) on this rank's
+    # largest block: device time of the kernels (circumcenters + star walk + fan sums), 60 T + 24 P algorithmic bytes ----
+    k2 = None
+    if not args.no_k2 and blocks:
+        bb = max(blocks, key=lambda b: len(b["tets"]))
+        best = None
+        for _ in range(3):
+            ctx.cell_volumes(int(bb["num_orig"]), bb["tets"], bb["particles"], bb["vert_to_tet"])
+            ms = ctx.cell_volumes_ms()
+            best = ms if best is None else min(best, ms)
+        k2_bytes = 60 * len(bb["tets"]) + 24 * len(bb["particles"])
+        k2 = {"block_gid": int(bb["gid"]), "sites": int(bb["num_orig"]), "tets": int(len(bb["tets"])), "ms": best, "algorithmic_bytes": k2_bytes,
+              "algorithmic_GBps": k2_bytes / (best * 1e-3) / 1e9 if best else None, "sites_per_sec": bb["num_orig"] / (best * 1e-3) if best else None}
     ctx.upload(blocks)
     st_main = ctx.run(params)
 
@@ -608,6 +622,9 @@ def run_ours(args, rank, world, local_rank):
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
     roofline = make_roofline(st, stage, args.steps, T_local, P_local, cells_local, G_local, spans, dev_ms, peak, peak_src, main_alg)
+    if k2:
+        k2["frac_of_peak"] = k2["algorithmic_GBps"] / peak if k2["algorithmic_GBps"] else None
+        roofline["stages"]["K2 k_cell_volumes on one block (60 T + 24 P), not part of dense()"] = k2
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------------
     cpu = None
@@ -701,6 +718,7 @@ def main():
     ap.add_argument("--scale", type=int, default=int(os.environ.get("TESSB200_BENCH_SCALE", "1")), help="development: shrink configs 3-5 by this factor per axis")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-k2", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -123,6 +123,9 @@ __attribute__((unused)) static tessb200_host_dblock *generate_and_tess(int tb, c
     free(hb[g].global_ids);
     hb[g].global_ids = NULL;
     db[g].complete = 1;
+    if (!hb[g].settled)
+      fprintf(stderr, "tess: WARNING: block %d: the ghost region stopped growing (margin %g, %d rounds) before every original cell was settled; "
+                      "cells near its border may be wrong\n", hb[g].gid, (double)hb[g].ghost_margin, hb[g].rounds);
     ntets += hb[g].num_tets;
     nghost += ng;
   }

@@ -40,7 +40,8 @@ enum
   TESSB200_ELIMIT = -5,    /* input exceeds a documented limit */
   TESSB200_ENCCL = -6,     /* NCCL error */
   TESSB200_ESTATE = -7,    /* call sequence error (e.g. run before upload) */
-  TESSB200_EIO = -8        /* file error in tessb200_write_grid */
+  TESSB200_EIO = -8,       /* file error in tessb200_write_grid */
+  TESSB200_EPEER = -9      /* multi-GPU run: another rank failed before the span exchange (every rank returns together) */
 };
 
 /* estimator algorithm: reference `enum alg`, include/tess/dense.hpp:33-38 */
@@ -170,6 +171,10 @@ int tessb200_cell_volumes(tessb200_ctx *ctx, int num_sites, int num_particles, c
                           const int *tets, const int *vert_to_tet, float mass, int *complete, float *volume,
                           float *density);
 
+/* device time (ms, CUDA events) of the kernels of the last tessb200_cell_volumes call on this context: circumcenters +
+ * the per-site star walk and fan sums, without the host <-> device copies (bench.py's K2 line) */
+int tessb200_cell_volumes_ms(tessb200_ctx *ctx, float *ms);
+
 /* Per-site density of the first-order DTFE mode (NOT in the reference, see TESSB200_DENSE_DTFE): for every particle
  * density[v] = 4 * mass / (sum of the volumes of the tets at v), -1 where the star is infinite or v is in no tet.
  * vert_to_tet may be NULL. */
@@ -200,8 +205,14 @@ int tessb200_write_grid(const char *outfile, const tessb200_dense_params *params
  * tessb200_dense_set_layout) and exchanges boundary spans with NCCL. */
 int tessb200_comm_unique_id(void *id128);
 int tessb200_comm_init(tessb200_ctx *ctx, int nranks, int rank, const void *id128);
+/* number of ranks of the communicator this context joined (1: none) */
+int tessb200_comm_size(tessb200_ctx *ctx);
 /* Global layout for multi-GPU runs: bounds and owner rank of EVERY block of the decomposition,
- * in ascending gid order (bounds: 6 floats per block: min xyz, max xyz). */
+ * in ascending gid order (bounds: 6 floats per block: min xyz, max xyz).  owner_rank must be
+ * non-decreasing over ascending gid (diy::ContiguousAssigner's rule: rank r owns one contiguous run
+ * of gids, and lower ranks own lower gids): the exchange routes a record by the row range of its
+ * rank and the accumulation order of received points follows the rank-windowed cell numbers.
+ * Anything else is refused with TESSB200_EINVAL.  Every rank must own at least one block. */
 int tessb200_dense_set_layout(tessb200_ctx *ctx, int nblocks_global, const int *gids, const float *bounds6,
                               const int *owner_rank);
 

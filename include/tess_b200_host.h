@@ -35,6 +35,10 @@ typedef struct tessb200_host_block {
   float ghost_margin;        /* width of the ghost region that was finally used */
   int rounds;                /* tessellation rounds (the region grows until every original cell is settled) */
   double seconds;            /* time spent in the Delaunay engine for this block */
+  int settled;               /* 1: the ghost region covers the circumsphere of every tet at an original, finite cell (or the whole
+                                domain); 0: the rounds / growth limits stopped the widening first -- the stars near the block border
+                                may differ from the global Delaunay triangulation and dense() may deposit wrong or missing mass there */
+  int reserved;
 } tessb200_host_block;
 
 /* tess() for one process holding all particles (replaces the round loop of src/tess.cpp:52-116 with

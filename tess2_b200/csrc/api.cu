@@ -170,11 +170,17 @@ struct tessb200_ctx
   Buf fz_hdr, fz_bits, fz_pool;     // k_cell_fused -> k_cell_emit: headers, in-line inside bits, pool for the larger index boxes
   Buf hdr_dir[3];                   // cells of the small-box classes (k_cell_direct)
   Buf pt_off, pt_fill, big_points;  // shared grid points: segment offsets, fill cursors, the points with many deposits
+  // span exchange: per (source, destination) capacities agreed in an exact round; later runs exchange fixed-size,
+  // sentinel-padded segments and need no host read-back before the deposit
+  std::vector<unsigned long long> xcap;   // [src * nranks + dst], identical on every rank; empty = no agreement yet
+  bool x_fast_used = false;               // this run exchanged fixed-size segments: the count matrix is checked at its end
+  unsigned long long *h_xall = nullptr;   // pinned copy of the all-gathered (counts | status) matrix
   bool segments = false;            // TESSB200_SEGMENTS=1: shared deposits through per-point segments instead of the radix sort + k_rows
                                     // (faster on uniform input, slower where clumps put hundreds of deposits on one point: profiles/r02)
   bool direct = true;               // TESSB200_DIRECT=0: every cell through k_cell_faces + k_cell_scan (A/B measurements)
   bool fused = false;               // TESSB200_FUSED=1 selects the one-kernel-per-cell path (fused.cuh; A/B measurements)
   int fz_ctas = 0;
+  float last_k2_ms = 0.0f;          // device time of the kernels of the last tessb200_cell_volumes call
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
@@ -261,6 +267,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
 #endif
   cudaFreeHost(c->h_cnt); cudaFreeHost(c->h_sum); cudaFreeHost(c->h_max);
+  if (c->h_xall) cudaFreeHost(c->h_xall);
   for (auto &ev : c->ev) cudaEventDestroy(ev);
   for (auto &ev : c->blk_ev) cudaEventDestroy(ev);
   for (auto &ev : c->grp_ev) cudaEventDestroy(ev);
@@ -585,7 +592,22 @@ static int read_counters(tessb200_ctx *c)
 
 #ifdef TESSB200_WITH_NCCL
 static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned long long *n_spans);
+static void exchange_poison(tessb200_ctx *c);
+static int exchange_check(tessb200_ctx *c, bool *redo);
 #endif
+// A rank that fails before the span exchange still takes part in it (empty, flagged), so that its peers return
+// TESSB200_EPEER instead of waiting in a collective forever.
+struct ExchangeGuard
+{
+  tessb200_ctx *c;
+  bool armed;
+  ~ExchangeGuard()
+  {
+#ifdef TESSB200_WITH_NCCL
+    if (armed) exchange_poison(c);
+#endif
+  }
+};
 
 // ---- run ---------------------------------------------------------------------------------------------
 // The stage runs group by group over the local blocks (cell kernels), then once over all span
@@ -733,6 +755,8 @@ static int run_dtfe(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
 
 static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_stats *st, const PipeIO &io)
 {
+  // from here to the span exchange every early return still takes part in the exchange (flagged), see ExchangeGuard
+  ExchangeGuard xguard{c, c->nranks > 1 && p && p->alg != TESSB200_DENSE_DTFE};
   if (c->blocks.empty()) return fail(TESSB200_ESTATE, "tessb200_dense_run before tessb200_dense_upload");
   CU(cudaSetDevice(c->device));
   Geometry G;
@@ -748,6 +772,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   c->launches = 0;
   const bool tess = p->alg == TESSB200_DENSE_TESS;
   const bool fused = tess && c->fused;
+  c->x_fast_used = false;
 
   CU(cudaEventRecord(c->ev[2], s));
   // groups of local blocks (indices into c->blocks)
@@ -1047,6 +1072,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   int cur = 0;
   long long n_shared_stat = -1;     // deposits that met another one on their grid point (-1: the full-sort path ran)
 #ifdef TESSB200_WITH_NCCL
+  xguard.armed = false;
   if (c->nranks > 1) TRY(exchange_spans(c, G, cur, &n_spans));
 #endif
   CU(cudaEventRecord(c->ev[7], s));
@@ -1218,6 +1244,15 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   CU(cudaStreamSynchronize(s));
   if (io.pipelined) CU(cudaStreamSynchronize(c->copy_stream));
 
+#ifdef TESSB200_WITH_NCCL
+  if (c->nranks > 1) {
+    // fixed-size exchange: the counts every rank really had arrive with the same all-gather; a segment that was too
+    // small (or a peer that failed) is seen by every rank alike, and the run is redone with exact sizes
+    bool redo = false;
+    TRY(exchange_check(c, &redo));
+    if (redo) return run_impl(c, p, st, io);
+  }
+#endif
   c->ran = true;
   c->last_params = *p;
   c->out_floats = G.out_floats;
@@ -1422,7 +1457,9 @@ extern "C" int tessb200_cell_volumes(tessb200_ctx *c, int num_sites, int num_par
   CU(cudaSetDevice(c->device));
   TmpBlock t;
   TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, vert_to_tet));
+  CU(cudaEventRecord(c->ev[18], c->stream));
   TRY(prep_block_geometry(c, &t.b));
+  c->last_k2_ms = 0.0f;
   if (num_sites) {
     Buf d_comp, d_vol, d_den, d_ovf, d_n, d_ws;
     auto cleanup = [&]() { d_comp.release(); d_vol.release(); d_den.release(); d_ovf.release(); d_n.release(); d_ws.release(); };
@@ -1444,13 +1481,22 @@ extern "C" int tessb200_cell_volumes(tessb200_ctx *c, int num_sites, int num_par
       k_cell_volumes_big<<<cdiv(n_ovf, 128), 128, 0, c->stream>>>(db, d_ovf.as<uint32_t>(), (int)n_ovf, d_ws.as<int>(), mass, d_comp.as<int>(),
                                                                   d_vol.as<float>(), d_den.as<float>());
     }
+    cudaEventRecord(c->ev[19], c->stream);
     if (complete) cudaMemcpyAsync(complete, d_comp.p, 4 * (size_t)num_sites, cudaMemcpyDeviceToHost, c->stream);
     if (volume) cudaMemcpyAsync(volume, d_vol.p, 4 * (size_t)num_sites, cudaMemcpyDeviceToHost, c->stream);
     if (density) cudaMemcpyAsync(density, d_den.p, 4 * (size_t)num_sites, cudaMemcpyDeviceToHost, c->stream);
     e = cudaStreamSynchronize(c->stream);
     cleanup();
     if (e != cudaSuccess) return fail(TESSB200_ECUDA, "cell volumes: %s", cudaGetErrorString(e));
+    cudaEventElapsedTime(&c->last_k2_ms, c->ev[18], c->ev[19]);
   }
+  return 0;
+}
+
+extern "C" int tessb200_cell_volumes_ms(tessb200_ctx *c, float *ms)
+{
+  if (!c || !ms) return fail(TESSB200_EINVAL, "NULL argument");
+  *ms = c->last_k2_ms;
   return 0;
 }
 
@@ -1590,10 +1636,13 @@ extern "C" int tessb200_write_grid(const char *outfile, const tessb200_dense_par
 }
 
 // ---- multi-GPU ----------------------------------------------------------------------------------------
+extern "C" int tessb200_comm_size(tessb200_ctx *c) { return c ? c->nranks : 0; }
+
 extern "C" int tessb200_dense_set_layout(tessb200_ctx *c, int n, const int *gids, const float *bounds6, const int *owner_rank)
 {
   if (!c) return fail(TESSB200_EINVAL, "ctx is NULL");
   c->layout.clear();
+  c->xcap.clear();
   if (n == 0) return 0;
   if (!gids || !bounds6 || !owner_rank) return fail(TESSB200_EINVAL, "NULL argument");
   for (int i = 0; i < n; i++) {
@@ -1602,8 +1651,13 @@ extern "C" int tessb200_dense_set_layout(tessb200_ctx *c, int n, const int *gids
     memcpy(l.bmin, bounds6 + 6 * i, 12); memcpy(l.bmax, bounds6 + 6 * i + 3, 12);
     l.owner = owner_rank[i];
     if (i && gids[i] <= gids[i - 1]) { c->layout.clear(); return fail(TESSB200_EINVAL, "layout gids must be ascending"); }
+    if (owner_rank[i] < 0 || (i && owner_rank[i] < owner_rank[i - 1])) {
+      c->layout.clear();
+      return fail(TESSB200_EINVAL, "layout owner ranks must be >= 0 and non-decreasing over ascending gid (block gid %d has owner %d)", gids[i], owner_rank[i]);
+    }
     c->layout.push_back(l);
   }
+  c->xcap.clear();
   return 0;
 }
 
@@ -1640,6 +1694,8 @@ extern "C" int tessb200_comm_init(tessb200_ctx *c, int nranks, int rank, const v
   NC(ncclw::g.CommInitRank(&c->comm, nranks, id, rank));
   c->nranks = nranks;
   c->rank = rank;
+  c->xcap.clear();
+  if (!c->h_xall) CU(cudaMallocHost(&c->h_xall, 8 * 65 * 64));
   return 0;
 }
 
@@ -1678,6 +1734,25 @@ __global__ void k_scatter_remote(uint64_t *__restrict__ keys, const uint64_t *__
   send_d[pos] = data[i];
   keys[i] = sentinel;
 }
+// the same into fixed-capacity segments: seg_start[r] .. seg_start[r] + seg_cap[r]; counts[r] ends up as the number of
+// records bound for rank r (those beyond the capacity are not written: the run is redone with exact sizes)
+__global__ void k_scatter_fixed(uint64_t *__restrict__ keys, const uint64_t *__restrict__ data, unsigned long long n, KeyLayout kl,
+                                const long long *__restrict__ rank_row_end, int nranks, int me, unsigned long long *__restrict__ counts,
+                                const unsigned long long *__restrict__ seg_start, const unsigned long long *__restrict__ seg_cap,
+                                uint64_t *__restrict__ send_k, uint64_t *__restrict__ send_d, uint64_t sentinel)
+{
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = keys[i];
+  int r = dest_rank_of(k, kl, rank_row_end, nranks);
+  if (r == me) return;
+  unsigned long long pos = atomicAdd(&counts[r], 1ull);
+  if (pos < seg_cap[r]) {
+    send_k[seg_start[r] + pos] = k;
+    send_d[seg_start[r] + pos] = data[i];
+  }
+  keys[i] = sentinel;
+}
 
 // grow a device buffer, keeping its first keep_bytes
 static int grow_keep(Buf &b, size_t bytes, size_t keep_bytes, cudaStream_t s)
@@ -1695,11 +1770,12 @@ static int grow_keep(Buf &b, size_t bytes, size_t keep_bytes, cudaStream_t s)
   return 0;
 }
 
+// x_small layout (8-byte words): row_end[R] | mine[R + 1] (counts per destination, status) | all[R][R + 1] | seg_start[R] | seg_cap[R]
 static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned long long *n_spans)
 {
   cudaStream_t s = c->stream;
-  const int R = c->nranks, me = c->rank;
-  // row range end of every rank (blocks of a rank are contiguous in gid order)
+  const int R = c->nranks, me = c->rank, W = R + 1;
+  // row range end of every rank (blocks of a rank are contiguous in gid order, ranks ascend with the gid)
   std::vector<long long> row_end(R, 0);
   {
     const std::vector<LayoutBlock> &L = c->layout;
@@ -1713,25 +1789,78 @@ static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned 
     for (int r = 1; r < R; r++) row_end[r] = std::max(row_end[r], row_end[r - 1]);
   }
   const unsigned long long n = *n_spans;
-  TRY(c->x_small.ensure(8 * (size_t)(R + R + (size_t)R * R)));      // row_end | counts / cursor | all-gathered matrix
+  TRY(c->x_small.ensure(8 * (size_t)(R + W + (size_t)R * W + 2 * R)));
   long long *d_row_end = c->x_small.as<long long>();
-  unsigned long long *d_counts = c->x_small.as<unsigned long long>() + R;
-  unsigned long long *d_all = d_counts + R;
+  unsigned long long *d_mine = c->x_small.as<unsigned long long>() + R;
+  unsigned long long *d_all = d_mine + W;
+  unsigned long long *d_seg_start = d_all + (size_t)R * W, *d_seg_cap = d_seg_start + R;
   CU(cudaMemcpyAsync(d_row_end, row_end.data(), 8 * (size_t)R, cudaMemcpyHostToDevice, s));
-  CU(cudaMemsetAsync(d_counts, 0, 8 * (size_t)R, s));
+  CU(cudaMemsetAsync(d_mine, 0, 8 * (size_t)W, s));
+  const uint64_t sentinel = G.key_bits >= 64 ? ~0ull : ((1ull << G.key_bits) - 1ull);
+  uint64_t *lk = nullptr, *ld = nullptr;
+
+  if (c->xcap.size() == (size_t)R * R) {
+    // ---- steady state: fixed-size, sentinel-padded segments; nothing is read back before the deposit ----
+    std::vector<unsigned long long> sstart(R + 1, 0), scap(R, 0), rstart(R + 1, 0);
+    for (int r = 0; r < R; r++) {
+      scap[r] = r == me ? 0ull : c->xcap[(size_t)me * R + r];
+      sstart[r + 1] = sstart[r] + scap[r];
+      rstart[r + 1] = rstart[r] + (r == me ? 0ull : c->xcap[(size_t)r * R + me]);
+    }
+    const unsigned long long send_total = sstart[R], recv_total = rstart[R];
+    TRY(c->recv_keys.ensure(8 * (size_t)std::max<unsigned long long>(1, send_total)));
+    TRY(c->recv_data.ensure(8 * (size_t)std::max<unsigned long long>(1, send_total)));
+    for (int i = 0; i < 2; i++) {
+      TRY(grow_keep(c->keys[i], 8 * (size_t)(n + recv_total), i == cur ? 8 * (size_t)n : 0, s));
+      TRY(grow_keep(c->data[i], 8 * (size_t)(n + recv_total), i == cur ? 8 * (size_t)n : 0, s));
+    }
+    uint64_t *sk = c->recv_keys.as<uint64_t>(), *sd = c->recv_data.as<uint64_t>();
+    lk = c->keys[cur].as<uint64_t>(); ld = c->data[cur].as<uint64_t>();
+    CU(cudaMemcpyAsync(d_seg_start, sstart.data(), 8 * (size_t)R, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_seg_cap, scap.data(), 8 * (size_t)R, cudaMemcpyHostToDevice, s));
+    if (send_total) CU(cudaMemsetAsync(sk, 0xFF, 8 * (size_t)send_total, s));        // unused slots: a key no row owns
+    if (n) {
+      k_scatter_fixed<<<cdiv((long long)n, 256), 256, 0, s>>>(lk, ld, n, G.kl, d_row_end, R, me, d_mine, d_seg_start, d_seg_cap, sk, sd, sentinel);
+      COUNT_LAUNCH(c, 1);
+    }
+    NC(ncclw::g.AllGather(d_mine, d_all, (size_t)W, ncclUint64, c->comm, s));
+    NC(ncclw::g.GroupStart());
+    for (int peer = 0; peer < R; peer++) {
+      if (peer == me) continue;
+      const unsigned long long ns = scap[peer], nr = c->xcap[(size_t)peer * R + me];
+      if (ns) {
+        NC(ncclw::g.Send(sk + sstart[peer], (size_t)ns, ncclUint64, peer, c->comm, s));
+        NC(ncclw::g.Send(sd + sstart[peer], (size_t)ns, ncclUint64, peer, c->comm, s));
+      }
+      if (nr) {
+        NC(ncclw::g.Recv(lk + n + rstart[peer], (size_t)nr, ncclUint64, peer, c->comm, s));
+        NC(ncclw::g.Recv(ld + n + rstart[peer], (size_t)nr, ncclUint64, peer, c->comm, s));
+      }
+    }
+    NC(ncclw::g.GroupEnd());
+    CU(cudaMemcpyAsync(c->h_xall, d_all, 8 * (size_t)R * W, cudaMemcpyDeviceToHost, s));   // read at the end of the run (exchange_check)
+    CU(cudaGetLastError());
+    c->x_fast_used = true;
+    *n_spans = n + recv_total;
+    return 0;
+  }
+
+  // ---- exact round (the first run of a layout, or after a segment proved too small): counts, one host read-back ----
   if (n) {
-    k_count_remote<<<cdiv((long long)n, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n, G.kl, d_row_end, R, me, d_counts);
+    k_count_remote<<<cdiv((long long)n, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n, G.kl, d_row_end, R, me, d_mine);
     COUNT_LAUNCH(c, 1);
   }
-  NC(ncclw::g.AllGather(d_counts, d_all, (size_t)R, ncclUint64, c->comm, s));
-  std::vector<unsigned long long> all((size_t)R * R);
-  CU(cudaMemcpyAsync(all.data(), d_all, 8 * (size_t)R * R, cudaMemcpyDeviceToHost, s));
+  NC(ncclw::g.AllGather(d_mine, d_all, (size_t)W, ncclUint64, c->comm, s));
+  std::vector<unsigned long long> all((size_t)R * W);
+  CU(cudaMemcpyAsync(all.data(), d_all, 8 * (size_t)R * W, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  // all[src * R + dst]
+  for (int r = 0; r < R; r++)
+    if (all[(size_t)r * W + R]) return fail(TESSB200_EPEER, "rank %d failed before the span exchange", r);
+  // all[src * W + dst]
   std::vector<unsigned long long> soff(R + 1, 0), roff(R + 1, 0);
   for (int r = 0; r < R; r++) {
-    soff[r + 1] = soff[r] + all[(size_t)me * R + r];
-    roff[r + 1] = roff[r] + all[(size_t)r * R + me];
+    soff[r + 1] = soff[r] + all[(size_t)me * W + r];
+    roff[r + 1] = roff[r] + all[(size_t)r * W + me];
   }
   const unsigned long long send_total = soff[R], recv_total = roff[R];
   TRY(c->recv_keys.ensure(8 * (size_t)std::max<unsigned long long>(1, send_total)));   // used as the send buffers
@@ -1741,17 +1870,16 @@ static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned 
     TRY(grow_keep(c->data[i], 8 * (size_t)(n + recv_total), i == cur ? 8 * (size_t)n : 0, s));
   }
   uint64_t *sk = c->recv_keys.as<uint64_t>(), *sd = c->recv_data.as<uint64_t>();
-  uint64_t *lk = c->keys[cur].as<uint64_t>(), *ld = c->data[cur].as<uint64_t>();
+  lk = c->keys[cur].as<uint64_t>(); ld = c->data[cur].as<uint64_t>();
   if (send_total) {
-    CU(cudaMemcpyAsync(d_counts, soff.data(), 8 * (size_t)R, cudaMemcpyHostToDevice, s));   // cursors start at the segment offsets
-    const uint64_t sentinel = G.key_bits >= 64 ? ~0ull : ((1ull << G.key_bits) - 1ull);
-    k_scatter_remote<<<cdiv((long long)n, 256), 256, 0, s>>>(lk, ld, n, G.kl, d_row_end, R, me, d_counts, sk, sd, sentinel);
+    CU(cudaMemcpyAsync(d_mine, soff.data(), 8 * (size_t)R, cudaMemcpyHostToDevice, s));   // cursors start at the segment offsets
+    k_scatter_remote<<<cdiv((long long)n, 256), 256, 0, s>>>(lk, ld, n, G.kl, d_row_end, R, me, d_mine, sk, sd, sentinel);
     COUNT_LAUNCH(c, 1);
   }
   NC(ncclw::g.GroupStart());
   for (int peer = 0; peer < R; peer++) {
     if (peer == me) continue;
-    const unsigned long long ns = all[(size_t)me * R + peer], nr = all[(size_t)peer * R + me];
+    const unsigned long long ns = all[(size_t)me * W + peer], nr = all[(size_t)peer * W + me];
     if (ns) {
       NC(ncclw::g.Send(sk + soff[peer], (size_t)ns, ncclUint64, peer, c->comm, s));
       NC(ncclw::g.Send(sd + soff[peer], (size_t)ns, ncclUint64, peer, c->comm, s));
@@ -1763,7 +1891,82 @@ static int exchange_spans(tessb200_ctx *c, const Geometry &G, int cur, unsigned 
   }
   NC(ncclw::g.GroupEnd());
   CU(cudaGetLastError());
+  // capacities for the runs that follow: every rank computes the same table from the same matrix
+  c->xcap.assign((size_t)R * R, 0ull);
+  for (int a = 0; a < R; a++)
+    for (int b = 0; b < R; b++)
+      if (a != b) {
+        const unsigned long long cnt = all[(size_t)a * W + b];
+        c->xcap[(size_t)a * R + b] = cnt ? cnt + cnt / 4 + 4096 : 0ull;
+      }
   *n_spans = n + recv_total;
   return 0;
+}
+
+// after the run of a fixed-size exchange: did every segment hold its records, did every rank get this far?
+static int exchange_check(tessb200_ctx *c, bool *redo)
+{
+  *redo = false;
+  if (!c->x_fast_used) return 0;
+  c->x_fast_used = false;
+  const int R = c->nranks, W = R + 1;
+  bool grow = false;
+  for (int a = 0; a < R; a++) {
+    if (c->h_xall[(size_t)a * W + R]) { c->xcap.clear(); return fail(TESSB200_EPEER, "rank %d failed before the span exchange", a); }
+    for (int b = 0; b < R; b++)
+      if (a != b && c->h_xall[(size_t)a * W + b] > c->xcap[(size_t)a * R + b]) grow = true;
+  }
+  if (grow) {
+    c->xcap.clear();        // the next run is an exact round (and sets new capacities)
+    *redo = true;
+  }
+  return 0;
+}
+
+// the failing rank's part of the exchange: empty, flagged.  Best effort (an allocation failure here leaves the peers waiting).
+static void exchange_poison(tessb200_ctx *c)
+{
+  if (!c->comm || c->nranks < 2) return;
+  cudaStream_t s = c->stream;
+  const int R = c->nranks, me = c->rank, W = R + 1;
+  std::string keep = g_err;
+  if (c->x_small.ensure(8 * (size_t)(R + W + (size_t)R * W + 2 * R))) { g_err = keep; return; }
+  unsigned long long *d_mine = c->x_small.as<unsigned long long>() + R, *d_all = d_mine + W;
+  std::vector<unsigned long long> mine(W, 0ull);
+  mine[R] = 1ull;
+  cudaMemcpyAsync(d_mine, mine.data(), 8 * (size_t)W, cudaMemcpyHostToDevice, s);
+  if (c->xcap.size() == (size_t)R * R) {
+    unsigned long long send_total = 0, recv_total = 0;
+    for (int r = 0; r < R; r++)
+      if (r != me) { send_total += c->xcap[(size_t)me * R + r]; recv_total += c->xcap[(size_t)r * R + me]; }
+    if (c->recv_keys.ensure(8 * (size_t)std::max<unsigned long long>(1, send_total)) || c->recv_data.ensure(8 * (size_t)std::max<unsigned long long>(1, send_total)) ||
+        c->keys[0].ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total)) || c->data[0].ensure(8 * (size_t)std::max<unsigned long long>(1, recv_total))) {
+      g_err = keep;
+      return;
+    }
+    if (send_total) cudaMemsetAsync(c->recv_keys.p, 0xFF, 8 * (size_t)send_total, s);
+    ncclw::g.AllGather(d_mine, d_all, (size_t)W, ncclUint64, c->comm, s);
+    ncclw::g.GroupStart();
+    unsigned long long so = 0, ro = 0;
+    for (int peer = 0; peer < R; peer++) {
+      if (peer == me) continue;
+      const unsigned long long ns = c->xcap[(size_t)me * R + peer], nr = c->xcap[(size_t)peer * R + me];
+      if (ns) {
+        ncclw::g.Send(c->recv_keys.as<uint64_t>() + so, (size_t)ns, ncclUint64, peer, c->comm, s);
+        ncclw::g.Send(c->recv_data.as<uint64_t>() + so, (size_t)ns, ncclUint64, peer, c->comm, s);
+      }
+      if (nr) {
+        ncclw::g.Recv(c->keys[0].as<uint64_t>() + ro, (size_t)nr, ncclUint64, peer, c->comm, s);
+        ncclw::g.Recv(c->data[0].as<uint64_t>() + ro, (size_t)nr, ncclUint64, peer, c->comm, s);
+      }
+      so += ns; ro += nr;
+    }
+    ncclw::g.GroupEnd();
+    c->xcap.clear();
+  } else {
+    ncclw::g.AllGather(d_mine, d_all, (size_t)W, ncclUint64, c->comm, s);
+  }
+  cudaStreamSynchronize(s);
+  g_err = keep;
 }
 #endif

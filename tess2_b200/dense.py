@@ -231,6 +231,11 @@ class Context:
                                                 _ip(v2t) if v2t is not None else None, float(mass), _ip(comp), _fp(vol), _fp(den)))
         return comp, vol, den
 
+    def cell_volumes_ms(self):
+        """device ms of the kernels of the last cell_volumes() call (no copies)"""
+        ms = C.c_float(0.0)
+        _l.check(self.lib.tessb200_cell_volumes_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
 
     def dtfe_vertex_density(self, tets, particles, vert_to_tet=None, mass=1.0):
         """Per-particle density of the first-order DTFE mode (not in the reference): 4 m / (volume of the star), -1 where

@@ -87,6 +87,7 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
   std::vector<float> P;
   std::vector<int> gids(job.mine.begin(), job.mine.end()), tets;
   int rounds = 0;
+  bool settled = false;
   double secs = 0.0;
   tb_host::Delaunay3 dt;       // lives across the rounds: a wider margin only inserts the new ghosts
   for (;;) {
@@ -112,7 +113,7 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     const size_t nt = tets.size() / 8;
     bool covered = true;
     for (int d = 0; d < 3; d++) covered = covered && job.bmin[d] - margin <= dmin[d] && job.bmax[d] + margin >= dmax[d];
-    if (covered || rounds >= max_rounds || np == n_orig) break;
+    if (covered) { settled = true; break; }
     // originals on the local hull have unbounded cells; fine next to the domain boundary, a sign of too
     // few ghosts anywhere else
     std::vector<char> on_hull(np, 0);
@@ -129,21 +130,30 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     }
     // circumspheres of the tets at original, finite cells must stay inside the searched region
     // (clipped at the domain: nothing lives beyond it)
-    double req = 0.0;
+    double req = 0.0, req_in = 0.0;
     for (size_t t = 0; t < nt; t++) {
       const int *v = &tets[8 * t];
       bool need = false;
       for (int j = 0; j < 4; j++) need = need || (v[j] < n_orig && !on_hull[v[j]]);
       if (!need) continue;
       const Sphere s = circumsphere(&P[3 * (size_t)v[0]], &P[3 * (size_t)v[1]], &P[3 * (size_t)v[2]], &P[3 * (size_t)v[3]]);
+      // a tet whose circumcenter lies outside the domain is a Voronoi vertex outside the data bounds: every cell it
+      // belongs to is dropped by dense() (src/dense.cpp:1385-1392), so it cannot unsettle the block (`settled`); it
+      // still drives the widening as before (flat tets at the domain boundary have spheres that reach far sideways)
+      bool inside = true;
+      for (int d = 0; d < 3; d++) inside = inside && s.c[d] >= dmin[d] && s.c[d] <= dmax[d];
       for (int d = 0; d < 3; d++) {
         const double lo_need = job.bmin[d] - (s.c[d] - s.r), hi_need = (s.c[d] + s.r) - job.bmax[d];
-        req = std::max(req, std::min(lo_need, job.bmin[d] - dmin[d]));
-        req = std::max(req, std::min(hi_need, dmax[d] - job.bmax[d]));
+        const double r_lo = std::min(lo_need, job.bmin[d] - dmin[d]), r_hi = std::min(hi_need, dmax[d] - job.bmax[d]);
+        req = std::max(req, std::max(r_lo, r_hi));
+        if (inside) req_in = std::max(req_in, std::max(r_lo, r_hi));
       }
     }
     if (grow) req = std::max(req, 2.0 * margin);
-    if (req <= margin || margin >= max_growth * margin0) break;
+    settled = req_in <= margin && !grow;
+    if (req <= margin) break;
+    // the limits end the widening; `settled` says whether the test held for every tet that can matter
+    if (rounds >= max_rounds || margin >= max_growth * margin0) break;
     prev_margin = margin;
     margin = std::min(req * 1.05, max_growth * margin0);
   }
@@ -184,6 +194,8 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     for (int j = 0; j < 4; j++) out->vert_to_tet[tets[8 * t + j]] = (int)t;
   out->ghost_margin = (float)margin;
   out->rounds = rounds;
+  out->settled = settled ? 1 : 0;
+  out->reserved = 0;
   out->seconds = secs;
   return 0;
 }

@@ -19,6 +19,7 @@ class HostBlock(C.Structure):
         ("num_orig_particles", C.c_int), ("num_particles", C.c_int), ("num_tets", C.c_int),
         ("particles", C.POINTER(C.c_float)), ("tets", C.POINTER(C.c_int)), ("vert_to_tet", C.POINTER(C.c_int)),
         ("global_ids", C.POINTER(C.c_int)), ("ghost_margin", C.c_float), ("rounds", C.c_int), ("seconds", C.c_double),
+        ("settled", C.c_int), ("reserved", C.c_int),
     ]
 
 
@@ -111,7 +112,7 @@ def tess(points, owner, bounds, domain_min, domain_max, margin0=0.0, threads=0, 
             vert_to_tet=np.ctypeslib.as_array(b.vert_to_tet, (n,)).copy() if n else np.zeros(0, np.int32),
             global_ids=np.ctypeslib.as_array(b.global_ids, (n,)).copy() if n else np.zeros(0, np.int32),
             bounds_min=np.array(b.bounds_min, np.float32), bounds_max=np.array(b.bounds_max, np.float32),
-            margin=b.ghost_margin, rounds=b.rounds, seconds=b.seconds))
+            margin=b.ghost_margin, rounds=b.rounds, seconds=b.seconds, settled=bool(b.settled)))
         lib.tessb200_host_free_block(C.byref(b))
     return out
 

@@ -17,9 +17,9 @@ EXPORTS = [
     "tessb200_create", "tessb200_destroy", "tessb200_last_error", "tessb200_version",
     "tessb200_dense", "tessb200_dense_upload", "tessb200_dense_run", "tessb200_dense_download",
     "tessb200_dense_geometry", "tessb200_dense_device_density",
-    "tessb200_fill_vert_to_tet", "tessb200_circumcenters", "tessb200_cell_volumes",
+    "tessb200_fill_vert_to_tet", "tessb200_circumcenters", "tessb200_cell_volumes", "tessb200_cell_volumes_ms",
     "tessb200_write_grid", "tessb200_check_block", "tessb200_dtfe_vertex_density",
-    "tessb200_comm_unique_id", "tessb200_comm_init", "tessb200_dense_set_layout",
+    "tessb200_comm_unique_id", "tessb200_comm_init", "tessb200_comm_size", "tessb200_dense_set_layout",
 ]
 
 
@@ -98,11 +98,13 @@ def load():
     lib.tessb200_fill_vert_to_tet.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p]
     lib.tessb200_circumcenters.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int, i32p, f32p]
     lib.tessb200_cell_volumes.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_int, i32p, i32p, C.c_float, i32p, f32p, f32p]
+    lib.tessb200_cell_volumes_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.tessb200_write_grid.argtypes = [C.c_char_p, C.POINTER(DenseParams), C.c_int, C.POINTER(Block)]
     lib.tessb200_check_block.argtypes = [C.POINTER(Block), C.c_int]
     lib.tessb200_dtfe_vertex_density.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int, i32p, i32p, C.c_float, f32p]
     lib.tessb200_comm_unique_id.argtypes = [C.c_void_p]
     lib.tessb200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.tessb200_comm_size.argtypes = [C.c_void_p]
     lib.tessb200_dense_set_layout.argtypes = [C.c_void_p, C.c_int, i32p, f32p, i32p]
     _lib = lib
     return lib

@@ -6,6 +6,8 @@ master.exchange() (src/dense.cpp:98).  Here torch.distributed carries the small 
 over NVLink (tessb200_comm_init / exchange inside tessb200_dense_run).
 """
 import ctypes as C
+import os
+
 import numpy as np
 
 
@@ -50,8 +52,26 @@ def set_layout(ctx, layout, owner):
                                            own.ctypes.data_as(_l.i32p)))
 
 
+def _preload_nccl():
+    """The library binds NCCL with dlopen("libnccl.so.2"); a process that imports torch afterwards needs torch's own
+    (newer) copy under that name, so map that one first when it exists."""
+    import ctypes
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            p = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
+                return p
+    except Exception:
+        pass
+    return None
+
+
 def init_comm(ctx, layout, owner):
     """Join this rank's Context to the job-wide NCCL communicator and install the block layout."""
+    _preload_nccl()
     import torch.distributed as dist
     from . import lib as _l
     rank, nranks = dist.get_rank(), dist.get_world_size()

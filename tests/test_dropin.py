@@ -47,3 +47,21 @@ def test_dropin_equals_reference(reference, name, gs):
                 assert_same_bits(d1, d2, f"{name} alg{alg} proj{proj} block {i}")
             assert_same_bits(raw1, raw2, f"{name} alg{alg} proj{proj} dense.raw")
             assert_same_bits(o1["step"], o2["step"], "grid_step_size")
+
+
+@pytest.mark.gpu
+def test_dropin_joins_the_masters_communicator(reference, monkeypatch):
+    # The multi-rank set-up of tessb200::dense (layout of every block gathered over master.communicator(), NCCL unique id
+    # from rank 0, tessb200_comm_init, tessb200_dense_set_layout) run in one process: the MPI stand-in has one rank, so
+    # the gathers are copies and the communicator has one member; the result must not change.
+    if not os.path.exists(DROPIN):
+        pytest.skip("oracle/_ref/libtess_dropin.so not built (needs /root/reference at build time)")
+    import torch  # noqa: F401  (maps torch's own libnccl.so.2 first: one NCCL per process, tess2_b200/multi.py)
+    from oracle import ref
+    monkeypatch.setenv("TESSB200_DIY_FORCE_JOIN", "1")
+    drp = ref.Checker("dropin")
+    blocks = dataset("u16x8")
+    o1 = reference.dense(blocks, (32, 32, 32), alg=0)
+    o2 = drp.dense(blocks, (32, 32, 32), alg=0)
+    for i, (d1, d2) in enumerate(zip(o1["block_density"], o2["block_density"])):
+        assert_same_bits(d1, d2, f"joined, block {i}")

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, h, alg, project, q):
+def _worker(rank, world, port, h, alg, project, q, mode="dense"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     try:
@@ -39,7 +39,29 @@ def _worker(rank, world, port, h, alg, project, q):
         ctx = tess2_b200.Context(rank)
         multi.init_comm(ctx, layout, owner)
         gs = (4 * h, 4 * h, 4 * h * world)
-        res = ctx.dense(alg, 3, dmin, dmax, project, (0.0, 0.0, 1.0), 1.0, 1e-4, gs, blocks, want_grid=False)
+        if mode == "peer_fails":
+            # rank 1 fails before the span exchange (nothing uploaded): rank 0 must come back with TESSB200_EPEER, not wait
+            params = ctx.make_params(alg, 3, dmin, dmax, project, (0.0, 0.0, 1.0), 1.0, 1e-4, gs)
+            if rank == 0:
+                ctx.upload(blocks)
+            codes = []
+            for _ in range(2):          # the second round starts from a clean exchange state again
+                try:
+                    ctx.run(params)
+                    codes.append(0)
+                except tess2_b200.TessB200Error as e:
+                    codes.append(e.code)
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(codes, gathered, dst=0)
+            if rank == 0:
+                q.put(("ok", gathered, 0))
+            ctx.close()
+            dist.destroy_process_group()
+            return
+        # three runs: the first agrees on the segment capacities (exact counts, one host read-back), the others exchange
+        # fixed-size sentinel-padded segments without reading anything back before the deposit
+        for _ in range(3):
+            res = ctx.dense(alg, 3, dmin, dmax, project, (0.0, 0.0, 1.0), 1.0, 1e-4, gs, blocks, want_grid=False)
         out = [(g, mn, num, np.ascontiguousarray(d)) for g, mn, num, d in zip(res.gids, res.block_min_idx, res.block_num_idx, res.block_density)]
         gathered = [None] * world if rank == 0 else None
         dist.gather_object(out, gathered, dst=0)
@@ -80,3 +102,23 @@ def test_two_gpu_dense_equals_oracle(port, alg, project):
         mn, num, d = by_gid[b["gid"]]
         assert mn == o["block_min_idx"][i] and num == o["block_num_idx"][i]
         assert_same_bits(d, o["block_density"][i], f"alg{alg} proj{project} block gid {b['gid']}")
+
+
+def test_a_failing_rank_does_not_hang_its_peers():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    tcp = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, tcp, 8, 0, False, q, "peer_fails")) for r in range(world)]
+    for p in procs:
+        p.start()
+    status, codes, _ = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+    assert status == "ok", codes
+    # rank 1: TESSB200_ESTATE (-7, run before upload); rank 0: TESSB200_EPEER (-9), both rounds
+    assert codes[1] == [-7, -7] and codes[0] == [-9, -9], codes

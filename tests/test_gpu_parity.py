@@ -246,6 +246,14 @@ def test_edge_cases(ctx):
         ctx.dense(7, 0, None, None, False, None, 1.0, 1e-4, (32, 32, 32), blocks)
     with pytest.raises(tess2_b200.TessB200Error):
         ctx.dense(0, 0, None, None, True, (1.0, 0.0, 0.0), 1.0, 1e-4, (32, 32, 32), blocks)
+    # a layout whose owner ranks do not ascend with the gid would route records to the wrong rank: refused
+    from tess2_b200 import multi
+    layout = [(b["gid"], b["bounds_min"], b["bounds_max"]) for b in blocks]
+    with pytest.raises(tess2_b200.TessB200Error):
+        multi.set_layout(ctx, layout, [1, 1, 1, 1, 0, 0, 0, 0])
+    with pytest.raises(tess2_b200.TessB200Error):
+        multi.set_layout(ctx, layout, [0, 0, 0, 0, 0, 0, 0, -1])
+    multi.set_layout(ctx, [], [])        # back to the single-rank state
 
 
 def test_three_step_interface_equals_one_call(ctx, port):

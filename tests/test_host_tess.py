@@ -196,3 +196,20 @@ def test_engine_is_exactly_delaunay_where_qhull_is_not():
                 opp = [x for x in v[u].tolist() if x not in face]
                 assert len(opp) == 1 and i in nb[u].tolist()
                 assert insphere(a, b, c, d, q[opp[0]]) * o * inside_sign <= 0, "a vertex inside a circumsphere"
+
+
+def test_settled_flag_reports_an_unsatisfied_ghost_region():
+    # the widening of the ghost region must never stop silently.  With one round and a margin far below the
+    # particle spacing the circumsphere test cannot hold for the border cells: settled == False; the defaults settle.
+    from tess2_b200 import host_tess
+    from tess2_b200.harness import particles
+    dom = (np.zeros(3, np.float32), np.full(3, 15, np.float32))
+    p = particles.uniform_particles(4000, *dom, seed=3)
+    bounds = host_tess.regular_blocks(*dom, 8)
+    ok = host_tess.tess(p, None, bounds, *dom)
+    assert all(b["settled"] for b in ok)
+    starved = host_tess.tess(p, None, bounds, *dom, margin0=0.05, max_rounds=1)
+    assert not any(b["settled"] for b in starved)
+    # a single block that holds the whole domain needs no ghosts and is settled at once
+    one = host_tess.tess(p, None, host_tess.regular_blocks(*dom, 1), *dom, margin0=0.05, max_rounds=1)
+    assert one[0]["settled"] and one[0]["rounds"] == 1
