@@ -621,7 +621,7 @@ def run_ours(args, rank, world, local_rank):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
-    roofline = make_roofline(st, stage, args.steps, T_local, P_local, cells_local, G_local, spans, dev_ms, peak, peak_src, main_alg)
+    roofline = make_roofline(st, stage, args.steps, T_local, P_local, cells_local, G_local, spans, dev_ms, peak, peak_src, main_alg, cfg, n)
     if k2:
         k2["frac_of_peak"] = k2["algorithmic_GBps"] / peak if k2["algorithmic_GBps"] else None
         roofline["stages"]["K2 k_cell_volumes on one block (60 T + 24 P), not part of dense()"] = k2
@@ -673,7 +673,7 @@ def run_ours(args, rank, world, local_rank):
     del st_main, keep, out_t
 
 
-def make_roofline(st, stage, steps, T, P, P0, G, S, dev_ms, peak, peak_src, alg):
+def make_roofline(st, stage, steps, T, P, P0, G, S, dev_ms, peak, peak_src, alg, cfg=3, n=1):
     """Per-stage device ms (CUDA events inside the library, same stream) against SURVEY 8(d)'s algorithmic bytes."""
     F = int(st.num_faces)
     ms = {k: v / steps for k, v in stage.items()}
@@ -697,7 +697,11 @@ def make_roofline(st, stage, steps, T, P, P0, G, S, dev_ms, peak, peak_src, alg)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom.split(" ")[0])
+        # DRAM bytes of the stage's kernels in one step, from the ncu launch list of profiles/run_step.py on one GPU
+        # (profiles/launches_r02.py); strong-scaling configs at N GPUs move 1/N of it per GPU
+        traffic = json.load(open(tpath)).get(f"c{cfg}_{dom.split(' ')[0]}")
+        if traffic is not None and n > 1:
+            traffic = traffic / n
     whole = 32 * T + 16 * P + 4 * G
     sub = {k: ms[k] for k in ms if ms[k] > 0}
     return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,

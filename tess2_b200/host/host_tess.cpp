@@ -75,6 +75,55 @@ struct BlockJob
   std::vector<int> mine;     // global ids of the originals, input order
 };
 
+// Tets in Morton order of their centroids.  The dense kernels chase tet records across neighbouring tets (star walks,
+// edge links, the neighbour gathers of the circumcenter pass); the incremental engine numbers tets in creation order,
+// with freed slots reused, which scatters the star of a site over the whole array.  Sorting them along a space-filling
+// curve makes neighbours in space neighbours in memory (measured on a B200: profiles/r02/summary.md, "tet order").
+// A renumbering only: same tets, same neighbour relation.
+static void morton_order_tets(std::vector<int> &tets, const std::vector<float> &P)
+{
+  const size_t nt = tets.size() / 8;
+  if (nt < 2 || nt >= (size_t)1 << 31) return;
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  std::vector<float> cen(3 * nt);
+  for (size_t t = 0; t < nt; t++)
+    for (int d = 0; d < 3; d++) {
+      const int *v = &tets[8 * t];
+      const float c = 0.25f * (P[3 * (size_t)v[0] + d] + P[3 * (size_t)v[1] + d] + P[3 * (size_t)v[2] + d] + P[3 * (size_t)v[3] + d]);
+      cen[3 * t + d] = c;
+      lo[d] = std::min(lo[d], (double)c);
+      hi[d] = std::max(hi[d], (double)c);
+    }
+  auto spread = [](uint32_t x) {
+    x &= 0x3ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+  };
+  std::vector<uint64_t> key(nt);
+  for (size_t t = 0; t < nt; t++) {
+    uint32_t q[3];
+    for (int d = 0; d < 3; d++) {
+      const double ext = std::max(hi[d] - lo[d], 1e-300);
+      q[d] = (uint32_t)std::min(1023.0, std::max(0.0, ((double)cen[3 * t + d] - lo[d]) / ext * 1024.0));
+    }
+    key[t] = ((uint64_t)(spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2)) << 32) | (uint64_t)t;
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<int> inv(nt), out(8 * nt);
+  for (size_t i = 0; i < nt; i++) inv[(size_t)(key[i] & 0xffffffffull)] = (int)i;
+  for (size_t i = 0; i < nt; i++) {
+    const int *src = &tets[8 * (size_t)(key[i] & 0xffffffffull)];
+    for (int j = 0; j < 4; j++) {
+      out[8 * i + j] = src[j];
+      out[8 * i + 4 + j] = src[4 + j] < 0 ? src[4 + j] : inv[src[4 + j]];
+    }
+  }
+  tets.swap(out);
+}
+
 int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, const double *dmin, const double *dmax, double margin0,
                int max_rounds, double max_growth, tessb200_host_block *out)
 {
@@ -176,6 +225,7 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     for (size_t t = 0; t < nt; t++)
       for (int j = 0; j < 4; j++) tets[8 * t + j] = pos[tets[8 * t + j]];
   }
+  if (!getenv("TESSB200_HOST_KEEP_TET_ORDER")) morton_order_tets(tets, P);
   out->gid = job.gid;
   for (int d = 0; d < 3; d++) { out->bounds_min[d] = (float)job.bmin[d]; out->bounds_max[d] = (float)job.bmax[d]; }
   out->num_orig_particles = n_orig;
