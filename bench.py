@@ -125,7 +125,7 @@ def clustered_blocks(spec, d, p, owner, bounds, gids, threads):
             try:
                 m = json.load(open(meta))
                 b = dict(gid=g, num_orig=m["num_orig"], bounds_min=bounds[g][0], bounds_max=bounds[g][1], rounds=m["rounds"], seconds=m["seconds"],
-                         settled=m.get("settled", True), cached=True)
+                         settled=m.get("settled", True), cached=True, made_in=m.get("made_in"), made_with=m.get("made_with"))
                 for k in keys:
                     b[k] = np.load(os.path.join(d, f"blk{g}_{k}.npy"))
                 blocks[g] = b
@@ -136,8 +136,10 @@ def clustered_blocks(spec, d, p, owner, bounds, gids, threads):
     t0 = time.time()
     if missing:
         made = host_tess.tess(np.asarray(p), np.asarray(owner), bounds, *dom, threads=threads, gids=missing)
+        wall = time.time() - t0
         for b in made:
             b["cached"] = False
+            b["made_in"], b["made_with"] = wall, f"{len(missing)} blocks on {threads} threads"
             b.pop("global_ids", None)
             blocks[b["gid"]] = b
             nbytes = sum(b[k].nbytes for k in keys)
@@ -146,7 +148,8 @@ def clustered_blocks(spec, d, p, owner, bounds, gids, threads):
                     for k in keys:
                         np.save(os.path.join(d, f"blk{b['gid']}_{k}.npy"), b[k])
                     tmp = os.path.join(d, f"blk{b['gid']}.json.tmp{os.getpid()}")
-                    json.dump(dict(num_orig=int(b["num_orig"]), rounds=int(b["rounds"]), seconds=float(b["seconds"]), settled=bool(b["settled"])), open(tmp, "w"))
+                    json.dump(dict(num_orig=int(b["num_orig"]), rounds=int(b["rounds"]), seconds=float(b["seconds"]), settled=bool(b["settled"]),
+                                   made_in=b["made_in"], made_with=b["made_with"]), open(tmp, "w"))
                     os.replace(tmp, os.path.join(d, f"blk{b['gid']}.json"))
                 except OSError as e:
                     log(f"block cache not written ({e})")
@@ -180,7 +183,11 @@ def build_workload(cfg, n_ranks, rank, scale=1, gids=None, threads=None):
     n = spec["side"]
     dmin, dmax = np.zeros(3, np.float32), np.full(3, n - 1, np.float32)
     layout = [(g, bounds[g][0], bounds[g][1]) for g in range(nb)]
+    # wall time of the host tess() of this rank's blocks: now, or -- blocks from the box's cache -- when they were made
+    if n_made == 0 and blocks:
+        tess_s = max((b.get("made_in") or 0.0) for b in blocks)
     host = dict(engine="tess2_b200/host (C++ incremental Delaunay, exact predicates)", generate_seconds=gen_s, tess_seconds=tess_s,
+                tess_made=sorted({str(b.get("made_with")) for b in blocks}), engine_seconds_per_block=[round(float(b["seconds"]), 2) for b in blocks],
                 blocks_tessellated_now=n_made, blocks_from_cache=len(mine) - n_made, threads=thr,
                 max_ghost_rounds=int(max([b["rounds"] for b in blocks], default=0)), all_blocks_settled=bool(all(b.get("settled", True) for b in blocks)))
     # ng = 0: DataBounds comes from the layout (every block's bounds), so the grid is the same at every N
