@@ -609,7 +609,7 @@ struct DirectSmem
   static constexpr int W = (M * M * M + 31) / 32;   // words of one cell's flags
   CellHdr hdr[DIRECT_THREADS];
   int off[DIRECT_THREADS + 1];                      // exclusive prefix of the cells' face counts
-  int warp_tot[DIRECT_THREADS / 32];
+  alignas(16) int warp_tot[DIRECT_THREADS / 32];     // own 16 bytes: the compiler reads the four totals with one 128-bit load
   uint32_t pos[DIRECT_THREADS][W], neg[DIRECT_THREADS][W];
   uint32_t lines[DIRECT_THREADS / 32][SCAN_LINE_CAP * 32];
 };
