@@ -1449,18 +1449,114 @@ extern "C" int tessb200_circumcenters(tessb200_ctx *c, int num_particles, const 
   return 0;
 }
 
+// K2 on the dense stage's star kernels (kernels.cuh, "K2 on the dense stage's star kernels"): k_cell_bfs + k_cell_nbrs
+// (+ the general walk) in their volumes-only mode give every complete site its face list in neighbor_edges' order, one
+// thread per face computes the face's term, one thread per site adds its terms in order.  TESSB200_K2_SIMPLE=1 keeps round 1's
+// one-thread-per-site kernel (k_cell_volumes) for A/B measurements.
+static int cell_volumes_simple(tessb200_ctx *c, TmpBlock &t, int num_sites, float mass, int *complete, float *volume, float *density);
+
 extern "C" int tessb200_cell_volumes(tessb200_ctx *c, int num_sites, int num_particles, const float *particles, int num_tets, const int *tets,
                                      const int *vert_to_tet, float mass, int *complete, float *volume, float *density)
 {
   if (!c || !particles) return fail(TESSB200_EINVAL, "NULL argument");
   if (num_sites < 0 || num_sites > num_particles) return fail(TESSB200_EINVAL, "num_sites out of range");
   CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
   TmpBlock t;
   TRY(upload_tmp(c, t, num_particles, particles, num_tets, tets, vert_to_tet));
-  CU(cudaEventRecord(c->ev[18], c->stream));
-  TRY(prep_block_geometry(c, &t.b));
   c->last_k2_ms = 0.0f;
-  if (num_sites) {
+  const char *simple = getenv("TESSB200_K2_SIMPLE");
+  if ((simple && simple[0] == '1') || num_sites == 0 || num_tets == 0) {
+    CU(cudaEventRecord(c->ev[18], s));
+    TRY(prep_block_geometry(c, &t.b));
+    return num_sites ? cell_volumes_simple(c, t, num_sites, mass, complete, volume, density) : 0;
+  }
+  BlockRes *b = &t.b;
+  b->num_orig = num_sites;
+  // processing order only: Morton keys inside the particles' bounding box
+  for (int d = 0; d < 3; d++) { b->bmin[d] = INFINITY; b->bmax[d] = -INFINITY; }
+  for (size_t i = 0; i < (size_t)num_particles; i++)
+    for (int d = 0; d < 3; d++) {
+      const float x = particles[3 * i + d];
+      if (x < b->bmin[d]) b->bmin[d] = x;
+      if (x > b->bmax[d]) b->bmax[d] = x;
+    }
+  const long long cells = num_sites, ntets = num_tets;
+  if ((unsigned long long)2 * ntets + (unsigned long long)cells + 64 >= 0xffffffffull) return fail(TESSB200_ELIMIT, "face list exceeds 2^32 face pairs");
+  const uint32_t pairs = (uint32_t)(2 * ntets + cells + 64), cap_ovf = (uint32_t)std::max<long long>(1024, cells / 64);
+  const int slow_warps = 148 * 4 * 4;
+  const unsigned gctas = cdiv(cells, TOPO_THREADS);
+  const size_t n_slots = (size_t)gctas * TOPO_THREADS;
+  // every allocation before the timed region (tessb200_cell_volumes_ms reports the kernels, not cudaMalloc)
+  Buf d_comp, d_vol, d_den, d_terms;
+  auto cleanup = [&]() { d_comp.release(); d_vol.release(); d_den.release(); d_terms.release(); };
+  int rc = 0;
+  size_t sort_tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)cells, 0, 30, s);
+  if ((rc = d_comp.ensure(4 * (size_t)cells)) || (rc = d_vol.ensure(4 * (size_t)cells)) || (rc = d_den.ensure(4 * (size_t)cells)) ||
+      (rc = d_terms.ensure(8 * (size_t)pairs)) || (rc = c->face_list.ensure(32 * (size_t)pairs)) || (rc = c->hdr_small.ensure(sizeof(CellHdr) * (size_t)cells)) ||
+      (rc = c->hdr_big.ensure(sizeof(CellHdr) * (size_t)cells)) || (rc = c->big_bitoff.ensure(8 * (size_t)cells)) || (rc = c->overflow.ensure(sizeof(uint2) * (size_t)cap_ovf)) ||
+      (rc = c->ws_big.ensure(sizeof(int) * (size_t)(BIG_STAR_CAP + 2 * BIG_NBR_CAP) * (size_t)slow_warps)) || (rc = c->pre_hdr.ensure(sizeof(CellHdr) * n_slots)) ||
+      (rc = c->cand.ensure(sizeof(int2) * n_slots * TOPO_CAND_CAP)) || (rc = c->d_blocks.ensure(sizeof(DevBlock))) || (rc = c->d_cnt.ensure(sizeof(Counters))) ||
+      (rc = c->mkeys[0].ensure(4 * (size_t)cells)) || (rc = c->mkeys[1].ensure(4 * (size_t)cells)) || (rc = c->order[0].ensure(4 * (size_t)cells)) ||
+      (rc = c->order[1].ensure(4 * (size_t)cells)) || (rc = c->cub_tmp.ensure(sort_tmp)) || (rc = b->walk.ensure(sizeof(WalkRec) * (size_t)ntets)) ||
+      (rc = b->hull.ensure((size_t)std::max(1, num_particles))) || (rc = b->p4.ensure(sizeof(float4) * (size_t)std::max(1, num_particles)))) {
+    cleanup();
+    return rc;
+  }
+  CU(cudaEventRecord(c->ev[18], s));
+  TRY(prep_block_geometry(c, b, true, true));
+  {
+    const float3 bmin = make_float3(b->bmin[0], b->bmin[1], b->bmin[2]);
+    const float3 inv = make_float3(1.0f / fmaxf(b->bmax[0] - b->bmin[0], 1e-30f), 1.0f / fmaxf(b->bmax[1] - b->bmin[1], 1e-30f), 1.0f / fmaxf(b->bmax[2] - b->bmin[2], 1e-30f));
+    k_morton_keys<<<cdiv(cells, 256), 256, 0, s>>>((const float *)b->particles.p, (int)cells, bmin, inv, 0u, 0, c->mkeys[0].as<uint32_t>(), c->order[0].as<uint32_t>());
+    size_t tmp = c->cub_tmp.cap;
+    CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, c->mkeys[0].as<uint32_t>(), c->mkeys[1].as<uint32_t>(), c->order[0].as<uint32_t>(), c->order[1].as<uint32_t>(), (int)cells, 0, 30, s));
+  }
+  DevBlock db = dev_block(b);
+  db.order = c->order[1].as<uint32_t>();
+  db.cell_base = 0;
+  cudaMemcpyAsync(c->d_blocks.p, &db, sizeof(DevBlock), cudaMemcpyHostToDevice, s);
+  cudaMemsetAsync(c->d_cnt.p, 0, sizeof(Counters), s);
+  Counters *cnt = c->d_cnt.as<Counters>();
+  GridGeom g;
+  memset(&g, 0, sizeof(g));
+  g.alg = TB_ALG_VOLUMES;
+  TopoOut to;
+  memset(&to, 0, sizeof(to));
+  to.small = c->hdr_small.as<CellHdr>(); to.big = c->hdr_big.as<CellHdr>(); to.big_bit_off = c->big_bitoff.as<unsigned long long>();
+  to.overflow = c->overflow.as<uint2>(); to.faces = c->face_list.as<FaceRef>(); to.cnt = cnt;
+  to.cap_pairs = pairs; to.cap_small = (uint32_t)cells; to.cap_big = (uint32_t)cells; to.cap_overflow = cap_ovf;
+  k_vol_defaults<<<cdiv(cells, 256), 256, 0, s>>>((const int *)b->v2t.p, (int)cells, d_comp.as<int>(), d_vol.as<float>(), d_den.as<float>());
+  k_cell_bfs<<<gctas, TOPO_THREADS, BFS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), 0, 1, g, to, c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
+  k_cell_nbrs<<<gctas, TOPO_THREADS, NBRS_SMEM, s>>>(c->d_blocks.as<DevBlock>(), to, c->pre_hdr.as<CellHdr>(), c->cand.as<int2>());
+  k_cell_bfs_big<<<slow_warps / 4, 128, 0, s>>>(c->d_blocks.as<DevBlock>(), g, to, c->overflow.as<uint2>(), c->ws_big.as<int>());
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_cnt, c->d_cnt.p, sizeof(Counters), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { cleanup(); return fail(TESSB200_ECUDA, "cell volumes (star kernels): %s", cudaGetErrorString(e)); }
+  const Counters &h = *c->h_cnt;
+  if (h.n_overflow > cap_ovf || h.plane_cursor > pairs) { cleanup(); return fail(TESSB200_ELIMIT, "cell volumes: %u oversized stars / %u face pairs exceed the workspace", h.n_overflow, h.plane_cursor); }
+  const size_t nfaces = (size_t)h.plane_cursor * 2;
+  if (nfaces) k_face_vol_terms<<<cdiv((long long)nfaces, 256), 256, 0, s>>>(c->face_list.as<FaceRef>(), nfaces, c->d_blocks.as<DevBlock>(), d_terms.as<float>());
+  const uint32_t n_small = std::min(h.n_small, to.cap_small), n_big = std::min(h.n_big, to.cap_big);
+  if (n_small) k_cell_vol_sum<<<cdiv(n_small, 256), 256, 0, s>>>(to.small, n_small, d_terms.as<float>(), c->d_blocks.as<DevBlock>(), mass, d_comp.as<int>(), d_vol.as<float>(), d_den.as<float>());
+  if (n_big) k_cell_vol_sum<<<cdiv(n_big, 256), 256, 0, s>>>(to.big, n_big, d_terms.as<float>(), c->d_blocks.as<DevBlock>(), mass, d_comp.as<int>(), d_vol.as<float>(), d_den.as<float>());
+  cudaEventRecord(c->ev[19], s);
+  if (complete) cudaMemcpyAsync(complete, d_comp.p, 4 * (size_t)cells, cudaMemcpyDeviceToHost, s);
+  if (volume) cudaMemcpyAsync(volume, d_vol.p, 4 * (size_t)cells, cudaMemcpyDeviceToHost, s);
+  if (density) cudaMemcpyAsync(density, d_den.p, 4 * (size_t)cells, cudaMemcpyDeviceToHost, s);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cleanup();
+  if (e != cudaSuccess) return fail(TESSB200_ECUDA, "cell volumes: %s", cudaGetErrorString(e));
+  cudaEventElapsedTime(&c->last_k2_ms, c->ev[18], c->ev[19]);
+  return 0;
+}
+
+static int cell_volumes_simple(tessb200_ctx *c, TmpBlock &t, int num_sites, float mass, int *complete, float *volume, float *density)
+{
+  {
     Buf d_comp, d_vol, d_den, d_ovf, d_n, d_ws;
     auto cleanup = [&]() { d_comp.release(); d_vol.release(); d_den.release(); d_ovf.release(); d_n.release(); d_ws.release(); };
     const uint32_t cap = (uint32_t)std::max(1024, num_sites / 64);

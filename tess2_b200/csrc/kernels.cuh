@@ -23,6 +23,10 @@
 namespace tb
 {
 
+// GridGeom::alg value of the per-site volume pipeline (tessb200_cell_volumes): the star kernels skip the data-bounds filter and
+// the index box of the dense stage (every complete cell is kept, whatever its extent)
+constexpr int TB_ALG_VOLUMES = -1;
+
 // ---- device-side descriptors -------------------------------------------------------------------
 struct DevBlock
 {
@@ -315,13 +319,15 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
                                            const DevBlock &blk, int blk_id, const GridGeom &g, const TopoOut &out)
 {
   int lo[3] = {0, 0, 0}, n3[3] = {0, 0, 0};
-  if (status == CELL_OK) {
+  const bool vol_only = g.alg == TB_ALG_VOLUMES;
+  if (status == CELL_OK && !vol_only) {
     // src/dense.cpp:1385-1392
     for (int d = 0; d < 3; d++)
       if (cmin[d] < fsub(g.dmin[d], g.dext_eps[d]) || cmax[d] > fadd(g.dmax[d], g.dext_eps[d])) status = CELL_OUTSIDE;
   }
   long long npts = 0;
-  if (status == CELL_OK) {
+  if (status == CELL_OK && vol_only) { n3[0] = n3[1] = n3[2] = 1; npts = 1; }
+  if (status == CELL_OK && !vol_only) {
     for (int d = 0; d < 3; d++) {
       lo[d] = phys2idx1(cmin[d], g.step[d], g.gmin[d]);
       int hi = phys2idx1(cmax[d], g.step[d], g.gmin[d]);
@@ -414,6 +420,7 @@ __global__ void k_morton_keys(const float *__restrict__ particles, int n, float3
 // src/dense.cpp:1385-1392: a cell whose box leaves the data bounds (plus eps) is skipped
 __device__ __forceinline__ bool box_outside_data(const float *cmin, const float *cmax, const GridGeom &g)
 {
+  if (g.alg == TB_ALG_VOLUMES) return false;
   bool out = false;
   for (int d = 0; d < 3; d++) out = out || cmin[d] < fsub(g.dmin[d], g.dext_eps[d]) || cmax[d] > fadd(g.dmax[d], g.dext_eps[d]);
   return out;
@@ -471,12 +478,14 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__res
   uint32_t o_slot = warp_append<unsigned int>(&out.cnt->n_overflow, ovf);
   if (ovf && o_slot < out.cap_overflow) out.overflow[o_slot] = make_uint2((unsigned)blk_id, (unsigned)cell);
   int lo[3] = {0, 0, 0}, n3[3] = {0, 0, 0};
-  if (status == CELL_OK) {
+  const bool vol_only = g.alg == TB_ALG_VOLUMES;
+  if (status == CELL_OK && !vol_only) {
     // src/dense.cpp:1385-1392
     for (int d = 0; d < 3; d++)
       if (cmin[d] < fsub(g.dmin[d], g.dext_eps[d]) || cmax[d] > fadd(g.dmax[d], g.dext_eps[d])) status = CELL_OUTSIDE;
   }
-  if (status == CELL_OK) {
+  if (status == CELL_OK && vol_only) n3[0] = n3[1] = n3[2] = 1;
+  if (status == CELL_OK && !vol_only) {
     for (int d = 0; d < 3; d++) {
       lo[d] = phys2idx1(cmin[d], g.step[d], g.gmin[d]);
       int hi = phys2idx1(cmax[d], g.step[d], g.gmin[d]);
@@ -1725,6 +1734,76 @@ __global__ void __launch_bounds__(128) k_cell_volumes_big(DevBlock blk, const ui
   if (complete_out) complete_out[site] = comp;
   if (volume_out) volume_out[site] = vol;
   if (density_out) density_out[site] = vol > 0.0f ? fdiv(mass, vol) : 0.0f;
+}
+
+
+// ---- K2 on the dense stage's star kernels ------------------------------------------------------------------
+// volume() (src/volume.cpp:13-54) = sum over the Delaunay neighbours u, in neighbor_edges' order, of [fan area of the dual face
+// from edge_link[0]] * |u - v| / 6.  k_cell_bfs + k_cell_nbrs (+ the general walk) give every complete site its face list in that
+// order; the per-face terms are independent -- one thread per FACE (k_face_vol_terms: edge-link walk, fan area through double as
+// the reference's sqrt binds to double, src/volume.cpp:45) -- and a site's terms are then added in order by one thread per site
+// (k_cell_vol_sum: the float sum of the reference, a segmented reduction that keeps the reference's order; no atomics).
+__global__ void __launch_bounds__(256) k_face_vol_terms(const FaceRef *__restrict__ faces, size_t n_faces, const DevBlock *__restrict__ blocks,
+                                                         float *__restrict__ terms)
+{
+  const size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  FaceRef r;
+  r.site = 0; r.u = -1; r.ut = 0; r.blk = 0;
+  if (f < n_faces) r = faces[f];
+  const bool act = f < n_faces && r.u >= 0;
+  AreaAccum aa;
+  aa.area = 0.0f;
+  if (act) {
+    const DevBlock &b = blocks[r.blk & ~FACE_DIRECT];
+    if (b.walk) {
+      const int4 v0 = b.tets[2 * (size_t)r.ut];
+      const int s_c = v0.x == r.site ? 0 : (v0.y == r.site ? 1 : (v0.z == r.site ? 2 : 3));
+      const int s_u = v0.x == r.u ? 0 : (v0.y == r.u ? 1 : (v0.z == r.u ? 2 : 3));
+      walk_edge_link_rec(s_c, s_u, r.ut, b.walk, aa);
+    } else {
+      walk_edge_link(r.site, r.u, r.ut, b.tets, b.cc, aa);
+    }
+  }
+  __syncwarp();
+  if (!act) return;
+  const DevBlock &b = blocks[r.blk & ~FACE_DIRECT];
+  const float *pv = b.particles + 3 * (size_t)r.site, *pu = b.particles + 3 * (size_t)r.u;
+  // distance(), src/tet.cpp:146-153: n += (u-v)*(u-v); sqrt in double rounded to float == sqrtf
+  float d2 = 0.0f;
+  for (int d = 0; d < 3; d++) {
+    const float df = fsub(pu[d], pv[d]);
+    d2 = fadd(d2, fmul(df, df));
+  }
+  terms[f] = fdiv(fmul(aa.area, fsqrt(d2)), 6.0f);      // src/volume.cpp:50
+}
+
+__global__ void __launch_bounds__(256) k_cell_vol_sum(const CellHdr *__restrict__ hdrs, uint32_t n_hdrs, const float *__restrict__ terms,
+                                                       const DevBlock *__restrict__ blocks, float mass, int *__restrict__ complete_out,
+                                                       float *__restrict__ volume_out, float *__restrict__ density_out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_hdrs) return;
+  const CellHdr h = hdrs[i];
+  const int nf = (int)(h.blk_nf & 0xffffu);
+  const uint32_t site = h.cell - blocks[h.blk_nf >> 16].cell_base;
+  const float *t = terms + (size_t)h.plane_off * 2;
+  float vol = 0.0f;
+  for (int k = 0; k < nf; k++) vol = fadd(vol, t[k]);
+  if (complete_out) complete_out[site] = 1;
+  if (volume_out) volume_out[site] = vol;
+  if (density_out) density_out[site] = vol > 0.0f ? fdiv(mass, vol) : 0.0f;
+}
+
+// sites that are in no tet (-1 / -2) or whose cell is infinite (0 / -1): the default the complete cells overwrite
+__global__ void k_vol_defaults(const int *__restrict__ v2t, int num_sites, int *__restrict__ complete_out, float *__restrict__ volume_out,
+                               float *__restrict__ density_out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_sites) return;
+  const bool none = v2t[i] < 0;
+  if (complete_out) complete_out[i] = none ? -1 : 0;
+  if (volume_out) volume_out[i] = none ? -2.0f : -1.0f;
+  if (density_out) density_out[i] = 0.0f;
 }
 
 // ---- DTFE mode (alg 2) -------------------------------------------------------------------------------
