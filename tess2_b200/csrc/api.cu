@@ -170,6 +170,8 @@ struct tessb200_ctx
   Buf fz_hdr, fz_bits, fz_pool;     // k_cell_fused -> k_cell_emit: headers, in-line inside bits, pool for the larger index boxes
   Buf hdr_dir[3];                   // cells of the small-box classes (k_cell_direct)
   Buf pt_off, pt_fill, big_points;  // shared grid points: segment offsets, fill cursors, the points with many deposits
+  Buf cic_vals, cic_keys[2], cic_ids[2], cic_count, cic_start;   // DENSE_CIC: weights, base cells and ids of the particles, particles per base cell
+  bool cic_gather = true;           // TESSB200_CIC_GATHER=0: every CIC deposit as a record (round 1's k_cic)
   // span exchange: per (source, destination) capacities agreed in an exact round; later runs exchange fixed-size,
   // sentinel-padded segments and need no host read-back before the deposit
   std::vector<unsigned long long> xcap;   // [src * nranks + dst], identical on every rank; empty = no agreement yet
@@ -231,6 +233,8 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
     c->fused = f && f[0] == '1';
     const char *d = getenv("TESSB200_DIRECT");
     c->direct = !(d && d[0] == '0');
+    const char *cg = getenv("TESSB200_CIC_GATHER");
+    c->cic_gather = !(cg && cg[0] == '0');
     const char *sg = getenv("TESSB200_SEGMENTS");
     c->segments = sg && sg[0] == '1';
     CU(cudaFuncSetAttribute(k_point_apply_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POINT_BIG_SMEM));        // opt-in: measured slower than the four-kernel path (profiles/r02/fused_a_*)
@@ -261,7 +265,8 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->pre_hdr, &c->cand, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
                  &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small, &c->pt_count,
-                 &c->fz_hdr, &c->fz_bits, &c->fz_pool, &c->hdr_dir[0], &c->hdr_dir[1], &c->hdr_dir[2], &c->pt_off, &c->pt_fill, &c->big_points};
+                 &c->fz_hdr, &c->fz_bits, &c->fz_pool, &c->hdr_dir[0], &c->hdr_dir[1], &c->hdr_dir[2], &c->pt_off, &c->pt_fill, &c->big_points,
+                 &c->cic_vals, &c->cic_keys[0], &c->cic_keys[1], &c->cic_ids[0], &c->cic_ids[1], &c->cic_count, &c->cic_start};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -872,6 +877,31 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
   } else {
     TRY(ensure_spans(std::max<unsigned long long>(1ull << 16, 8ull * (unsigned long long)cells + 1024)));
   }
+  // DENSE_CIC, 3-D: the deposits of a block's own points are gathered per grid point (kernels.cuh, "K4 without records for the
+  // local deposits"); only the deposits that leave their block are records
+  std::vector<CicBlock> cicb(nloc);
+  unsigned long long cic_cells = 0;
+  bool gather = false;
+  if (!tess && !G.g.project && c->cic_gather && cells > 0) {
+    unsigned long long part0 = 0;
+    for (int k = 0; k < nloc; k++) {
+      const BlockBox &bx = G.boxes[first_local_all + k];
+      CicBlock &cb = cicb[k];
+      for (int d = 0; d < 3; d++) { cb.o[d] = bx.b_lo[d] - 1; cb.d[d] = bx.b_num[d] + 1; }
+      cb.cell0 = cic_cells;
+      cb.part0 = part0;
+      cic_cells += (unsigned long long)cb.d[0] * cb.d[1] * cb.d[2];
+      part0 += (unsigned long long)c->blocks[k]->num_orig;
+    }
+    gather = cic_cells < 0xfffffff0ull && (unsigned long long)cells < 0xfffffff0ull;
+    if (gather) {
+      TRY(c->cic_vals.ensure(32 * (size_t)cells));
+      for (int i = 0; i < 2; i++) { TRY(c->cic_keys[i].ensure(4 * (size_t)cells)); TRY(c->cic_ids[i].ensure(4 * (size_t)cells)); }
+      TRY(c->cic_count.ensure(4 * (size_t)cic_cells));
+      TRY(c->cic_start.ensure(4 * (size_t)cic_cells));
+      CU(cudaMemsetAsync(c->cic_count.p, 0, 4 * (size_t)cic_cells, s));
+    }
+  }
 
   CU(cudaEventRecord(c->ev[3], s));
   long long cell_off = 0;
@@ -899,7 +929,11 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
       for (int k = k0; k < k1; k++) {
         const DevBlock &db = hblocks[first_local_all + k];
         if (db.num_orig == 0) continue;
-        k_cic<<<cdiv(db.num_orig, 256), 256, 0, s>>>(db, first_local_all + k, sc, G.g, so);
+        if (gather)
+          k_cic_prepare<<<cdiv(db.num_orig, 256), 256, 0, s>>>(db, first_local_all + k, cicb[k], sc, G.g, so, c->cic_vals.as<float>(), c->cic_keys[0].as<uint32_t>(),
+                                                               c->cic_ids[0].as<uint32_t>(), c->cic_count.as<unsigned int>());
+        else
+          k_cic<<<cdiv(db.num_orig, 256), 256, 0, s>>>(db, first_local_all + k, sc, G.g, so);
         COUNT_LAUNCH(c, 1);
       }
       CU(cudaGetLastError());
@@ -1112,7 +1146,42 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
 
   // 3-D runs: only the deposits that meet on a grid point need the reference's order (kernels.cuh, "K3b without the big sort")
   bool placed = false;
-  if (!G.g.project && n_spans && G.out_floats && c->segments && G.kl.cell_bits <= 31 && G.out_floats < 0xffffffffll) {
+  if (gather && G.out_floats) {
+    // DENSE_CIC: per grid point, the block's own particles in particle order (k_cic_gather writes every point of the
+    // sub-grids once), then the records that crossed block boundaries on top, in order (sort + k_rows, sparse form)
+    {
+      size_t tmp = 0;
+      CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->cic_count.as<unsigned int>(), c->cic_start.as<unsigned int>(), (int)cic_cells, s));
+      size_t tmp2 = 0;
+      const int kbits = ceil_log2(cic_cells + 2);
+      CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, c->cic_keys[0].as<uint32_t>(), c->cic_keys[1].as<uint32_t>(), c->cic_ids[0].as<uint32_t>(),
+                                         c->cic_ids[1].as<uint32_t>(), (int)cells, 0, kbits, s));
+      TRY(c->cub_tmp.ensure(std::max(tmp, tmp2)));
+      tmp = tmp2 = c->cub_tmp.cap;
+      CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cic_count.as<unsigned int>(), c->cic_start.as<unsigned int>(), (int)cic_cells, s));
+      CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp2, c->cic_keys[0].as<uint32_t>(), c->cic_keys[1].as<uint32_t>(), c->cic_ids[0].as<uint32_t>(),
+                                         c->cic_ids[1].as<uint32_t>(), (int)cells, 0, kbits, s));
+    }
+    for (int k = 0; k < nloc; k++) {
+      BlockRes *b = c->blocks[k];
+      if (!b->npts) continue;
+      k_cic_gather<<<cdiv(b->npts, 256), 256, 0, s>>>(cicb[k], G.boxes[first_local_all + k], c->cic_start.as<unsigned int>(), c->cic_count.as<unsigned int>(),
+                                                      c->cic_ids[1].as<uint32_t>(), c->cic_vals.as<float>(), G.g.div, c->out.as<float>() + b->out_off);
+      COUNT_LAUNCH(c, 1);
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->ev[8], s));      // ms_sort (7 -> 8): scan + particle sort + gather; ms_deposit: the records that crossed block boundaries
+    TRY(sort_records(n_spans));
+    if (n_spans) {
+      k_row_starts<<<cdiv((long long)n_spans + 1, 256), 256, 0, s>>>(c->keys[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->row_start.as<unsigned long long>());
+      k_rows<<<cdiv((long long)G.nrows, rw), rw * 32, rows_smem, s>>>(c->data[cur].as<uint64_t>(), c->row_start.as<unsigned long long>(), G.row0, 0ull, G.nrows,
+                                                                    c->d_rblocks.as<RowBlock>(), (int)G.rblocks.size(), G.g.div, G.nx_max, c->out.as<float>(), 1);
+      COUNT_LAUNCH(c, 2);
+    }
+    placed = true;
+    n_shared_stat = (long long)n_spans;
+    if (io.pipelined) TRY(copy_out_all());
+  } else if (!G.g.project && n_spans && G.out_floats && c->segments && G.kl.cell_bits <= 31 && G.out_floats < 0xffffffffll) {
     // every shared point gets a segment of 8-byte records (offsets = scan of the counts); a point's few records are
     // sorted where they are applied: no global sort, no host read-back before the deposit
     const unsigned long long seg_cap = span_cap;                    // the second half of the double buffer

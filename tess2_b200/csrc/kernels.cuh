@@ -1228,6 +1228,134 @@ __global__ void __launch_bounds__(256) k_cic(DevBlock blk, int blk_id, ScanCtx s
   }
 }
 
+
+// ---- K4 without records for the local deposits ---------------------------------------------------------------
+// IterateCellsCic (src/dense.cpp:486-562) adds, at every grid point, first the block's OWN particles in particle order
+// (float path, :539) and then the points received from other blocks by source gid (recvd_pts, double path).  The first
+// part needs no deposit records at all: k_cic_prepare computes every particle's eight weights once and its base cell
+// (the truncated index of DistributeScalarCIC, :1787-1872); a stable radix sort of the particle ids by base cell keeps
+// the particle order inside a cell; k_cic_gather, one thread per grid point of a block's sub-grid, merges the (at most
+// eight) base cells that touch its point by particle id and adds their weights in that order -- the reference's float
+// sum, every grid point written once, no atomics.  Only the deposits that leave their block (block and rank
+// boundaries) still travel as records and are added on top in the reference's order (sort + k_rows in its sparse form).
+struct CicBlock
+{
+  int o[3];                  // origin of the block's base-cell box: b_lo - 1
+  int d[3];                  // its extent: b_num + 1
+  unsigned long long cell0;  // first base cell of this block in the rank-wide numbering
+  unsigned long long part0;  // first particle of this block in the rank-wide arrays (vals, keys)
+};
+
+// drops the records of the emitting block's own points (key bit `remote` == 0): the gather adds those
+template <class Inner>
+struct RemoteOnlyEmit
+{
+  Inner &in;
+  KeyLayout kl;
+  __device__ __forceinline__ void operator()(uint64_t k, uint64_t d)
+  {
+    if ((k >> (kl.z_bits + kl.cell_bits)) & 1ull) in(k, d);
+  }
+};
+
+__global__ void __launch_bounds__(256) k_cic_prepare(DevBlock blk, int blk_id, CicBlock cb, ScanCtx sc, const __grid_constant__ GridGeom g, SpanOut out,
+                                                      float *__restrict__ vals_out, uint32_t *__restrict__ keys, uint32_t *__restrict__ ids,
+                                                      unsigned int *__restrict__ cell_count)
+{
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = cell < blk.num_orig;
+  float site[3] = {0, 0, 0};
+  int nrec = 0;
+  const uint32_t gc = blk.cell_base + (uint32_t)cell;
+  if (act) {
+    site[0] = blk.particles[3 * (size_t)cell]; site[1] = blk.particles[3 * (size_t)cell + 1]; site[2] = blk.particles[3 * (size_t)cell + 2];
+    int i0[3];
+    float vals[8];
+    cic_weights(site, g.mass, g, i0, vals);
+    float4 *vo = reinterpret_cast<float4 *>(vals_out + 8 * (cb.part0 + (size_t)cell));
+    vo[0] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+    vo[1] = make_float4(vals[4], vals[5], vals[6], vals[7]);
+    // base cell inside the block's box of base cells, or behind every cell (a particle none of whose corners is a point of
+    // the block's own sub-grid)
+    const long long bx = (long long)i0[0] - cb.o[0], by = (long long)i0[1] - cb.o[1], bz = (long long)i0[2] - cb.o[2];
+    uint32_t key = 0xffffffffu;                      // (the host keeps the number of base cells below 2^32 - 1)
+    if (bx >= 0 && bx < cb.d[0] && by >= 0 && by < cb.d[1] && bz >= 0 && bz < cb.d[2]) {
+      key = (uint32_t)(cb.cell0 + (unsigned long long)((bz * cb.d[1] + by) * cb.d[0] + bx));
+      atomicAdd(&cell_count[key], 1u);
+    }
+    keys[cb.part0 + (size_t)cell] = key;
+    ids[cb.part0 + (size_t)cell] = (uint32_t)cell;
+    // the whole window inside the block's own points and sub-grid (every interior particle): no record, no second look
+    const BlockBox &bb = sc.boxes[blk_id];
+    bool interior = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const int lo = bb.p_lo[d] > bb.b_lo[d] ? bb.p_lo[d] : bb.b_lo[d];
+      const int hi = bb.p_hi[d] < bb.b_lo[d] + bb.b_num[d] - 1 ? bb.p_hi[d] : bb.b_lo[d] + bb.b_num[d] - 1;
+      interior = interior && i0[d] >= lo && i0[d] + 1 <= hi;
+    }
+    if (!interior) {
+      CountEmit ce{0};
+      RemoteOnlyEmit<CountEmit> re{ce, sc.kl};
+      emit_cic(sc, blk_id, gc, site, g, 1, re);
+      nrec = ce.n;
+    }
+  }
+  unsigned long long base = warp_alloc<unsigned long long>(&out.cnt->n_spans, (unsigned long long)nrec);
+  warp_count(&out.cnt->n_deposit, act);
+  if (act && nrec) {
+    StoreEmit se{out.keys, out.data, base, out.capacity};
+    RemoteOnlyEmit<StoreEmit> re{se, sc.kl};
+    emit_cic(sc, blk_id, gc, site, g, 1, re);
+  }
+}
+
+// one thread per grid point of the block's sub-grid
+__global__ void __launch_bounds__(256) k_cic_gather(CicBlock cb, BlockBox bx, const unsigned int *__restrict__ cell_start, const unsigned int *__restrict__ cell_count,
+                                                     const uint32_t *__restrict__ sorted_ids, const float *__restrict__ vals, float div, float *__restrict__ out)
+{
+  const long long npts = (long long)bx.b_num[0] * bx.b_num[1] * bx.b_num[2];
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  const int lx = (int)(p % bx.b_num[0]);
+  const long long r = p / bx.b_num[0];
+  const int ly = (int)(r % bx.b_num[1]), lz = (int)(r / bx.b_num[1]);
+  const int x = bx.b_lo[0] + lx, y = bx.b_lo[1] + ly, z = bx.b_lo[2] + lz;
+  float cur = 0.0f;
+  // a point is the block's own only where its position lies in the block's closed bounds (src/dense.cpp:523-531)
+  if (x >= bx.p_lo[0] && x <= bx.p_hi[0] && y >= bx.p_lo[1] && y <= bx.p_hi[1] && z >= bx.p_lo[2] && z <= bx.p_hi[2]) {
+    // the eight base cells whose window holds the point: base = point - (dx, dy, dz); the point is corner n = dz*4 + dy*2 + dx
+    unsigned int pos[8], end[8];
+    uint32_t head[8];                                  // the next particle id of every list (each list ascends: the sort is stable)
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      const int dx = n & 1, dy = (n >> 1) & 1, dz = n >> 2;
+      // box coordinates of the base cell (lx + 1 - dx is always inside [0, d))
+      const unsigned long long c = cb.cell0 + (unsigned long long)(((long long)(lz + 1 - dz) * cb.d[1] + (ly + 1 - dy)) * cb.d[0] + (lx + 1 - dx));
+      pos[n] = cell_start[c];
+      end[n] = pos[n] + cell_count[c];
+      head[n] = pos[n] < end[n] ? sorted_ids[pos[n]] : 0xffffffffu;
+    }
+    for (;;) {
+      uint32_t best = 0xffffffffu;
+      int bn = -1;
+#pragma unroll
+      for (int n = 0; n < 8; n++)
+        if (head[n] < best) { best = head[n]; bn = n; }
+      if (bn < 0) break;
+      const float m = vals[8 * (cb.part0 + (size_t)best) + bn];
+      cur = fadd(cur, fdiv(m, div));                       // src/dense.cpp:539
+#pragma unroll
+      for (int n = 0; n < 8; n++)
+        if (n == bn) {
+          pos[n]++;
+          head[n] = pos[n] < end[n] ? sorted_ids[pos[n]] : 0xffffffffu;
+        }
+    }
+  }
+  out[p] = cur;
+}
+
 // after the cell kernels of a group: what was appended so far is done
 __global__ void k_advance(Counters *cnt, uint32_t cap_small)
 {

@@ -34,8 +34,8 @@ print(json.dumps({"values": n, "differing": bad}))
 '''
 
 
-@pytest.mark.parametrize("env", [{"TESSB200_FUSED": "1"}, {"TESSB200_SEGMENTS": "1"}, {"TESSB200_DIRECT": "0"}, {"TESSB200_FUSED": "1", "TESSB200_SEGMENTS": "1"}],
-                         ids=["fused", "segments", "no_direct", "fused+segments"])
+@pytest.mark.parametrize("env", [{"TESSB200_FUSED": "1"}, {"TESSB200_SEGMENTS": "1"}, {"TESSB200_DIRECT": "0"}, {"TESSB200_FUSED": "1", "TESSB200_SEGMENTS": "1"}, {"TESSB200_CIC_GATHER": "0"}],
+                         ids=["fused", "segments", "no_direct", "fused+segments", "cic_records"])
 def test_optin_path_matches_oracle(env):
     r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT], capture_output=True, text=True, env=dict(os.environ, **env), timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
