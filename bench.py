@@ -686,16 +686,19 @@ def make_roofline(st, stage, steps, T, P, P0, G, S, dev_ms, peak, peak_src, alg,
     ms = {k: v / steps for k, v in stage.items()}
     n_shared = int(st.num_shared_deposits)
     if alg == 1:
-        stages = {"K4 k_cic (12 P0 + spans out)": (ms["ms_cells"] + ms["ms_scan"] + ms["ms_circumcenters"], 12 * P0 + 16 * S)}
+        # K4 (CIC) = 12 P + 4 G: particles in, grid out (weights, base cells, the particle sort and the few boundary
+        # records are intermediates)
+        stages = {"K4 cloud-in-cell: k_cic_prepare + particle sort + k_cic_gather + boundary records (12 P0 + 4 G)":
+                  (ms["ms_circumcenters"] + ms["ms_cells"] + ms["ms_scan"] + ms["ms_slow_path"] + ms["ms_sort"] + ms["ms_deposit"], 12 * P0 + 4 * G)}
     else:
         stages = {
             "K1 k_circumcenters + cell order (28 T + 12 P)": (ms["ms_circumcenters"], 28 * T + 12 * P),
             "K3a cell set-up + scan (44 T + 16 P + S)": (ms["ms_cells"] + ms["ms_scan"] + ms["ms_slow_path"], 44 * T + 16 * P + 16 * S),
         }
-    if n_shared >= 0:
-        stages["K3b deposit: count + place + ordered shared points (S + 4 G)"] = (ms["ms_sort"] + ms["ms_deposit"], 16 * S + 4 * G)
-    else:
-        stages["K3b deposit: sort + k_rows (S + 4 G)"] = (ms["ms_sort"] + ms["ms_deposit"], 16 * S + 4 * G)
+        if n_shared >= 0:
+            stages["K3b deposit: count + place + ordered shared points (S + 4 G)"] = (ms["ms_sort"] + ms["ms_deposit"], 16 * S + 4 * G)
+        else:
+            stages["K3b deposit: sort + k_rows (S + 4 G)"] = (ms["ms_sort"] + ms["ms_deposit"], 16 * S + 4 * G)
     stages["span exchange (NCCL)"] = (ms["ms_exchange"], 0)
     detail = {k: {"ms": v[0], "algorithmic_bytes": v[1], "algorithmic_GBps": (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None),
                   "frac_of_peak": (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None)} for k, v in stages.items()}
