@@ -606,6 +606,26 @@ def run_ours(args, rank, world, local_rank):
         ms = multi.max_over_ranks(ms / reps)
         other[names[alg]] = {"ms_per_step": ms, "grid_points_per_sec": G_total / (ms * 1e-3), "tot_mass": multi.sum_over_ranks(float(so.tot_mass)),
                              "max_dense": multi.max_over_ranks(float(so.max_dense))}
+    # the projected variant of the main estimator (`project` = 1 along z, the reference run scripts' default: TESS_DENSE_TEST,
+    # DENSE_TEST): every z of a column lands on one 2-D grid point, so every deposit is shared and the whole step's span records
+    # go through the ordered path (sort + k_rows).  Reported in box points/s of the same 3-D index box for comparison.
+    try:
+        pp = ctx.make_params(main_alg, ng, dmin, dmax, True, (0.0, 0.0, 1.0), 1.0, 1e-4, gsize)
+        for _ in range(2):
+            ctx.run(pp)
+        barrier()
+        ms = 0.0
+        for _ in range(3):
+            so = ctx.run(pp)
+            ms += so.ms_total_device
+        barrier()
+        ms = multi.max_over_ranks(ms / 3)
+        other[names[main_alg] + " projected along z"] = {
+            "ms_per_step": ms, "box_points_per_sec": G_total / (ms * 1e-3), "grid_points_2d": gsize[0] * gsize[1],
+            "tot_mass": multi.sum_over_ranks(float(so.tot_mass)), "ms_sort_and_rows": multi.max_over_ranks(float(so.ms_deposit)),
+            "max_dense": multi.max_over_ranks(float(so.max_dense))}
+    except Exception as e:      # an auxiliary line: its failure is reported in it and must not take the headline down
+        other[names[main_alg] + " projected along z"] = {"error": repr(e)}
     # ---- K2 (per-site Voronoi volume + zero-order density, volume() of src/volume.cpp:13-54) on this rank's
     # largest block: device time of the kernels (circumcenters + star walk + fan sums), 60 T + 24 P algorithmic bytes ----
     k2 = None

@@ -170,7 +170,7 @@ struct tessb200_ctx
   Buf fz_hdr, fz_bits, fz_pool;     // k_cell_fused -> k_cell_emit: headers, in-line inside bits, pool for the larger index boxes
   Buf hdr_dir[3];                   // cells of the small-box classes (k_cell_direct)
   Buf pt_off, pt_fill, big_points;  // shared grid points: segment offsets, fill cursors, the points with many deposits
-  Buf cic_vals, cic_keys[2], cic_ids[2], cic_count, cic_start;   // DENSE_CIC: weights, base cells and ids of the particles, particles per base cell
+  Buf cic_vals, cic_keys[2], cic_ids[2], cic_count, cic_start, cic_vals2;   // DENSE_CIC: weights, base cells and ids of the particles, particles per base cell
   bool cic_gather = true;           // TESSB200_CIC_GATHER=0: every CIC deposit as a record (round 1's k_cic)
   // span exchange: per (source, destination) capacities agreed in an exact round; later runs exchange fixed-size,
   // sentinel-padded segments and need no host read-back before the deposit
@@ -266,7 +266,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
                  &c->row_start, &c->out, &c->stat_sum, &c->stat_max, &c->recv_keys, &c->recv_data, &c->mkeys[0], &c->mkeys[1], &c->order[0], &c->order[1], &c->x_small, &c->pt_count,
                  &c->fz_hdr, &c->fz_bits, &c->fz_pool, &c->hdr_dir[0], &c->hdr_dir[1], &c->hdr_dir[2], &c->pt_off, &c->pt_fill, &c->big_points,
-                 &c->cic_vals, &c->cic_keys[0], &c->cic_keys[1], &c->cic_ids[0], &c->cic_ids[1], &c->cic_count, &c->cic_start};
+                 &c->cic_vals, &c->cic_keys[0], &c->cic_keys[1], &c->cic_ids[0], &c->cic_ids[1], &c->cic_count, &c->cic_start, &c->cic_vals2};
   for (Buf *b : bufs) b->release();
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
@@ -897,9 +897,11 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     if (gather) {
       TRY(c->cic_vals.ensure(32 * (size_t)cells));
       for (int i = 0; i < 2; i++) { TRY(c->cic_keys[i].ensure(4 * (size_t)cells)); TRY(c->cic_ids[i].ensure(4 * (size_t)cells)); }
-      TRY(c->cic_count.ensure(4 * (size_t)cic_cells));
-      TRY(c->cic_start.ensure(4 * (size_t)cic_cells));
-      CU(cudaMemsetAsync(c->cic_count.p, 0, 4 * (size_t)cic_cells, s));
+      // one entry past the last cell: the scan's last output is where the last list ends
+      TRY(c->cic_count.ensure(4 * ((size_t)cic_cells + 1)));
+      TRY(c->cic_start.ensure(4 * ((size_t)cic_cells + 1)));
+      CU(cudaMemsetAsync(c->cic_count.p, 0, 4 * ((size_t)cic_cells + 1), s));
+      TRY(c->cic_vals2.ensure(32 * (size_t)cells));
     }
   }
 
@@ -1028,14 +1030,14 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
         // small index boxes: one thread per cell, planes applied to the whole box as they are produced (no plane storage)
         const unsigned up = cdiv(gcells, DIRECT_THREADS);
         const bool exact = !io.pipelined;      // resident runs read the counters before the faces launch
-        const unsigned g2 = exact ? cdiv(c->h_cnt->n_dir[0], DIRECT_THREADS) : up, g3 = exact ? cdiv(c->h_cnt->n_dir[1], DIRECT_THREADS) : up,
-                       g4 = exact ? cdiv(c->h_cnt->n_dir[2], DIRECT_THREADS) : up;
+        const unsigned g2 = exact ? cdiv(c->h_cnt->n_dir[0].v, DIRECT_THREADS) : up, g3 = exact ? cdiv(c->h_cnt->n_dir[1].v, DIRECT_THREADS) : up,
+                       g4 = exact ? cdiv(c->h_cnt->n_dir[2].v, DIRECT_THREADS) : up;
         if (g2) k_cell_direct<2><<<g2, DIRECT_THREADS, 0, s>>>(to.dir[0], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
-                                                                       &cnt->dir_done[0], &cnt->n_dir[0], to.cap_dir, 0u);
+                                                                       &cnt->dir_done[0], &cnt->n_dir[0].v, to.cap_dir, 0u);
         if (g3) k_cell_direct<3><<<g3, DIRECT_THREADS, 0, s>>>(to.dir[1], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
-                                                                       &cnt->dir_done[1], &cnt->n_dir[1], to.cap_dir, 0u);
+                                                                       &cnt->dir_done[1], &cnt->n_dir[1].v, to.cap_dir, 0u);
         if (g4) k_cell_direct<4><<<g4, DIRECT_THREADS, 0, s>>>(to.dir[2], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so,
-                                                                       &cnt->dir_done[2], &cnt->n_dir[2], to.cap_dir, 0u);
+                                                                       &cnt->dir_done[2], &cnt->n_dir[2].v, to.cap_dir, 0u);
         COUNT_LAUNCH(c, (g2 ? 1 : 0) + (g3 ? 1 : 0) + (g4 ? 1 : 0));
       }
       if (timed) CU(cudaEventRecord(c->ev[17], s));
@@ -1090,7 +1092,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
                                                                                   nullptr, nullptr, 0);
     if (done_big) TRY(scan_big_list(so));
     if (to.cap_dir) {
-      const unsigned n2 = std::min(z.n_dir[0], to.cap_dir), n3 = std::min(z.n_dir[1], to.cap_dir), n4 = std::min(z.n_dir[2], to.cap_dir);
+      const unsigned n2 = std::min(z.n_dir[0].v, to.cap_dir), n3 = std::min(z.n_dir[1].v, to.cap_dir), n4 = std::min(z.n_dir[2].v, to.cap_dir);
       if (n2) k_cell_direct<2><<<cdiv(n2, DIRECT_THREADS), DIRECT_THREADS, 0, s>>>(to.dir[0], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so, nullptr, nullptr, 0u, n2);
       if (n3) k_cell_direct<3><<<cdiv(n3, DIRECT_THREADS), DIRECT_THREADS, 0, s>>>(to.dir[1], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so, nullptr, nullptr, 0u, n3);
       if (n4) k_cell_direct<4><<<cdiv(n4, DIRECT_THREADS), DIRECT_THREADS, 0, s>>>(to.dir[2], c->face_list.as<FaceRef>(), c->d_blocks.as<DevBlock>(), sc, G.g, so, nullptr, nullptr, 0u, n4);
@@ -1151,22 +1153,28 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     // sub-grids once), then the records that crossed block boundaries on top, in order (sort + k_rows, sparse form)
     {
       size_t tmp = 0;
-      CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->cic_count.as<unsigned int>(), c->cic_start.as<unsigned int>(), (int)cic_cells, s));
+      CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->cic_count.as<unsigned int>(), c->cic_start.as<unsigned int>(), cic_cells + 1, s));
       size_t tmp2 = 0;
       const int kbits = ceil_log2(cic_cells + 2);
       CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, c->cic_keys[0].as<uint32_t>(), c->cic_keys[1].as<uint32_t>(), c->cic_ids[0].as<uint32_t>(),
                                          c->cic_ids[1].as<uint32_t>(), (int)cells, 0, kbits, s));
       TRY(c->cub_tmp.ensure(std::max(tmp, tmp2)));
       tmp = tmp2 = c->cub_tmp.cap;
-      CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cic_count.as<unsigned int>(), c->cic_start.as<unsigned int>(), (int)cic_cells, s));
+      CU(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, c->cic_count.as<unsigned int>(), c->cic_start.as<unsigned int>(), cic_cells + 1, s));
       CU(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp2, c->cic_keys[0].as<uint32_t>(), c->cic_keys[1].as<uint32_t>(), c->cic_ids[0].as<uint32_t>(),
                                          c->cic_ids[1].as<uint32_t>(), (int)cells, 0, kbits, s));
     }
+    k_cic_permute<<<cdiv(cells, 256), 256, 0, s>>>(c->cic_ids[1].as<uint32_t>(), (unsigned long long)cells, c->cic_vals.as<float4>(), c->cic_vals2.as<float4>());
+    COUNT_LAUNCH(c, 1);
     for (int k = 0; k < nloc; k++) {
       BlockRes *b = c->blocks[k];
       if (!b->npts) continue;
-      k_cic_gather<<<cdiv(b->npts, 256), 256, 0, s>>>(cicb[k], G.boxes[first_local_all + k], c->cic_start.as<unsigned int>(), c->cic_count.as<unsigned int>(),
-                                                      c->cic_ids[1].as<uint32_t>(), c->cic_vals.as<float>(), G.g.div, c->out.as<float>() + b->out_off);
+      const BlockBox &gb = G.boxes[first_local_all + k];
+      const dim3 cgrid(cdiv(gb.b_num[0], CIC_TILE_X), cdiv(gb.b_num[1], CIC_TILE_Y), cdiv(gb.b_num[2], CIC_TILE_Z));
+      if (cgrid.y > 65535u || cgrid.z > 65535u)
+        return fail(TESSB200_EINVAL, "DENSE_CIC: a block's sub-grid exceeds 131070 points in y or z");
+      k_cic_gather<<<cgrid, CIC_THREADS, 0, s>>>(cicb[k], gb, c->cic_start.as<unsigned int>(), c->cic_ids[1].as<uint32_t>(), c->cic_vals2.as<float>(),
+                                                 c->out.as<float>() + b->out_off);
       COUNT_LAUNCH(c, 1);
     }
     CU(cudaGetLastError());
@@ -1235,7 +1243,7 @@ static int run_impl(tessb200_ctx *c, tessb200_dense_params *p, tessb200_dense_st
     const unsigned grid = cdiv((long long)n_spans, 256);
     k_span_count<<<grid, 256, 0, s>>>(c->keys[cur].as<uint64_t>(), c->data[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->d_rblocks.as<RowBlock>(),
                                       (int)G.rblocks.size(), c->pt_count.as<unsigned int>());
-    k_span_place<<<grid, 256, 0, s>>>(c->keys[cur].as<uint64_t>(), c->data[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->d_rblocks.as<RowBlock>(),
+    k_span_place<<<grid, SPAN_PLACE_THREADS, 0, s>>>(c->keys[cur].as<uint64_t>(), c->data[cur].as<uint64_t>(), n_spans, G.kl, G.row0, G.nrows, c->d_rblocks.as<RowBlock>(),
                                       (int)G.rblocks.size(), c->pt_count.as<unsigned int>(), G.g.div, c->out.as<float>(), c->keys[cur ^ 1].as<uint64_t>(),
                                       c->data[cur ^ 1].as<uint64_t>(), shared_cap, &cnt->n_shared);
     COUNT_LAUNCH(c, 2);

@@ -502,9 +502,40 @@ __global__ void __launch_bounds__(FZ_THREADS) k_cell_fused(const DevBlock *__res
 // ---- the scan-line walk + span emission of one cell per lane (phase 3 of k_cell_scan) -----------------------------------
 // h: this lane's header (any lane may be idle: in_sub == false); bits_w / lines_w: the warp's shared-memory slices;
 // row(j, k) / inside(i, j, k): the inside bits of the lane's cell.
-template <class Row, class Inside>
+// Where the span records of the lanes' cells go, and the two counts: per warp (the callers whose warps run on their own) ...
+struct WarpSpanAlloc
+{
+  __device__ __forceinline__ unsigned long long operator()(const SpanOut &out, int nrec, bool in_sub, bool fallback) const
+  {
+    const unsigned long long base = warp_alloc<unsigned long long>(&out.cnt->n_spans, (unsigned long long)nrec);
+    warp_count(&out.cnt->n_deposit, in_sub);
+    warp_count(&out.cnt->n_cic_fallback, fallback);
+    return base;
+  }
+};
+// ... or per CTA (k_cell_direct: every thread of the CTA arrives here together): three atomics per CTA instead of per warp
+template <int NW>
+struct CtaSpanAlloc
+{
+  unsigned long long *scratch;        // shared memory, NW + 3 entries
+  __device__ __forceinline__ unsigned long long operator()(const SpanOut &out, int nrec, bool in_sub, bool fallback) const
+  {
+    const unsigned nd = (unsigned)__popc(__ballot_sync(0xffffffffu, in_sub)), nf = (unsigned)__popc(__ballot_sync(0xffffffffu, fallback));
+    if (threadIdx.x == 0) { scratch[NW + 1] = 0ull; scratch[NW + 2] = 0ull; }
+    __syncthreads();
+    if (lane_id() == 0 && nd) atomicAdd(&scratch[NW + 1], (unsigned long long)nd);
+    if (lane_id() == 0 && nf) atomicAdd(&scratch[NW + 2], (unsigned long long)nf);
+    const unsigned long long base = cta_alloc<unsigned long long, NW>(&out.cnt->n_spans, (unsigned long long)nrec, scratch);   // (its barriers order the adds above)
+    if (threadIdx.x == 0 && scratch[NW + 1]) atomicAdd(&out.cnt->n_deposit, scratch[NW + 1]);
+    if (threadIdx.x == 0 && scratch[NW + 2]) atomicAdd(&out.cnt->n_cic_fallback, scratch[NW + 2]);
+    return base;
+  }
+};
+
+template <class Row, class Inside, class Alloc = WarpSpanAlloc>
 __device__ __forceinline__ void scan_emit_lane(const CellHdr &h, bool in_sub, Row row, Inside inside, uint32_t *lines_w, int lane,
-                                               const ScanCtx &sc, const GridGeom &g, const DevBlock *__restrict__ blocks, const SpanOut &out)
+                                               const ScanCtx &sc, const GridGeom &g, const DevBlock *__restrict__ blocks, const SpanOut &out,
+                                               Alloc alloc = Alloc())
 {
   const int e = (int)(h.blk_nf >> 16);
   int tot = 0, nrec = 0, nlines = 0;
@@ -553,9 +584,7 @@ __device__ __forceinline__ void scan_emit_lane(const CellHdr &h, bool in_sub, Ro
     }
   }
   __syncwarp();
-  unsigned long long base = warp_alloc<unsigned long long>(&out.cnt->n_spans, (unsigned long long)nrec);
-  warp_count(&out.cnt->n_deposit, in_sub);
-  warp_count(&out.cnt->n_cic_fallback, in_sub && tot == 0);
+  const unsigned long long base = alloc(out, nrec, in_sub, in_sub && tot == 0);
   if (in_sub) {
     StoreEmit se{out.keys, out.data, base, out.capacity};
     if (tot > 0) {
@@ -612,6 +641,7 @@ struct DirectSmem
   alignas(16) int warp_tot[DIRECT_THREADS / 32];     // own 16 bytes: the compiler reads the four totals with one 128-bit load
   uint32_t pos[DIRECT_THREADS][W], neg[DIRECT_THREADS][W];
   uint32_t lines[DIRECT_THREADS / 32][SCAN_LINE_CAP * 32];
+  unsigned long long alloc[DIRECT_THREADS / 32 + 3];  // CtaSpanAlloc's scratch
 };
 
 // One CTA = 128 cells of one class.  Step 2 runs one thread per FACE over all faces of the CTA's cells (the lanes of a
@@ -732,7 +762,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) k_cell_direct(const CellHdr *_
         if (k < (int)h.n3[2] && j < (int)h.n3[1]) vm |= rowm << ((k * M + j) * M);
   }
   const unsigned long long bits = ~(pos & neg) & vm;
-  scan_emit_lane(h, valid, RegRow<M>{bits}, RegInside<M>{bits}, S.lines[warp], lane, sc, g, blocks, out);
+  scan_emit_lane(h, valid, RegRow<M>{bits}, RegInside<M>{bits}, S.lines[warp], lane, sc, g, blocks, out, CtaSpanAlloc<DIRECT_THREADS / 32>{S.alloc});
 }
 
 constexpr int EMIT_WARPS = 8;

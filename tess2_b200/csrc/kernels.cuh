@@ -54,24 +54,31 @@ struct __align__(16) CellHdr
   uint32_t plane_off;      // offset into the plane pool in units of 2 faces (48 bytes)
 };
 
+// The counters every warp (or CTA) of a kernel adds to sit on 128-byte lines of their own: atomics on one line are served one
+// after the other by one L2 slice (measured: half a million adds on one address cost k_cic_prepare 1 ms of its 2), so
+// the hot ones neither share a line with each other nor with the marks the kernels read.
+struct alignas(128) HotU32 { unsigned int v; };
 struct Counters
 {
-  unsigned long long n_no_tet, n_incomplete, n_outside, n_bad, n_deposit, n_cic_fallback;
-  unsigned int n_small, n_big, n_overflow;     // list lengths
-  unsigned int plane_cursor;                   // units of 2 faces
+  unsigned long long n_no_tet, n_incomplete, n_outside, n_bad;
+  unsigned int n_big, n_overflow;              // list lengths (rare appends)
   unsigned long long big_bits;                 // bits needed by the big-cell list (multiples of 32)
-  unsigned long long n_spans;                  // span records requested (may exceed capacity)
-  unsigned long long n_cands;                  // candidate neighbours written by k_cell_bfs
   // progress marks kept on the device (k_advance): the cell kernels of a group work on what was
   // appended since the previous group, so the host never has to read a count between launches
   unsigned int pairs_done, small_done, ovf_done;
-  unsigned int pad0;
-  unsigned long long n_shared;                 // one-point records k_span_place handed to the sorted path
+  unsigned int dir_done[3];
   unsigned long long n_faces_fused;            // Voronoi faces (padded to pairs) of the cells k_cell_fused accepted
   unsigned long long pool_cursor;              // words of the inside-bit pool handed out by k_cell_fused
-  unsigned int n_dir[3], dir_done[3];          // cells of the three small-box classes handed to k_cell_direct (lengths, progress marks)
   unsigned int n_big_points;                   // grid points with more than POINT_SMALL deposits (k_point_apply -> k_point_apply_big)
   unsigned int dep_flags;                      // 1: the segment buffer was too small for the shared deposits (the run falls back to the sorted path)
+  alignas(128) unsigned long long n_deposit;
+  alignas(128) unsigned long long n_cic_fallback;
+  alignas(128) unsigned int n_small;           // list length
+  alignas(128) unsigned int plane_cursor;      // units of 2 faces
+  alignas(128) unsigned long long n_spans;     // span records requested (may exceed capacity)
+  alignas(128) unsigned long long n_cands;     // candidate neighbours written by k_cell_bfs
+  alignas(128) unsigned long long n_shared;    // one-point records k_span_place handed to the sorted path
+  HotU32 n_dir[3];                             // cells of the three small-box classes handed to k_cell_direct (list lengths)
 };
 
 struct FaceRef;
@@ -153,6 +160,37 @@ __device__ __forceinline__ void warp_count(unsigned long long *counter, bool pre
 {
   unsigned m = __ballot_sync(0xffffffffu, pred);
   if (m && (int)lane_id() == __ffs(m) - 1) atomicAdd(counter, (unsigned long long)__popc(m));
+}
+
+// ---- CTA helpers: one atomic per CTA and counter instead of one per warp -----------------------------------
+// Every thread of the CTA calls (NW warps, all converged, no early exits before); `scratch` holds NW + 1 entries of T in
+// shared memory and is free again on return.
+template <class T, int NW>
+__device__ __forceinline__ T cta_alloc(T *counter, T want, T *scratch)
+{
+  T incl = want;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((int)lane_id() >= d) incl += o;
+  }
+  const int w = (int)(threadIdx.x >> 5);
+  if (lane_id() == 31) scratch[w] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T tot = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+      const T t = scratch[i];
+      scratch[i] = tot;
+      tot += t;
+    }
+    scratch[NW] = tot ? atomicAdd(counter, tot) : (T)0;
+  }
+  __syncthreads();
+  const T base = scratch[NW] + scratch[w] + incl - want;
+  __syncthreads();
+  return base;
 }
 
 // ---- K0: vert_to_tet ("the last one wins" == highest tet index) ----------------------------------
@@ -382,7 +420,7 @@ __device__ __forceinline__ void bfs_finish(int status, int cell, int n_nbr, WS &
   if (out.cap_dir) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const uint32_t d_slot = warp_append<unsigned int>(&out.cnt->n_dir[c], cls == c);
+      const uint32_t d_slot = warp_append<unsigned int>(&out.cnt->n_dir[c].v, cls == c);
       if (cls == c && d_slot < out.cap_dir) out.dir[c][d_slot] = h;
     }
   }
@@ -510,9 +548,14 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_bfs(const DevBlock *__res
   warp_count(&out.cnt->n_incomplete, status == CELL_INCOMPLETE);
   warp_count(&out.cnt->n_outside, status == CELL_OUTSIDE);
   {
-    // candidates of accepted cells (for the roofline's algorithmic bytes)
+    // candidates of accepted cells (for the roofline's algorithmic bytes): one add per CTA
+    __shared__ unsigned int cta_cands;
+    if (threadIdx.x == 0) cta_cands = 0u;
+    __syncthreads();
     unsigned long long nc = warp_incl_scan_ull(status == CELL_OK ? (unsigned long long)(n_star + 2) : 0ull);
-    if (lane_id() == 31 && nc) atomicAdd(&out.cnt->n_cands, nc);
+    if (lane_id() == 31 && nc) atomicAdd(&cta_cands, (unsigned int)nc);
+    __syncthreads();
+    if (threadIdx.x == 0 && cta_cands) atomicAdd(&out.cnt->n_cands, (unsigned long long)cta_cands);
   }
   warp_count(&out.cnt->n_bad, status == CELL_BAD_MESH);
 }
@@ -567,19 +610,19 @@ __global__ void __launch_bounds__(TOPO_THREADS) k_cell_nbrs(const DevBlock *__re
   h.plane_off = poff;
   uint32_t s_slot = warp_append<unsigned int>(&out.cnt->n_small, small);
   if (small && s_slot < out.cap_small) out.small[s_slot] = h;
+  if (out.cap_dir) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint32_t d_slot = warp_append<unsigned int>(&out.cnt->n_dir[c].v, cls == c);
+      if (cls == c && d_slot < out.cap_dir) out.dir[c][d_slot] = h;
+    }
+  }
   uint32_t b_slot = warp_append<unsigned int>(&out.cnt->n_big, big);
   unsigned long long bits = big ? (unsigned long long)((npts + 31) & ~31LL) : 0ull;
   unsigned long long boff = warp_alloc<unsigned long long>(&out.cnt->big_bits, bits);
   if (big && b_slot < out.cap_big) {
     out.big[b_slot] = h;
     out.big_bit_off[b_slot] = boff;
-  }
-  if (out.cap_dir) {
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const uint32_t d_slot = warp_append<unsigned int>(&out.cnt->n_dir[c], cls == c);
-      if (cls == c && d_slot < out.cap_dir) out.dir[c][d_slot] = h;
-    }
   }
 }
 
@@ -1272,9 +1315,10 @@ __global__ void __launch_bounds__(256) k_cic_prepare(DevBlock blk, int blk_id, C
     int i0[3];
     float vals[8];
     cic_weights(site, g.mass, g, i0, vals);
+    // what the accumulate step adds is m / div (src/dense.cpp:539): one division per weight here instead of one per merge step
     float4 *vo = reinterpret_cast<float4 *>(vals_out + 8 * (cb.part0 + (size_t)cell));
-    vo[0] = make_float4(vals[0], vals[1], vals[2], vals[3]);
-    vo[1] = make_float4(vals[4], vals[5], vals[6], vals[7]);
+    vo[0] = make_float4(fdiv(vals[0], g.div), fdiv(vals[1], g.div), fdiv(vals[2], g.div), fdiv(vals[3], g.div));
+    vo[1] = make_float4(fdiv(vals[4], g.div), fdiv(vals[5], g.div), fdiv(vals[6], g.div), fdiv(vals[7], g.div));
     // base cell inside the block's box of base cells, or behind every cell (a particle none of whose corners is a point of
     // the block's own sub-grid)
     const long long bx = (long long)i0[0] - cb.o[0], by = (long long)i0[1] - cb.o[1], bz = (long long)i0[2] - cb.o[2];
@@ -1284,7 +1328,7 @@ __global__ void __launch_bounds__(256) k_cic_prepare(DevBlock blk, int blk_id, C
       atomicAdd(&cell_count[key], 1u);
     }
     keys[cb.part0 + (size_t)cell] = key;
-    ids[cb.part0 + (size_t)cell] = (uint32_t)cell;
+    ids[cb.part0 + (size_t)cell] = (uint32_t)(cb.part0 + (unsigned long long)cell);       // rank-wide: the position of the particle's weights
     // the whole window inside the block's own points and sub-grid (every interior particle): no record, no second look
     const BlockBox &bb = sc.boxes[blk_id];
     bool interior = true;
@@ -1302,7 +1346,8 @@ __global__ void __launch_bounds__(256) k_cic_prepare(DevBlock blk, int blk_id, C
     }
   }
   unsigned long long base = warp_alloc<unsigned long long>(&out.cnt->n_spans, (unsigned long long)nrec);
-  warp_count(&out.cnt->n_deposit, act);
+  // every particle of the block deposits: one add per launch instead of one per warp on the same address
+  if (blockIdx.x == 0 && threadIdx.x == 0 && blk.num_orig > 0) atomicAdd(&out.cnt->n_deposit, (unsigned long long)blk.num_orig);
   if (act && nrec) {
     StoreEmit se{out.keys, out.data, base, out.capacity};
     RemoteOnlyEmit<StoreEmit> re{se, sc.kl};
@@ -1310,47 +1355,71 @@ __global__ void __launch_bounds__(256) k_cic_prepare(DevBlock blk, int blk_id, C
   }
 }
 
-// one thread per grid point of the block's sub-grid
-__global__ void __launch_bounds__(256) k_cic_gather(CicBlock cb, BlockBox bx, const unsigned int *__restrict__ cell_start, const unsigned int *__restrict__ cell_count,
-                                                     const uint32_t *__restrict__ sorted_ids, const float *__restrict__ vals, float div, float *__restrict__ out)
+// the weights in sorted order: position q of the sorted ids gets the eight quotients of particle sorted_ids[q] (one
+// 32-byte sector in, one out).  The gather then walks a cell's list front to back, and the eight grid points around a
+// cell -- lanes of one warp, mostly -- read the same sectors: by particle id they were 8 P random sector reads
+// (config 3's input: 4.3 GB from DRAM per step for 0.54 GB of weights, the whole of the gather's time; ncu r02).
+__global__ void __launch_bounds__(256) k_cic_permute(const uint32_t *__restrict__ sorted_ids, unsigned long long n, const float4 *__restrict__ vals,
+                                                      float4 *__restrict__ vals_sorted)
 {
-  const long long npts = (long long)bx.b_num[0] * bx.b_num[1] * bx.b_num[2];
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npts) return;
-  const int lx = (int)(p % bx.b_num[0]);
-  const long long r = p / bx.b_num[0];
-  const int ly = (int)(r % bx.b_num[1]), lz = (int)(r / bx.b_num[1]);
+  const unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const size_t id = sorted_ids[q];
+  const float4 a = vals[2 * id], b = vals[2 * id + 1];
+  vals_sorted[2 * q] = a;
+  vals_sorted[2 * q + 1] = b;
+}
+
+// k_cic_gather, one thread per grid point of the block's sub-grid.  `cell_start` is the exclusive scan of the particles per
+// base cell over cic_cells + 1 entries (the list of cell c ends where that of c + 1 starts); `vals` holds the quotients
+// m / div (k_cic_prepare) in sorted order (k_cic_permute), so the merge loop is select -> load -> add.
+// Launch shape: a CTA of 4 warps covers 32 x 2 x 2 grid points, a warp a brick of 8 x 2 x 2 (x fastest): the lanes of a
+// warp wait for the longest merge among them, and the particle density of a compact brick varies less than that of 32
+// points in a row (clustered config 3: 2.4 instead of 3.1 times the work of a perfectly even split); the lanes of a brick
+// also share most of their base cells; a warp still writes whole 32-byte sectors.  3-D launch grid: no index divisions.
+// (Tried and dropped, both slower on config 3's input: the merge running eight steps ahead of the adds -- the padding of
+// the last group costs the many short lists more than the long ones gain; a first pass that compacts the grid points with
+// something to add into a work list -- the pass costs more than the idle lanes it removes.)
+constexpr int CIC_TILE_X = 32, CIC_TILE_Y = 2, CIC_TILE_Z = 2, CIC_THREADS = 128;
+__global__ void __launch_bounds__(CIC_THREADS) k_cic_gather(CicBlock cb, BlockBox bx, const unsigned int *__restrict__ cell_start,
+                                                             const uint32_t *__restrict__ sorted_ids, const float *__restrict__ vals, float *__restrict__ out)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lx = (int)blockIdx.x * CIC_TILE_X + warp * 8 + (lane & 7);
+  const int ly = (int)blockIdx.y * CIC_TILE_Y + ((lane >> 3) & 1);
+  const int lz = (int)blockIdx.z * CIC_TILE_Z + (lane >> 4);
+  if (lx >= bx.b_num[0] || ly >= bx.b_num[1] || lz >= bx.b_num[2]) return;
+  const long long p = ((long long)lz * bx.b_num[1] + ly) * bx.b_num[0] + lx;
   const int x = bx.b_lo[0] + lx, y = bx.b_lo[1] + ly, z = bx.b_lo[2] + lz;
   float cur = 0.0f;
   // a point is the block's own only where its position lies in the block's closed bounds (src/dense.cpp:523-531)
   if (x >= bx.p_lo[0] && x <= bx.p_hi[0] && y >= bx.p_lo[1] && y <= bx.p_hi[1] && z >= bx.p_lo[2] && z <= bx.p_hi[2]) {
-    // the eight base cells whose window holds the point: base = point - (dx, dy, dz); the point is corner n = dz*4 + dy*2 + dx
-    unsigned int pos[8], end[8];
-    uint32_t head[8];                                  // the next particle id of every list (each list ascends: the sort is stable)
+    // the eight base cells whose window holds the point: base = point - (dx, dy, dz); the point is corner n = dz*4 + dy*2 + dx.
+    // Box coordinates of a base cell: (lx + 1 - dx, ly + 1 - dy, lz + 1 - dz), always inside the box.  The cells of dx = 1
+    // and dx = 0 follow each other: three scan entries bound both lists.
+    const long long row = cb.d[0], slab = (long long)cb.d[0] * cb.d[1];
+    const unsigned int *cs11 = cell_start + (cb.cell0 + (unsigned long long)((long long)lz * slab + (long long)ly * row + lx));   // dy = dz = 1
+    CicLists l;
+    unsigned int total = 0;
 #pragma unroll
-    for (int n = 0; n < 8; n++) {
-      const int dx = n & 1, dy = (n >> 1) & 1, dz = n >> 2;
-      // box coordinates of the base cell (lx + 1 - dx is always inside [0, d))
-      const unsigned long long c = cb.cell0 + (unsigned long long)(((long long)(lz + 1 - dz) * cb.d[1] + (ly + 1 - dy)) * cb.d[0] + (lx + 1 - dx));
-      pos[n] = cell_start[c];
-      end[n] = pos[n] + cell_count[c];
-      head[n] = pos[n] < end[n] ? sorted_ids[pos[n]] : 0xffffffffu;
+    for (int h = 0; h < 4; h++) {
+      const int dy = h & 1, dz = h >> 1;
+      const unsigned int *cs = cs11 + (dy ? 0 : row) + (dz ? 0 : slab);
+      const unsigned int s0 = cs[0], s1 = cs[1], s2 = cs[2];
+      const int n1 = dz * 4 + dy * 2 + 1, n0 = dz * 4 + dy * 2;
+      l.pos[n1] = s0; l.end[n1] = s1;
+      l.pos[n0] = s1; l.end[n0] = s2;
+      total += s2 - s0;
     }
-    for (;;) {
-      uint32_t best = 0xffffffffu;
-      int bn = -1;
+    if (total) {
 #pragma unroll
-      for (int n = 0; n < 8; n++)
-        if (head[n] < best) { best = head[n]; bn = n; }
-      if (bn < 0) break;
-      const float m = vals[8 * (cb.part0 + (size_t)best) + bn];
-      cur = fadd(cur, fdiv(m, div));                       // src/dense.cpp:539
-#pragma unroll
-      for (int n = 0; n < 8; n++)
-        if (n == bn) {
-          pos[n]++;
-          head[n] = pos[n] < end[n] ? sorted_ids[pos[n]] : 0xffffffffu;
-        }
+      for (int n = 0; n < 8; n++) {
+        // (an empty list reads entry 0, which exists: the array holds every particle of the rank)
+        const bool some = l.pos[n] < l.end[n];
+        const uint32_t first = sorted_ids[some ? l.pos[n] : 0u];
+        l.head[n] = some ? first : 0xffffffffu;
+      }
+      cur = cic_merge_sum(l, total, sorted_ids, vals);
     }
   }
   out[p] = cur;
@@ -1362,7 +1431,7 @@ __global__ void k_advance(Counters *cnt, uint32_t cap_small)
   cnt->pairs_done = cnt->plane_cursor;
   cnt->small_done = cnt->n_small < cap_small ? cnt->n_small : cap_small;
   cnt->ovf_done = cnt->n_overflow;
-  for (int c = 0; c < 3; c++) cnt->dir_done[c] = cnt->n_dir[c];
+  for (int c = 0; c < 3; c++) cnt->dir_done[c] = cnt->n_dir[c].v;
 }
 
 // ---- K3b: deposit.  Spans sorted by (row, remote, cell, z); one warp owns one row -----------------
@@ -1513,7 +1582,8 @@ __global__ void k_span_count(const uint64_t *__restrict__ keys, const uint64_t *
   for (int x = x0; x < x1; x++) atomicAdd(&count[base + x], 1u);
 }
 
-__global__ void k_span_place(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ data, unsigned long long n, KeyLayout kl,
+constexpr int SPAN_PLACE_THREADS = 256;
+__global__ void __launch_bounds__(SPAN_PLACE_THREADS) k_span_place(const uint64_t *__restrict__ keys, const uint64_t *__restrict__ data, unsigned long long n, KeyLayout kl,
                              unsigned long long row0, unsigned long long nrows, const RowBlock *__restrict__ rblocks, int n_rblocks,
                              const unsigned int *__restrict__ count, float div, float *__restrict__ out, uint64_t *__restrict__ shared_keys,
                              uint64_t *__restrict__ shared_data, unsigned long long shared_cap, unsigned long long *n_shared)
@@ -1539,7 +1609,8 @@ __global__ void k_span_place(const uint64_t *__restrict__ keys, const uint64_t *
     }
   }
   // deposits on shared points: one-point records, same key (row, remote, cell, z) as the span they come from
-  const unsigned long long at = warp_alloc<unsigned long long>(n_shared, (unsigned long long)mine);
+  __shared__ unsigned long long cta_scratch[SPAN_PLACE_THREADS / 32 + 1];
+  const unsigned long long at = cta_alloc<unsigned long long, SPAN_PLACE_THREADS / 32>(n_shared, (unsigned long long)mine, cta_scratch);
   if (mine) {
     unsigned long long pos = at;
     for (int x = x0; x < x1; x++) {

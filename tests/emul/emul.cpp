@@ -544,3 +544,19 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
   ep->seconds = 0;
   return 0;
 }
+
+// k_cic_gather's sum at one grid point: the eight lists [pos[n], end[n]) of sorted_ids, weights vals[8 * id + n]
+extern "C" int emu_cic_point(const uint32_t *sorted_ids, const float *vals, const unsigned int *pos, const unsigned int *end, float *out)
+{
+  CicLists l;
+  unsigned int total = 0;
+  for (int n = 0; n < 8; n++) {
+    l.pos[n] = pos[n]; l.end[n] = end[n];
+    total += end[n] - pos[n];
+    l.head[n] = pos[n] < end[n] ? sorted_ids[pos[n]] : 0xffffffffu;
+  }
+  out[0] = cic_merge_sum(l, total, sorted_ids, vals);
+  // one step past the end must be the neutral element
+  out[1] = fadd(out[0], cic_merge_step(l, sorted_ids, vals));
+  return 0;
+}

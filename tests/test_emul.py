@@ -82,3 +82,39 @@ def test_fuzz_reference_port_device_logic(reference, port, emul):
     import fuzz_logic
     n, failures = fuzz_logic.run(seed=12345, cases=120, checkers=(reference, port, emul), log=lambda *a: None)
     assert n == 120 and not failures, failures[:3]
+
+
+def test_cic_gather_merge_adds_in_particle_order(emul):
+    """k_cic_gather's sum at a grid point (cic_merge_sum, cell_core.cuh): eight ascending id lists merged by id, float adds in
+    that order (src/dense.cpp:539) -- against a plain loop over the sorted ids; a step past the end of the lists yields -0.0f,
+    which must not change a bit (NaN and infinities included)."""
+    import ctypes
+    lib = emul.lib
+    rng = np.random.default_rng(31)
+    for case in range(300):
+        lens = rng.integers(0, [1, 3, 9, 40][case % 4] + 1, size=8)
+        if case % 7 == 0:
+            lens[rng.integers(0, 8)] = rng.integers(50, 400)
+        n_part = int(lens.sum()) + 5
+        ids = rng.permutation(n_part)[:int(lens.sum())].astype(np.uint32)
+        # the sorted array: some foreign entries in front, then list after list, each ascending
+        front = rng.integers(0, 4)
+        sorted_ids = np.concatenate([np.full(front, 0, np.uint32)] + [np.sort(ids[int(lens[:n].sum()):int(lens[:n + 1].sum())]) for n in range(8)] + [np.zeros(1, np.uint32)])
+        pos = (front + np.concatenate([[0], np.cumsum(lens)[:-1]])).astype(np.uint32)
+        end = (pos + lens).astype(np.uint32)
+        vals = (rng.random((n_part, 8), dtype=np.float32) * np.float32(10.0) ** rng.integers(-6, 6, size=(n_part, 8)).astype(np.float32)).astype(np.float32)
+        if case % 11 == 0 and n_part:
+            vals[rng.integers(0, n_part), :] = np.float32(np.inf) if case % 2 else np.float32(np.nan)
+        if case % 13 == 0:
+            vals[:] = 0.0
+        out = np.zeros(2, np.float32)
+        vals_sorted = np.ascontiguousarray(vals[sorted_ids])          # k_cic_permute: the weights in the order of the sorted ids
+        lib.emu_cic_point(sorted_ids.ctypes.data_as(ctypes.c_void_p), vals_sorted.ctypes.data_as(ctypes.c_void_p), pos.ctypes.data_as(ctypes.c_void_p),
+                          end.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p))
+        want = np.float32(0.0)
+        order = sorted((int(sorted_ids[q]), n) for n in range(8) for q in range(int(pos[n]), int(end[n])))
+        with np.errstate(all="ignore"):
+            for pid, n in order:
+                want = np.float32(want + vals[pid, n])
+        assert_same_bits(out[0:1], np.array([want], np.float32), f"case {case}")
+        assert_same_bits(out[1:2], np.array([want], np.float32), f"case {case} one step past the end")
