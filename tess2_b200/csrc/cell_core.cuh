@@ -902,10 +902,17 @@ TB_HD void cic_weights(const float *pt, float scalar, const GridGeom &g, int *id
 
 // ---- k_cic_gather's merge: the (at most) eight base cells around a grid point, each a list of particle ids in
 // ascending order, added in particle order (IterateCellsCic, src/dense.cpp:523-541) ----------------------------
+// The lists of one grid point: the heads live in registers (every step compares all eight); position and end of a list
+// are looked up by the index of the list that moves on -- plain arrays here (tests/emul), shared memory in k_cic_gather
+// (a register array indexed by a run-time value would turn into sixteen selects a step).
 struct CicLists
 {
-  unsigned int pos[8], end[8];
+  unsigned int pos_[8], end_[8];
   uint32_t head[8];                                  // the next particle id of every list, 0xffffffff at its end
+  TB_HD unsigned int pos(int n) const { return pos_[n]; }
+  TB_HD unsigned int end(int n) const { return end_[n]; }
+  TB_HD void set(int n, unsigned int p, unsigned int e) { pos_[n] = p; end_[n] = e; }
+  TB_HD void set_pos(int n, unsigned int p) { pos_[n] = p; }
 };
 
 TB_HD uint32_t tb_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -913,43 +920,43 @@ TB_HD uint32_t tb_minu(uint32_t a, uint32_t b) { return a < b ? a : b; }
 // one step: the weight of the next particle (corner n of the particle whose id heads list n); past the end -0.0f, which
 // `x + (-0.0f)` leaves as it is for every x.  `vals` is in SORTED order (eight weights per position of sorted_ids): the lists
 // of a cell are read front to back, and the eight grid points around a cell read the same 32-byte sectors.
-TB_HD float cic_merge_step(CicLists &l, const uint32_t *sorted_ids, const float *vals)
+template <class Lists>
+TB_HD float cic_merge_step(Lists &l, const uint32_t *sorted_ids, const float *vals)
 {
   // a particle has one base cell, so the ids of the eight heads are distinct: the smallest is the next particle
   const uint32_t b01 = tb_minu(l.head[0], l.head[1]), b23 = tb_minu(l.head[2], l.head[3]), b45 = tb_minu(l.head[4], l.head[5]),
                  b67 = tb_minu(l.head[6], l.head[7]);
   const uint32_t best = tb_minu(tb_minu(b01, b23), tb_minu(b45, b67));
-  const bool valid = best != 0xffffffffu;
+  if (best == 0xffffffffu) return -0.0f;
   bool e[8];
 #pragma unroll
-  for (int n = 0; n < 8; n++) e[n] = valid && l.head[n] == best;
+  for (int n = 0; n < 8; n++) e[n] = l.head[n] == best;
   const int bn = (int)(e[1] | e[3] | e[5] | e[7]) | ((int)(e[2] | e[3] | e[6] | e[7]) << 1) | ((int)(e[4] | e[5] | e[6] | e[7]) << 2);
-  // exactly one list moves on: its position and end by selects, ONE load of its next id, selects back (eight `if (e[n])`
-  // blocks with a load each compile to eight divergent branches per step: 120 instead of 60 warp instructions, ncu r02)
-  unsigned int ap = 0, ae = 0;
-#pragma unroll
-  for (int n = 0; n < 8; n++) {
-    ap = e[n] ? l.pos[n] : ap;
-    ae = e[n] ? l.end[n] : ae;
-  }
-  const float m = valid ? vals[8 * (size_t)ap + bn] : -0.0f;
+  // exactly one list moves on
+  unsigned int ap = l.pos(bn);
+  const unsigned int ae = l.end(bn);
+  const float m = vals[8 * (size_t)ap + bn];
   ap++;
-  const uint32_t nh = valid && ap < ae ? sorted_ids[ap] : 0xffffffffu;
+  l.set_pos(bn, ap);
+  const uint32_t nh = ap < ae ? sorted_ids[ap] : 0xffffffffu;
 #pragma unroll
-  for (int n = 0; n < 8; n++) {
-    l.pos[n] = e[n] ? ap : l.pos[n];
-    l.head[n] = e[n] ? nh : l.head[n];
-  }
+  for (int n = 0; n < 8; n++) l.head[n] = e[n] ? nh : l.head[n];
   return m;
 }
 
-TB_HD float cic_merge_sum(CicLists &l, unsigned int total, const uint32_t *sorted_ids, const float *vals)
+// the float adds in particle order (src/dense.cpp:539).  The add of a weight is issued one step after its load, so that the
+// chain of adds does not wait for the memory while the merge could go on.
+template <class Lists>
+TB_HD float cic_merge_sum(Lists &l, unsigned int total, const uint32_t *sorted_ids, const float *vals)
 {
-  float cur = 0.0f;
-  for (unsigned int done = 0; done < total; done++) cur = fadd(cur, cic_merge_step(l, sorted_ids, vals));   // src/dense.cpp:539
-  return cur;
+  float cur = 0.0f, m_prev = -0.0f;
+  for (unsigned int done = 0; done < total; done++) {
+    const float m = cic_merge_step(l, sorted_ids, vals);
+    cur = fadd(cur, m_prev);
+    m_prev = m;
+  }
+  return fadd(cur, m_prev);
 }
-
 
 // ---- DTFE, first order (alg 2; not in the reference) ------------------------------
 // determinant in tet.cpp:139-143's term order

@@ -1381,9 +1381,24 @@ __global__ void __launch_bounds__(256) k_cic_permute(const uint32_t *__restrict_
 // the last group costs the many short lists more than the long ones gain; a first pass that compacts the grid points with
 // something to add into a work list -- the pass costs more than the idle lanes it removes.)
 constexpr int CIC_TILE_X = 32, CIC_TILE_Y = 2, CIC_TILE_Z = 2, CIC_THREADS = 128;
+// position and end of the eight lists of every thread of the CTA: column threadIdx.x (no bank conflicts), row = list
+struct CicSmem
+{
+  unsigned int pos[8][CIC_THREADS], end[8][CIC_THREADS];
+};
+struct CicListsShared
+{
+  unsigned int *pos_, *end_;                         // this thread's column
+  uint32_t head[8];
+  __device__ __forceinline__ unsigned int pos(int n) const { return pos_[n * CIC_THREADS]; }
+  __device__ __forceinline__ unsigned int end(int n) const { return end_[n * CIC_THREADS]; }
+  __device__ __forceinline__ void set(int n, unsigned int p, unsigned int e) { pos_[n * CIC_THREADS] = p; end_[n * CIC_THREADS] = e; }
+  __device__ __forceinline__ void set_pos(int n, unsigned int p) { pos_[n * CIC_THREADS] = p; }
+};
 __global__ void __launch_bounds__(CIC_THREADS) k_cic_gather(CicBlock cb, BlockBox bx, const unsigned int *__restrict__ cell_start,
                                                              const uint32_t *__restrict__ sorted_ids, const float *__restrict__ vals, float *__restrict__ out)
 {
+  __shared__ CicSmem S;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = (int)blockIdx.x * CIC_TILE_X + warp * 8 + (lane & 7);
   const int ly = (int)blockIdx.y * CIC_TILE_Y + ((lane >> 3) & 1);
@@ -1399,25 +1414,27 @@ __global__ void __launch_bounds__(CIC_THREADS) k_cic_gather(CicBlock cb, BlockBo
     // and dx = 0 follow each other: three scan entries bound both lists.
     const long long row = cb.d[0], slab = (long long)cb.d[0] * cb.d[1];
     const unsigned int *cs11 = cell_start + (cb.cell0 + (unsigned long long)((long long)lz * slab + (long long)ly * row + lx));   // dy = dz = 1
-    CicLists l;
+    CicListsShared l{&S.pos[0][threadIdx.x], &S.end[0][threadIdx.x], {0, 0, 0, 0, 0, 0, 0, 0}};
     unsigned int total = 0;
+    unsigned int sv[4][3];
 #pragma unroll
     for (int h = 0; h < 4; h++) {
       const int dy = h & 1, dz = h >> 1;
       const unsigned int *cs = cs11 + (dy ? 0 : row) + (dz ? 0 : slab);
-      const unsigned int s0 = cs[0], s1 = cs[1], s2 = cs[2];
-      const int n1 = dz * 4 + dy * 2 + 1, n0 = dz * 4 + dy * 2;
-      l.pos[n1] = s0; l.end[n1] = s1;
-      l.pos[n0] = s1; l.end[n0] = s2;
-      total += s2 - s0;
+      sv[h][0] = cs[0]; sv[h][1] = cs[1]; sv[h][2] = cs[2];
+      total += sv[h][2] - sv[h][0];
     }
     if (total) {
 #pragma unroll
-      for (int n = 0; n < 8; n++) {
+      for (int h = 0; h < 4; h++) {
+        const unsigned int s0 = sv[h][0], s1 = sv[h][1], s2 = sv[h][2];
+        const int n1 = h * 2 + 1, n0 = h * 2;          // h = dz * 2 + dy
+        l.set(n1, s0, s1);
+        l.set(n0, s1, s2);
         // (an empty list reads entry 0, which exists: the array holds every particle of the rank)
-        const bool some = l.pos[n] < l.end[n];
-        const uint32_t first = sorted_ids[some ? l.pos[n] : 0u];
-        l.head[n] = some ? first : 0xffffffffu;
+        const uint32_t f1 = sorted_ids[s0 < s1 ? s0 : 0u], f0 = sorted_ids[s1 < s2 ? s1 : 0u];
+        l.head[n1] = s0 < s1 ? f1 : 0xffffffffu;
+        l.head[n0] = s1 < s2 ? f0 : 0xffffffffu;
       }
       cur = cic_merge_sum(l, total, sorted_ids, vals);
     }

@@ -551,7 +551,7 @@ extern "C" int emu_cic_point(const uint32_t *sorted_ids, const float *vals, cons
   CicLists l;
   unsigned int total = 0;
   for (int n = 0; n < 8; n++) {
-    l.pos[n] = pos[n]; l.end[n] = end[n];
+    l.set(n, pos[n], end[n]);
     total += end[n] - pos[n];
     l.head[n] = pos[n] < end[n] ? sorted_ids[pos[n]] : 0xffffffffu;
   }
