@@ -732,7 +732,7 @@ def make_roofline(st, stage, steps, T, P, P0, G, S, dev_ms, peak, peak_src, alg,
         traffic = json.load(open(tpath)).get(f"c{cfg}_{dom.split(' ')[0]}")
         if traffic is not None and n > 1:
             traffic = traffic / n
-    whole = 32 * T + 16 * P + 4 * G
+    whole = 12 * P0 + 4 * G if alg == 1 else 32 * T + 16 * P + 4 * G          # K4 reads the block's own particles only
     sub = {k: ms[k] for k in ms if ms[k] > 0}
     return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
             "peak_source": peak_src, "algorithmic_bytes": stages[dom][1], "kernel_ms": stages[dom][0],

@@ -18,22 +18,27 @@ def row(tag, d, base=None):
     e = d["e2e"]
     eff = f"{base / (ms * d['n_gpus']):.2f}" if base else "—"
     return (f"| {tag} | {d['n_gpus']} | {ms:.2f} | {d['value']:.3e} | {d['tets_per_sec']:.3e} | {eff} | {e['ms_per_step']:.1f} | {e['value']:.3e} | "
-            f"{d['roofline']['whole_stage']['frac'] * 100:.2f} % | {d['parity']['small_clone']['bit_identical']} | {d['parity']['mass_rel_err']:.1e} | "
+            f"{(d['roofline']['frac'] if 'CIC' in d['config'].get('alg', '') else d['roofline']['whole_stage']['frac']) * 100:.2f} % | {d['parity']['small_clone']['bit_identical']} | {d['parity']['mass_rel_err']:.1e} | "
             f"`{d['parity'].get('grid_sha256', '')[:12]}` |")
 
 
 out = ["# Round 2 — measured on B200 (driver-independent runs of `bench.py`, lines under `profiles/r02/`)", "",
        "Device-resident `value` = grid points / (max over ranks of the device time of `tessb200_dense_run`); `e2e` = the same through",
        "`tessb200_dense()` with pinned host buffers.  Clocks 1965 / 1965 MHz, no throttle reason in any line.  `frac` = SURVEY 8(d)'s",
-       "whole-stage bytes (32 T + 16 P + 4 G) over the device time, of the measured 6558 GB/s.", "",
+       "whole-stage bytes (32 T + 16 P + 4 G; DENSE_CIC: 12 P0 + 4 G) over the device time, of the measured 6558 GB/s.", "",
        "| config | GPUs | ms/step | grid points/s | tets/s | strong-scaling eff. | e2e ms | e2e grid points/s | frac of HBM | clone == oracle | mass rel. err | grid sha256 |",
        "|---|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|---|"]
-c3 = {n: load(f"bench_c3_n{n}.json") for n in (1, 2, 4, 8)}
+# config 3: 1 and 2 GPUs with the final library; 4 and 8 GPUs were measured one build earlier (before the per-CTA record allocation of
+# k_span_place: 52.45 ms on one GPU, bench_c3_n1_a.json) and are compared with that build's one-GPU line
+c3 = {1: load("bench_c3_n1.json"), 2: load("bench_c3_n2.json"), 4: load("bench_c3_n4.json"), 8: load("bench_c3_n8.json")}
+c3_prev1 = load("bench_c3_n1_a.json")
 base = c3[1]["ms_per_step"] if c3[1] else None
+base_prev = c3_prev1["ms_per_step"] if c3_prev1 else base
 for n in (1, 2, 4, 8):
     if c3[n]:
-        out.append(row("3: 256³ clustered, kd-tree 8 blocks → 512³", c3[n], base))
-for tag, name in (("4: 512³ clustered, kd-tree 64 blocks → 1024³", "bench_c4_n8.json"), ("5: config 3's input, DENSE_CIC", "bench_c5_n8.json"),
+        out.append(row("3: 256³ clustered, kd-tree 8 blocks → 512³" + (" (previous build)" if n > 2 else ""), c3[n], base if n <= 2 else base_prev))
+for tag, name in (("4: 512³ clustered, kd-tree 64 blocks → 1024³ (previous build)", "bench_c4_n8.json"), ("5: config 3's input, DENSE_CIC", "bench_c5_n1.json"),
+                  ("5: config 3's input, DENSE_CIC", "bench_c5_n2.json"), ("5: config 3's input, DENSE_CIC (gather before its last four steps, DESIGN 3.5)", "bench_c5_n8.json"),
                   ("2: 128³ uniform, 8 regular blocks → 256³", "bench_c2_n1.json")):
     d = load(name)
     if d:
@@ -60,6 +65,14 @@ if d:
             f"Device-resident / CPU = {d['value'] / cb['value']:.0f}×, end to end / CPU = {d['e2e']['value'] / cb['value']:.0f}×.",
             f"Host tess of the same input: {d['host_tess'].get('tess_seconds') or 0:.1f} s on {d['host_tess'].get('threads')} threads (tess + dense end to end: "
             f"{d['host_tess'].get('tess_plus_dense_seconds') or 0:.1f} s).", ""]
+if d:
+    out += ["## The other estimators on config 3's resident input (one GPU, `other_algs`)", ""]
+    for k, v in d.get("other_algs", {}).items():
+        out.append(f"* {k}: {v.get('ms_per_step', float('nan')):.2f} ms/step")
+    k2 = d["roofline"]["stages"].get("K2 k_cell_volumes on one block (60 T + 24 P), not part of dense()")
+    if k2:
+        out.append(f"* K2 (`tessb200_cell_volumes`, one block of {k2['tets']} tets): {k2['ms']:.2f} ms, {k2['algorithmic_GBps']:.0f} GB/s of 60 T + 24 P")
+    out.append("")
 d8 = c3[8]
 if d8:
     c = d8["e2e"]["pinned_h2d_ceiling"]

@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer over the whole dense path without Python: the `dense` driver on the prepared 8-block file
-# (make_expected.py), every case of cases.txt under memcheck, the first 3-D and the first projected case also under
+# (make_expected.py), every case of cases.txt under memcheck, the first 3-D case of each estimator and the first projected case also under
 # racecheck, initcheck and synccheck.  Usage on the GPU box: bash profiles/quick/sanitize.sh  (log: gpurun_out/sanitize.log)
 cd "$(dirname "$0")/_bin" || exit 1
 mkdir -p ../../../gpurun_out
@@ -18,7 +18,7 @@ run() {   # tool, case name, alg, driver tail
 while read -r name alg tail; do run memcheck $name $alg $tail; done < cases.txt
 for tool in racecheck initcheck synccheck; do
   while read -r name alg tail; do
-    case $name in a_3d_tess|d_proj_narrow_z) run $tool $name $alg $tail;; esac
+    case $name in a_3d_tess|b_3d_cic|d_proj_narrow_z) run $tool $name $alg $tail;; esac
   done < cases.txt
 done
 grep -c "^OK" $log | sed 's/^/passed: /'
