@@ -141,7 +141,9 @@ int tessb200_version(void);
 /* ---- the dense stage: replaces dense() (include/tess/dense.hpp:75-89) ----
  * One call = DataBounds + GridStepParams + init_dense + est_dense + exchange + recvd_pts for
  * the given blocks, host buffers in, host buffers out (per-block `density`, and the global
- * C-order grid `global_grid` [gz][gy][gx] (or [gy][gx]) when non-NULL and not projecting). */
+ * C-order grid `global_grid` [gz][gy][gx] when non-NULL and not projecting).  `global_grid` receives the sub-grids of
+ * THIS context's blocks only, each copied to its place: where no given block holds a grid point (blocks of other ranks,
+ * or a decomposition that does not tile the grid) the caller's array is left as it was -- zero it first if needed. */
 int tessb200_dense(tessb200_ctx *ctx, tessb200_dense_params *params, int nblocks, tessb200_block *blocks,
                    float *global_grid, tessb200_dense_stats *stats);
 
@@ -153,8 +155,9 @@ int tessb200_dense_download(tessb200_ctx *ctx, int nblocks, tessb200_block *bloc
 /* grid geometry of the uploaded blocks without running: fills params outputs and the blocks'
  * block_min_idx / block_num_idx / num_grid_pts (BlockGridParams, src/dense.cpp:575-648) */
 int tessb200_dense_geometry(tessb200_ctx *ctx, tessb200_dense_params *params, int nblocks, tessb200_block *blocks);
-/* device pointer of block i's density array after tessb200_dense_run (for zero-copy consumers) */
-int tessb200_dense_device_density(tessb200_ctx *ctx, int block, void **dptr, int64_t *num_floats);
+/* device pointer of the density array of the uploaded block with this gid after tessb200_dense_run (for zero-copy
+ * consumers); TESSB200_EINVAL when no uploaded block has that gid */
+int tessb200_dense_device_density(tessb200_ctx *ctx, int gid, void **dptr, int64_t *num_floats);
 
 /* ---- per-tet / per-site geometry: replaces src/volume.cpp and pieces of src/tet.cpp ---- */
 /* fill_vert_to_tet (src/tess.cpp:767-787) */

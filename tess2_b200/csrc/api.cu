@@ -151,8 +151,8 @@ struct tessb200_ctx
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t blk_ev[64];
-  cudaEvent_t grp_ev[64];   // end of each group's cell kernels (TESSB200_TRACE)
+  cudaEvent_t blk_ev[64] = {};
+  cudaEvent_t grp_ev[64] = {};   // end of each group's cell kernels (TESSB200_TRACE)
   cudaEvent_t part_ev = nullptr;
   std::vector<cudaEvent_t> tr_ev;          // TESSB200_TRACE: fine-grained marks inside the groups
   std::vector<const char *> tr_name;
@@ -186,7 +186,7 @@ struct tessb200_ctx
   Counters *h_cnt = nullptr;        // pinned
   double *h_sum = nullptr;
   float *h_max = nullptr;
-  cudaEvent_t ev[20];
+  cudaEvent_t ev[20] = {};
   bool ran = false;
   long long launches = 0;           // kernels launched by the current run
   tessb200_dense_params last_params;
@@ -197,10 +197,30 @@ struct tessb200_ctx
 extern "C" const char *tessb200_last_error(void) { return g_err.c_str(); }
 extern "C" int tessb200_version(void) { return TESSB200_VERSION; }
 
+static int create_impl(tessb200_ctx **out, int device);
+extern "C" void tessb200_destroy(tessb200_ctx *c);
+
 extern "C" int tessb200_create(tessb200_ctx **out, int device)
 {
   if (!out) return fail(TESSB200_EINVAL, "tessb200_create: ctx is NULL");
   *out = nullptr;
+  tessb200_ctx *c = nullptr;
+  const int rc = create_impl(&c, device);
+  if (rc) {
+    // a CUDA call failed half way: give back what was created (the message of the failure stays)
+    const std::string keep = g_err;
+    if (c) tessb200_destroy(c);
+    cudaGetLastError();
+    g_err = keep;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+// `*out` is set as soon as the context exists, so that the caller can free it when a later step fails
+static int create_impl(tessb200_ctx **out, int device)
+{
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -211,6 +231,7 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
   if (device < 0 || device >= n) return fail(TESSB200_EINVAL, "device %d out of range [0,%d)", device, n);
   CU(cudaSetDevice(device));
   tessb200_ctx *c = new tessb200_ctx;
+  *out = c;
   c->device = device;
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -243,7 +264,6 @@ extern "C" int tessb200_create(tessb200_ctx **out, int device)
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     c->fz_ctas = std::max(1, per_sm) * std::max(1, sms);
   }
-  *out = c;
   return 0;
 }
 
@@ -260,7 +280,7 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   free_blocks(c);
   Buf *bufs[] = {&c->d_blocks, &c->d_boxes, &c->d_rblocks, &c->d_cnt, &c->plane_pool, &c->face_list, &c->pre_hdr, &c->cand, &c->hdr_small, &c->hdr_big, &c->big_bitoff,
                  &c->overflow, &c->ws_big, &c->bits_big, &c->keys[0], &c->keys[1], &c->data[0], &c->data[1], &c->cub_tmp,
@@ -271,15 +291,17 @@ extern "C" void tessb200_destroy(tessb200_ctx *c)
 #ifdef TESSB200_WITH_NCCL
   if (c->comm && ncclw::g.h) ncclw::g.CommDestroy(c->comm);
 #endif
-  cudaFreeHost(c->h_cnt); cudaFreeHost(c->h_sum); cudaFreeHost(c->h_max);
+  if (c->h_cnt) cudaFreeHost(c->h_cnt);
+  if (c->h_sum) cudaFreeHost(c->h_sum);
+  if (c->h_max) cudaFreeHost(c->h_max);
   if (c->h_xall) cudaFreeHost(c->h_xall);
-  for (auto &ev : c->ev) cudaEventDestroy(ev);
-  for (auto &ev : c->blk_ev) cudaEventDestroy(ev);
-  for (auto &ev : c->grp_ev) cudaEventDestroy(ev);
+  for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->blk_ev) if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->grp_ev) if (ev) cudaEventDestroy(ev);
   if (c->part_ev) cudaEventDestroy(c->part_ev);
   for (auto &ev : c->h2d_ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(c->copy_stream);
-  cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
