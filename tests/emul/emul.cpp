@@ -1,11 +1,12 @@
 // CPU single-stepping of the __host__ __device__ logic in tess2_b200/csrc/cell_core.cuh and
 // host_geom.hpp -- TEST ONLY.  It exists because the development container has no GPU: the same
 // functions the kernels call (star walk, edge circulation, Newell normals, plane tests, the
-// scan-line state machine, CIC weights, span emission, the accumulate step) are driven here in
+// scan-line state machine, CIC weights and the per-grid-point gather of DENSE_CIC, span emission, the accumulate step) are driven here in
 // the kernels' order so that logic errors show up against the oracle before a GPU run.
 // This file is never linked into libtess_b200.so and is not a fallback: the product has none.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "../../tess2_b200/csrc/host_geom.hpp"
@@ -187,6 +188,18 @@ struct VecEmit
 {
   std::vector<Rec> *v;
   void operator()(uint64_t k, uint64_t d) { v->push_back(Rec{k, d}); }
+};
+
+// keeps the records of points outside the emitting block (key bit `remote`): RemoteOnlyEmit of kernels.cuh
+template <class Inner>
+struct RemoteOnly
+{
+  Inner &in;
+  KeyLayout kl;
+  void operator()(uint64_t k, uint64_t d)
+  {
+    if ((k >> (kl.z_bits + kl.cell_bits)) & 1ull) in(k, d);
+  }
 };
 
 struct BitsIn
@@ -412,6 +425,8 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
   }
   std::vector<Rec> recs;
   VecEmit emit{&recs};
+  std::vector<char> gathered(nblocks, 0);      // blocks whose own CIC deposits are already in their density (the gather)
+  const bool cic_gather = getenv("TESSB200_EMUL_CIC_RECORDS") == nullptr;
   Topo tp;
   for (int bi = 0; bi < nblocks; bi++) {
     emu_block_t &b = blocks[bi];
@@ -422,6 +437,68 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
       v2t_own.resize(b.num_particles);
       emu_fill_vert_to_tet(b.num_particles, b.num_tets, b.tets, v2t_own.data());
       v2t = v2t_own.data();
+    }
+    if (p.alg == TESSB200_DENSE_CIC && !g.project && cic_gather) {
+      // k_cic_prepare + stable sort by base cell + scan + k_cic_permute + k_cic_gather, in the kernels' terms: the block's own
+      // deposits are gathered per grid point (written into b.density here), only the records that leave the block are kept
+      const BlockBox &bx = boxes[bi];
+      const int o[3] = {bx.b_lo[0] - 1, bx.b_lo[1] - 1, bx.b_lo[2] - 1}, dd[3] = {bx.b_num[0] + 1, bx.b_num[1] + 1, bx.b_num[2] + 1};
+      const size_t ncell = (size_t)dd[0] * dd[1] * dd[2];
+      const int np = b.num_orig_particles;
+      std::vector<float> q8(8 * (size_t)np);
+      std::vector<uint32_t> key(np), ids(np);
+      std::vector<unsigned int> count(ncell + 1, 0u), start(ncell + 2, 0u);
+      RemoteOnly<VecEmit> remote{emit, kl};
+      for (int cell = 0; cell < np; cell++) {
+        int i0[3];
+        float vals[8];
+        cic_weights(&b.particles[3 * cell], g.mass, g, i0, vals);
+        for (int n = 0; n < 8; n++) q8[8 * (size_t)cell + n] = fdiv(vals[n], g.div);
+        const long long cx = (long long)i0[0] - o[0], cy = (long long)i0[1] - o[1], cz = (long long)i0[2] - o[2];
+        key[cell] = 0xffffffffu;
+        if (cx >= 0 && cx < dd[0] && cy >= 0 && cy < dd[1] && cz >= 0 && cz < dd[2]) {
+          key[cell] = (uint32_t)((cz * dd[1] + cy) * dd[0] + cx);
+          count[key[cell]]++;
+        }
+        ids[cell] = (uint32_t)cell;
+        int n = 0;
+        for (int dz = 0; dz < 2; dz++)
+          for (int dy = 0; dy < 2; dy++)
+            for (int dx = 0; dx < 2; dx++, n++)
+              emit_line(boxes.data(), nblocks, bi, kl, g.project, cell_base[bi] + cell, i0[0] + dx, i0[0] + dx, i0[1] + dy, i0[2] + dz, 1, vals[n], remote);
+      }
+      std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t c) { return key[a] < key[c]; });
+      for (size_t c = 0; c <= ncell; c++) start[c + 1] = start[c] + count[c];          // start[c] = exclusive scan, ncell + 1 entries used
+      std::vector<float> q8s(8 * (size_t)np);
+      for (int q = 0; q < np; q++) memcpy(&q8s[8 * (size_t)q], &q8[8 * (size_t)ids[q]], 32);
+      if (np == 0) { ids.push_back(0); q8s.resize(8); }
+      for (int lz = 0; lz < bx.b_num[2]; lz++)
+        for (int ly = 0; ly < bx.b_num[1]; ly++)
+          for (int lx = 0; lx < bx.b_num[0]; lx++) {
+            const int x = bx.b_lo[0] + lx, y = bx.b_lo[1] + ly, z = bx.b_lo[2] + lz;
+            float cur = 0.0f;
+            if (x >= bx.p_lo[0] && x <= bx.p_hi[0] && y >= bx.p_lo[1] && y <= bx.p_hi[1] && z >= bx.p_lo[2] && z <= bx.p_hi[2]) {
+              const long long row = dd[0], slab = (long long)dd[0] * dd[1];
+              const unsigned int *cs11 = start.data() + ((long long)lz * slab + (long long)ly * row + lx);
+              CicLists l;
+              unsigned int total = 0;
+              for (int h = 0; h < 4; h++) {
+                const int dy = h & 1, dz = h >> 1;
+                const unsigned int *cs = cs11 + (dy ? 0 : row) + (dz ? 0 : slab);
+                const unsigned int s0 = cs[0], s1 = cs[1], s2 = cs[2];
+                const int n1 = h * 2 + 1, n0 = h * 2;
+                l.set(n1, s0, s1);
+                l.set(n0, s1, s2);
+                l.head[n1] = s0 < s1 ? ids[s0] : 0xffffffffu;
+                l.head[n0] = s1 < s2 ? ids[s1] : 0xffffffffu;
+                total += s2 - s0;
+              }
+              if (total) cur = cic_merge_sum(l, total, ids.data(), q8s.data());
+            }
+            b.density[((size_t)lz * bx.b_num[1] + ly) * bx.b_num[0] + lx] = cur;
+          }
+      gathered[bi] = 1;
+      continue;
     }
     if (p.alg == TESSB200_DENSE_CIC) {
       for (int cell = 0; cell < b.num_orig_particles; cell++) {
@@ -525,7 +602,8 @@ extern "C" int emu_dense(emu_params_t *ep, int nblocks, emu_block_t *blocks, int
     }
   }
   std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.key < b.key; });
-  for (int i = 0; i < nblocks; i++) memset(blocks[i].density, 0, sizeof(float) * (size_t)blocks[i].num_grid_pts);
+  for (int i = 0; i < nblocks; i++)
+    if (!gathered[i]) memset(blocks[i].density, 0, sizeof(float) * (size_t)blocks[i].num_grid_pts);
   for (const Rec &r : recs) {
     long long row = (long long)key_row(kl, r.key);
     int bi = nblocks - 1;
