@@ -62,7 +62,10 @@ __attribute__((unused)) static int parse_grid_args(int argc, char **argv, int a,
 __attribute__((unused)) static tessb200_host_dblock *generate_and_tess(int tb, const int *dsize, int wrap, int walls, float minvol, float maxvol, double *seconds)
 {
   if (tb < 1 || dsize[0] < 2 || dsize[1] < 2 || dsize[2] < 2) { fprintf(stderr, "need tot_blocks >= 1 and a domain of at least 2 x 2 x 2\n"); exit(2); }
-  if (wrap || walls) { fprintf(stderr, "wrap / walls are not supported by the single-process host driver\n"); exit(2); }
+  /* walls: parsed by the reference drivers and read by nothing (examples/tess/main.cpp:46, examples/tess-dense/main.cpp:121; no
+   * wall_particles in src/): accepted and without effect here too.  wrap: periodic neighbours -- the images of particles shifted
+   * by whole domain extents become ghosts (tessb200_host_tess_periodic). */
+  if (walls) fprintf(stderr, "note: walls has no effect (the reference parses it and never reads it)\n");
   if (minvol > 0.0f || maxvol > 0.0f) fprintf(stderr, "note: minvol / maxvol do not act on the tets handed to dense(); ignored\n");
   const float dmin[3] = {0, 0, 0}, dmax[3] = {dsize[0] - 1.0f, dsize[1] - 1.0f, dsize[2] - 1.0f};
   float *bounds = (float *)malloc(sizeof(float) * 6 * (size_t)tb);
@@ -90,7 +93,7 @@ __attribute__((unused)) static tessb200_host_dblock *generate_and_tess(int tb, c
   }
   const double t0 = now_s();
   tessb200_host_block *hb = (tessb200_host_block *)calloc((size_t)tb, sizeof(*hb));
-  HCHECK(tessb200_host_tess((int)np, xyz, owner, dmin, dmax, tb, bounds, 0, NULL, 0.0f, 0, 0.0f, 0, hb));
+  HCHECK(tessb200_host_tess_periodic((int)np, xyz, owner, dmin, dmax, tb, bounds, 0, NULL, 0.0f, wrap ? 6 : 0, wrap ? 8.0f : 0.0f, 0, wrap ? 1 : 0, hb));
   if (seconds) *seconds = now_s() - t0;
   tessb200_host_dblock *db = (tessb200_host_dblock *)calloc((size_t)tb, sizeof(*db));
   long long ntets = 0, nghost = 0;

@@ -58,6 +58,13 @@ typedef struct tessb200_host_block {
 int tessb200_host_tess(int num_particles, const float *particles, const int *owner, const float *domain_min, const float *domain_max,
                        int nblocks, const float *block_bounds, int num_gids, const int *gids, float margin0, int max_rounds,
                        float max_growth, int num_threads, tessb200_host_block *blocks_out);
+/* the same with a periodic domain (wrap != 0: x, y and z, as the reference drivers set all three, examples/tess/main.cpp:83-88):
+ * a block's ghosts are also the images of particles -- its own included -- shifted by whole domain extents, with the
+ * coordinates of wrap_pt (src/tess.cpp:698-710); an image keeps the global id of its particle.  The margin then widens until
+ * no original is left on the hull and every circumsphere at an original cell fits (no clipping at the domain). */
+int tessb200_host_tess_periodic(int num_particles, const float *particles, const int *owner, const float *domain_min, const float *domain_max,
+                       int nblocks, const float *block_bounds, int num_gids, const int *gids, float margin0, int max_rounds,
+                       float max_growth, int num_threads, int wrap, tessb200_host_block *blocks_out);
 void tessb200_host_free_block(tessb200_host_block *b);
 
 /* Block decompositions (the reference delegates both to DIY: RegularDecomposer,

@@ -124,8 +124,18 @@ static void morton_order_tets(std::vector<int> &tets, const std::vector<float> &
   tets.swap(out);
 }
 
+// `wrap`: the domain is periodic in x, y and z (diy's wrap links, examples/tess/main.cpp:83-88): a block's ghosts are also the
+// images of particles -- its own included -- shifted by whole domain extents, with the coordinates of wrap_pt (src/tess.cpp:698-710:
+// float `x -= dir * (domain.max - domain.min)`).  An image keeps the id of its particle.  Code 13 = no shift.
+constexpr int NO_SHIFT = 13;
+inline void image_of(const float *q, int code, const float *ext, float *out)
+{
+  const int s[3] = {code % 3 - 1, (code / 3) % 3 - 1, code / 9 - 1};
+  for (int d = 0; d < 3; d++) out[d] = s[d] == 0 ? q[d] : q[d] - (float)s[d] * ext[d];
+}
+
 int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, const double *dmin, const double *dmax, double margin0,
-               int max_rounds, double max_growth, tessb200_host_block *out)
+               int max_rounds, double max_growth, bool wrap, const float *ext, tessb200_host_block *out)
 {
   const int n_orig = (int)job.mine.size();
   if (margin0 <= 0.0) {
@@ -135,6 +145,7 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
   double margin = margin0, prev_margin = -1.0;
   std::vector<float> P;
   std::vector<int> gids(job.mine.begin(), job.mine.end()), tets;
+  std::vector<signed char> shift(job.mine.size(), (signed char)NO_SHIFT);     // image of every entry of gids
   int rounds = 0;
   bool settled = false;
   double secs = 0.0;
@@ -142,19 +153,22 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
   for (;;) {
     rounds++;
     for (int i = 0; i < n; i++) {
-      if (owner[i] == job.gid) continue;
-      const float *q = pts + 3 * (size_t)i;
-      bool in = true, before = prev_margin >= 0.0;
-      for (int d = 0; d < 3; d++) {
-        in = in && (double)q[d] >= job.bmin[d] - margin && (double)q[d] <= job.bmax[d] + margin;
-        before = before && (double)q[d] >= job.bmin[d] - prev_margin && (double)q[d] <= job.bmax[d] + prev_margin;
+      for (int code = wrap ? 0 : NO_SHIFT; code <= (wrap ? 26 : NO_SHIFT); code++) {
+        if (code == NO_SHIFT && owner[i] == job.gid) continue;       // the original itself
+        float qi[3];
+        image_of(pts + 3 * (size_t)i, code, ext, qi);
+        bool in = true, before = prev_margin >= 0.0;
+        for (int d = 0; d < 3; d++) {
+          in = in && (double)qi[d] >= job.bmin[d] - margin && (double)qi[d] <= job.bmax[d] + margin;
+          before = before && (double)qi[d] >= job.bmin[d] - prev_margin && (double)qi[d] <= job.bmax[d] + prev_margin;
+        }
+        if (in && !before) { gids.push_back(i); shift.push_back((signed char)code); }
       }
-      if (in && !before) gids.push_back(i);
     }
     const int np = (int)gids.size();
     const size_t had = P.size() / 3;
     P.resize(3 * (size_t)np);
-    for (size_t i = had; i < (size_t)np; i++) memcpy(&P[3 * i], pts + 3 * (size_t)gids[i], 12);
+    for (size_t i = had; i < (size_t)np; i++) image_of(pts + 3 * (size_t)gids[i], shift[i], ext, &P[3 * i]);
     const auto t0 = std::chrono::steady_clock::now();
     tets.clear();
     if (dt.add(P.data(), np)) dt.export_tets(tets);
@@ -162,7 +176,7 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     const size_t nt = tets.size() / 8;
     bool covered = true;
     for (int d = 0; d < 3; d++) covered = covered && job.bmin[d] - margin <= dmin[d] && job.bmax[d] + margin >= dmax[d];
-    if (covered) { settled = true; break; }
+    if (covered && !wrap) { settled = true; break; }     // (a periodic domain has no outside: its images always lie beyond)
     // originals on the local hull have unbounded cells; fine next to the domain boundary, a sign of too
     // few ghosts anywhere else
     std::vector<char> on_hull(np, 0);
@@ -175,7 +189,7 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
       if (!on_hull[i]) continue;
       double dist = INFINITY;
       for (int d = 0; d < 3; d++) dist = std::min(dist, std::min((double)P[3 * (size_t)i + d] - dmin[d], dmax[d] - (double)P[3 * (size_t)i + d]));
-      if (dist > margin) grow = true;
+      if (dist > margin || wrap) grow = true;            // periodic: no original may stay on the hull
     }
     // circumspheres of the tets at original, finite cells must stay inside the searched region
     // (clipped at the domain: nothing lives beyond it)
@@ -190,10 +204,10 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
       // belongs to is dropped by dense() (src/dense.cpp:1385-1392), so it cannot unsettle the block (`settled`); it
       // still drives the widening as before (flat tets at the domain boundary have spheres that reach far sideways)
       bool inside = true;
-      for (int d = 0; d < 3; d++) inside = inside && s.c[d] >= dmin[d] && s.c[d] <= dmax[d];
+      for (int d = 0; d < 3; d++) inside = inside && (wrap || (s.c[d] >= dmin[d] && s.c[d] <= dmax[d]));
       for (int d = 0; d < 3; d++) {
         const double lo_need = job.bmin[d] - (s.c[d] - s.r), hi_need = (s.c[d] + s.r) - job.bmax[d];
-        const double r_lo = std::min(lo_need, job.bmin[d] - dmin[d]), r_hi = std::min(hi_need, dmax[d] - job.bmax[d]);
+        const double r_lo = wrap ? lo_need : std::min(lo_need, job.bmin[d] - dmin[d]), r_hi = wrap ? hi_need : std::min(hi_need, dmax[d] - job.bmax[d]);
         req = std::max(req, std::max(r_lo, r_hi));
         if (inside) req_in = std::max(req_in, std::max(r_lo, r_hi));
       }
@@ -212,7 +226,7 @@ int tess_block(const float *pts, int n, const int *owner, const BlockJob &job, c
     // ghosts in input order whatever round brought them in (the layout of a single-round run)
     std::vector<int> ord(np), pos(np);
     for (int i = 0; i < np; i++) ord[i] = i;
-    std::sort(ord.begin() + n_orig, ord.end(), [&](int a, int b) { return gids[a] < gids[b]; });
+    std::sort(ord.begin() + n_orig, ord.end(), [&](int a, int b) { return gids[a] != gids[b] ? gids[a] < gids[b] : shift[a] < shift[b]; });
     std::vector<float> P2(P.size());
     std::vector<int> g2(np);
     for (int i = 0; i < np; i++) {
@@ -256,8 +270,17 @@ extern "C" int tessb200_host_tess(int num_particles, const float *particles, con
                                   int nblocks, const float *block_bounds, int num_gids, const int *gids, float margin0, int max_rounds,
                                   float max_growth, int num_threads, tessb200_host_block *blocks_out)
 {
+  return tessb200_host_tess_periodic(num_particles, particles, owner, domain_min, domain_max, nblocks, block_bounds, num_gids, gids, margin0, max_rounds,
+                                     max_growth, num_threads, 0, blocks_out);
+}
+
+extern "C" int tessb200_host_tess_periodic(int num_particles, const float *particles, const int *owner, const float *domain_min, const float *domain_max,
+                                           int nblocks, const float *block_bounds, int num_gids, const int *gids, float margin0, int max_rounds,
+                                           float max_growth, int num_threads, int wrap, tessb200_host_block *blocks_out)
+{
   if (!particles || !domain_min || !domain_max || !block_bounds || !blocks_out || nblocks < 1 || num_particles < 0) { g_err = "bad argument"; return -1; }
   const double dmin[3] = {domain_min[0], domain_min[1], domain_min[2]}, dmax[3] = {domain_max[0], domain_max[1], domain_max[2]};
+  const float ext[3] = {domain_max[0] - domain_min[0], domain_max[1] - domain_min[1], domain_max[2] - domain_min[2]};      // float, as wrap_pt has it
   std::vector<BlockJob> jobs(nblocks);
   for (int b = 0; b < nblocks; b++) {
     jobs[b].gid = b;
@@ -306,7 +329,7 @@ extern "C" int tessb200_host_tess(int num_particles, const float *particles, con
       const int b = next.fetch_add(1);
       if (b >= ntodo) return;
       try {
-        const int r = tess_block(particles, num_particles, owner, jobs[todo[b]], dmin, dmax, margin0, max_rounds, max_growth, &blocks_out[b]);
+        const int r = tess_block(particles, num_particles, owner, jobs[todo[b]], dmin, dmax, margin0, max_rounds, max_growth, wrap != 0, ext, &blocks_out[b]);
         if (r) { rc = r; errs[tid] = "out of memory"; }
       } catch (const std::exception &e) {
         rc = -3;

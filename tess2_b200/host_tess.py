@@ -36,7 +36,7 @@ class HostDBlock(C.Structure):
 
 BOUNDS_DYNAMIC, BOUNDS_STATIC4 = 0, 1
 
-EXPORTS = ["tessb200_host_delaunay", "tessb200_host_tess", "tessb200_host_free_block", "tessb200_host_free", "tessb200_host_last_error",
+EXPORTS = ["tessb200_host_delaunay", "tessb200_host_tess", "tessb200_host_tess_periodic", "tessb200_host_free_block", "tessb200_host_free", "tessb200_host_last_error",
            "tessb200_host_regular_blocks", "tessb200_host_kdtree_blocks",
            "tessb200_host_write_blocks", "tessb200_host_read_blocks", "tessb200_host_free_dblocks"]
 
@@ -52,6 +52,9 @@ def load():
         lib.tessb200_host_tess.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                            C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_int, C.c_float,
                                            C.c_int, C.POINTER(HostBlock)]
+        lib.tessb200_host_tess_periodic.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                                    C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_float, C.c_int, C.c_float,
+                                                    C.c_int, C.c_int, C.POINTER(HostBlock)]
         lib.tessb200_host_free_block.argtypes = [C.POINTER(HostBlock)]
         lib.tessb200_host_regular_blocks.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float)]
         lib.tessb200_host_kdtree_blocks.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
@@ -83,11 +86,12 @@ def delaunay(points):
     return out
 
 
-def tess(points, owner, bounds, domain_min, domain_max, margin0=0.0, threads=0, gids=None, max_rounds=3, max_growth=2.5):
+def tess(points, owner, bounds, domain_min, domain_max, margin0=0.0, threads=0, gids=None, max_rounds=3, max_growth=2.5, wrap=False):
     """Blocks of one process.  bounds: list of (min[3], max[3]) indexed by gid; owner: gid per
     particle or None (containment); gids: the blocks to tessellate (default all).  Returns the list
     of block dicts used throughout the package (gid, particles, num_orig, tets, vert_to_tet,
-    bounds_min, bounds_max, margin, rounds, global_ids)."""
+    bounds_min, bounds_max, margin, rounds, global_ids).  wrap: periodic domain (the reference drivers' `wrap` argument): ghosts
+    include the images of particles shifted by whole domain extents; an image keeps its particle's global id."""
     lib = load()
     p = np.ascontiguousarray(points, dtype=np.float32)
     nb = len(bounds)
@@ -97,9 +101,9 @@ def tess(points, owner, bounds, domain_min, domain_max, margin0=0.0, threads=0, 
     own = None if owner is None else np.ascontiguousarray(owner, dtype=np.int32)
     g = None if gids is None else np.ascontiguousarray(gids, dtype=np.int32)
     arr = (HostBlock * (nb if g is None else len(g)))()
-    rc = lib.tessb200_host_tess(len(p), _fp(p), own.ctypes.data_as(C.POINTER(C.c_int)) if own is not None else None, _fp(dmin), _fp(dmax),
-                                nb, _fp(bb), 0 if g is None else len(g), g.ctypes.data_as(C.POINTER(C.c_int)) if g is not None else None,
-                                float(margin0), int(max_rounds), float(max_growth), int(threads), arr)
+    rc = lib.tessb200_host_tess_periodic(len(p), _fp(p), own.ctypes.data_as(C.POINTER(C.c_int)) if own is not None else None, _fp(dmin), _fp(dmax),
+                                         nb, _fp(bb), 0 if g is None else len(g), g.ctypes.data_as(C.POINTER(C.c_int)) if g is not None else None,
+                                         float(margin0), int(max_rounds), float(max_growth), int(threads), 1 if wrap else 0, arr)
     if rc:
         raise RuntimeError(lib.tessb200_host_last_error().decode())
     out = []

@@ -9,6 +9,7 @@ import pytest
 
 from tess2_b200 import host_tess
 from tess2_b200.harness import particles, decomp, delaunay
+from conftest import assert_same_bits
 
 
 def tet_set(tets):
@@ -213,3 +214,58 @@ def test_settled_flag_reports_an_unsatisfied_ghost_region():
     # a single block that holds the whole domain needs no ghosts and is settled at once
     one = host_tess.tess(p, None, host_tess.regular_blocks(*dom, 1), *dom, margin0=0.05, max_rounds=1)
     assert one[0]["settled"] and one[0]["rounds"] == 1
+
+
+@pytest.mark.parametrize("nblocks", [1, 8])
+def test_periodic_domain_matches_the_delaunay_of_all_images(nblocks, port, reference):
+    """`wrap` of the reference drivers (examples/tess/main.cpp:83-88; wrap_pt, src/tess.cpp:698-710): the ghosts of a block include
+    the images of particles -- its own too -- shifted by whole domain extents.  Oracle: SciPy-Qhull over all 27 images of the
+    particle set; every tet at an original particle of a block must be a tet of that triangulation and the other way round, no
+    original stays on a block's hull, an image keeps its particle's id and sits at the particle's position minus the shift.
+    The dense stage then runs on such blocks as on any others: port and unmodified reference agree bit for bit, and every cell of
+    the periodic set is complete."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(3)
+    dmin, dmax = np.zeros(3, np.float32), np.array([10.0, 8.0, 12.0], np.float32)
+    ext = (dmax - dmin).astype(np.float32)
+    p = (rng.random((500, 3)) * ext * 0.98 + dmin + 0.01 * ext).astype(np.float32)
+    bounds = host_tess.regular_blocks(dmin, dmax, nblocks)
+    blocks = host_tess.tess(p, None, bounds, dmin, dmax, wrap=True, max_rounds=6, max_growth=8.0)
+    imgs = []
+    for sz in (-1, 0, 1):
+        for sy in (-1, 0, 1):
+            for sx in (-1, 0, 1):
+                q = p.copy()
+                for d, s in enumerate((sx, sy, sz)):
+                    if s:
+                        q[:, d] = (q[:, d] - np.float32(s) * ext[d]).astype(np.float32)
+                imgs.append(q)
+    allp = np.concatenate(imgs).astype(np.float32)
+    known = set(map(tuple, allp.tolist()))
+    tri = Delaunay(allp.astype(np.float64), qhull_options="Qt")
+
+    def key(pts):
+        return tuple(sorted(map(tuple, pts.tolist())))
+
+    for b in blocks:
+        assert b["settled"]
+        no = b["num_orig"]
+        assert np.array_equal(b["particles"][:no], p[b["global_ids"][:no]])
+        ghosts, gid = b["particles"][no:], b["global_ids"][no:]
+        assert all(tuple(g) in known for g in ghosts.tolist())
+        shift = (p[gid] - ghosts) / ext                      # whole extents (0 for a ghost that is no image)
+        assert np.allclose(shift, np.round(shift), atol=1e-5) and np.abs(np.round(shift)).max() <= 1
+        own = set(map(tuple, b["particles"][:no].tolist()))
+        mine = set(key(b["particles"][t[:4]]) for t in b["tets"] if (t[:4] < no).any())
+        want = set(key(allp[s]) for s in tri.simplices if any(tuple(x) in own for x in allp[s].tolist()))
+        assert mine == want
+        hull = b["tets"][(b["tets"][:, 4:] < 0).any(axis=1)]
+        for t in hull:
+            for k in range(4):
+                if t[4 + k] < 0:
+                    assert all(t[j] >= no for j in range(4) if j != k), "an original on the hull of a periodic block"
+    o1 = port.dense(blocks, (24, 24, 24))
+    o2 = reference.dense(blocks, (24, 24, 24))
+    for a, c in zip(o1["block_density"], o2["block_density"]):
+        assert_same_bits(a, c, "periodic blocks: port vs reference")
+    assert all(port.complete(b["num_orig"], b["tets"], b["vert_to_tet"]).all() for b in blocks)

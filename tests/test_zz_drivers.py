@@ -52,13 +52,33 @@ def test_tess_driver_writes_the_blocks(drivers, tmp_path):
     assert r.returncode == 0 and sorted(os.listdir(tmp_path)) == ["del.out"]
 
 
+def test_tess_driver_wrap_and_walls(drivers, tmp_path):
+    # wrap = 1: periodic neighbours (images of particles as ghosts): every cell of every block is complete, where the open domain
+    # leaves the cells at its boundary unbounded; walls = 1 is parsed and read by nothing in the reference: accepted, no effect
+    from tess2_b200.harness import delaunay
+    from oracle import ref
+    port = ref.Checker("port")
+    out = {}
+    for wrap, walls in ((0, 0), (1, 0), (0, 1)):
+        f = tmp_path / f"del_{wrap}{walls}.out"
+        r = subprocess.run([str(drivers / "tess"), "8", "-1", "10", "10", "10", "0", "-1", "-1", str(wrap), str(walls), str(f)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out[(wrap, walls)] = host_tess.read_blocks(str(f))[0]
+    for a, b in zip(out[(0, 0)], out[(0, 1)]):
+        for k in ("particles", "tets", "vert_to_tet"):
+            assert_same_bits(np.asarray(a[k]), b[k], "walls changes nothing: " + k)
+    done_open = sum(int(port.complete(b["num_orig"], b["tets"], b["vert_to_tet"]).sum()) for b in out[(0, 0)])
+    done_wrap = sum(int(port.complete(b["num_orig"], b["tets"], b["vert_to_tet"]).sum()) for b in out[(1, 0)])
+    total = sum(b["num_orig"] for b in out[(1, 0)])
+    assert done_wrap == total and done_open < total
+    for b in out[(1, 0)]:
+        assert np.array_equal(b["vert_to_tet"], delaunay.fill_vert_to_tet(len(b["particles"]), b["tets"]))
+
+
 def test_driver_argument_errors(drivers, tmp_path):
     assert subprocess.run([str(drivers / "tess"), "8"], capture_output=True).returncode == 2
     assert subprocess.run([str(drivers / "dense"), "a", "b", "0", "8", "8"], capture_output=True).returncode == 2
     assert subprocess.run([str(drivers / "tess-dense"), "0", "8", "8", "8", "8"], capture_output=True).returncode == 2
-    # wrap is DIY's periodic neighbour exchange: not in the single-process host driver
-    r = subprocess.run([str(drivers / "tess"), "8", "-1", "8", "8", "8", "0", "-1", "-1", "1", "0", "!"], capture_output=True, text=True)
-    assert r.returncode == 2 and "wrap" in r.stderr
     # an unreadable block file
     r = subprocess.run([str(drivers / "dense"), str(tmp_path / "none.out"), "x.raw", "0", "8", "8", "8", "!", "1", "0"], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stderr
