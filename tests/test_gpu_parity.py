@@ -185,6 +185,22 @@ def test_dense_on_native_tess_blocks(ctx, port):
         compare_dense(run_gpu(ctx, blocks, (40, 40, 40), alg=alg), port.dense(blocks, (40, 40, 40), alg=alg), f"native tess alg {alg}")
 
 
+def test_dense_on_periodic_blocks(ctx, port):
+    # wrap = 1 of the reference drivers: ghosts include the images of particles beyond the domain (tessb200_host_tess_periodic);
+    # every cell is complete, and the cells that reach across the domain boundary are the ones dense() drops by its data-bounds test
+    from tess2_b200 import host_tess
+    from tess2_b200.harness import particles
+    dom = (np.zeros(3, np.float32), np.full(3, 15, np.float32))
+    p = particles.uniform_particles(16 ** 3, *dom, seed=21)
+    bounds = host_tess.regular_blocks(*dom, 8)
+    blocks = host_tess.tess(p, None, bounds, *dom, wrap=True, max_rounds=6, max_growth=8.0)
+    assert all(b["settled"] for b in blocks)
+    for alg in (0, 1):
+        for proj in (False, True):
+            compare_dense(run_gpu(ctx, blocks, (32, 32, 32), alg=alg, project=proj), port.dense(blocks, (32, 32, 32), alg=alg, project=proj),
+                          f"periodic blocks alg {alg} proj {proj}")
+
+
 @pytest.mark.parametrize("kd", [0, 1])
 def test_c_example_end_to_end(ctx, port, tmp_path, kd):
     # examples/tess_dense.c: particles -> decomposition -> tess -> dense -> raw file through the two C ABIs only
