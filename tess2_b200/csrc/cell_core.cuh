@@ -944,18 +944,26 @@ TB_HD float cic_merge_step(Lists &l, const uint32_t *sorted_ids, const float *va
   return m;
 }
 
-// the float adds in particle order (src/dense.cpp:539).  The add of a weight is issued one step after its load, so that the
-// chain of adds does not wait for the memory while the merge could go on.
+// the float adds in particle order (src/dense.cpp:539).  The add of a weight is issued CIC_ADD_DELAY steps after its load, so
+// that the chain of adds does not wait for the memory while the merge could go on (the pending weights start as -0.0f, the
+// neutral element).
+constexpr int CIC_ADD_DELAY = 3;
 template <class Lists>
 TB_HD float cic_merge_sum(Lists &l, unsigned int total, const uint32_t *sorted_ids, const float *vals)
 {
-  float cur = 0.0f, m_prev = -0.0f;
+  float cur = 0.0f, pend[CIC_ADD_DELAY];
+#pragma unroll
+  for (int i = 0; i < CIC_ADD_DELAY; i++) pend[i] = -0.0f;
   for (unsigned int done = 0; done < total; done++) {
     const float m = cic_merge_step(l, sorted_ids, vals);
-    cur = fadd(cur, m_prev);
-    m_prev = m;
+    cur = fadd(cur, pend[0]);
+#pragma unroll
+    for (int i = 0; i + 1 < CIC_ADD_DELAY; i++) pend[i] = pend[i + 1];
+    pend[CIC_ADD_DELAY - 1] = m;
   }
-  return fadd(cur, m_prev);
+#pragma unroll
+  for (int i = 0; i < CIC_ADD_DELAY; i++) cur = fadd(cur, pend[i]);
+  return cur;
 }
 
 // ---- DTFE, first order (alg 2; not in the reference) ------------------------------
