@@ -10,7 +10,7 @@ and projected, eps 1e-6..1e-2, 0-3 given bounds wider or narrower than the data.
 child: the reference has no bounds checks, and where a deposit falls outside its block's sub-grid (counted by
 the port: `out_of_range`) the reference's result is undefined and only port == device logic is asked for.
 Round 1: 74 000 cases over 11 seeds (5 x 300 s, 6 x 1200 s), no difference; it found the projection-with-narrow-z case (test_emul.py).
-Round 2: the emulation runs DENSE_CIC in the gather form of k_cic_prepare / k_cic_gather (3-D): seeds 777 (240 s) and 4242 (1200 s), 15 778 cases, no difference."""
+Round 2: the emulation runs DENSE_CIC in the gather form of k_cic_prepare / k_cic_gather (3-D): seeds 777 (240 s), 4242 (1200 s) and, with the final merge loop, 99 (300 s): 18 905 cases, no difference."""
 import os
 import sys
 import time
