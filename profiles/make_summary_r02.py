@@ -43,6 +43,10 @@ for tag, name in (("4: 512³ clustered, kd-tree 64 blocks → 1024³ (previous b
     d = load(name)
     if d:
         out.append(row(tag, d))
+dl = load("bench_c5_n1_delay3.json")
+if dl:
+    out += ["", f"Config 5 on one GPU with the library as committed last (`k_cic_gather`'s adds three steps behind their loads; a 5-step run, "
+            f"`bench_c5_n1_delay3.json`): {dl['ms_per_step']:.2f} ms/step, grid sha256 `{dl['parity'].get('grid_sha256', '')[:12]}`."]
 out += ["", "The digest of config 3 is the same at 1, 2, 4 and 8 GPUs: the NCCL span exchange reproduces the single-GPU bits.", ""]
 d = c3[1]
 if d:
